@@ -1,0 +1,700 @@
+// runner.cpp — drives c2d::Registry<uint32_t, Method> through its public API.
+// TEST INFRASTRUCTURE (see runner_api.h).  Compiled unchanged against
+//   (a) the reference headers  (-DRN_BACKEND_REF)   -> oracle/_ref/
+//   (b) this repo's headers    (-DRN_BACKEND_B200)  -> colli2de_b200/
+// Everything below the "free functions" marker is backend specific only in
+// how a batch of (shape, transform) pairs is evaluated: the reference calls
+// c2d::collide & co. directly, the B200 build forwards the batch to the
+// C-ABI (c2d_gpu_*_batch), i.e. to the CUDA narrowphase.
+#include "runner_api.h"
+
+#include <colli2de/Registry.hpp>
+
+#include <array>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#if defined(RN_BACKEND_B200)
+#include <c2d_gpu.h>
+#endif
+
+using namespace c2d;
+
+namespace
+{
+
+struct PairRec
+{
+    uint32_t entityA, entityB, shapeA, shapeB;
+    float manifold[17]; // normal(2) + 2 x (point, anchorA, anchorB, separation) + pointCount byte
+};
+static_assert(sizeof(PairRec) == 84);
+
+struct HitRec
+{
+    uint32_t entity, shape;
+    float entry[2], exit[2], entryTime, exitTime;
+};
+static_assert(sizeof(HitRec) == 32);
+
+Transform makeRawTransform(const float* xf5)
+{
+    Transform t{};
+    t.translation = Vec2{xf5[0], xf5[1]};
+    t.rotation.angleRadians = xf5[2];
+    t.rotation.sin = xf5[3];
+    t.rotation.cos = xf5[4];
+    return t;
+}
+
+void storeRawTransform(const Transform& t, float* xf5)
+{
+    xf5[0] = t.translation.x;
+    xf5[1] = t.translation.y;
+    xf5[2] = t.rotation.angleRadians;
+    xf5[3] = t.rotation.sin;
+    xf5[4] = t.rotation.cos;
+}
+
+Circle makeCircle(const float* g)
+{
+    return Circle{Vec2{g[0], g[1]}, g[2]};
+}
+Capsule makeCapsule(const float* g)
+{
+    return Capsule{Vec2{g[0], g[1]}, Vec2{g[2], g[3]}, g[4]};
+}
+Segment makeSegment(const float* g)
+{
+    return Segment{Vec2{g[0], g[1]}, Vec2{g[2], g[3]}};
+}
+Polygon makePoly(const float* g, uint8_t count)
+{
+    std::array<Vec2, MAX_POLYGON_VERTICES> verts{};
+    for (uint8_t i = 0; i < count; ++i)
+        verts[i] = Vec2{g[2 * i], g[2 * i + 1]};
+    return Polygon(verts, count);
+}
+
+ShapeVariant makeShape(uint8_t type, const float* g, uint8_t count)
+{
+    switch (type)
+    {
+    case 0:
+        return makeCircle(g);
+    case 1:
+        return makeCapsule(g);
+    case 2:
+        return makeSegment(g);
+    default:
+        return makePoly(g, count);
+    }
+}
+
+void storeManifold(const Manifold& m, void* out68)
+{
+    static_assert(sizeof(Manifold) == 68);
+    std::memcpy(out68, &m, 68);
+}
+
+struct IRegistry
+{
+    virtual ~IRegistry() = default;
+    virtual void createEntity(uint32_t id, BodyType type, const Transform& t) = 0;
+    virtual void removeEntity(uint32_t id) = 0;
+    virtual ShapeId addShape(uint32_t e, const ShapeVariant& s, uint64_t cat, uint64_t mask) = 0;
+    virtual void removeShape(ShapeId s) = 0;
+    virtual void setShapeActive(ShapeId s, bool a) = 0;
+    virtual void teleportEntity(uint32_t id, const Transform& t) = 0;
+    virtual void teleportEntity(uint32_t id, Translation t) = 0;
+    virtual void moveEntity(uint32_t id, const Transform& d) = 0;
+    virtual void moveEntity(uint32_t id, Translation d) = 0;
+    virtual Transform getEntityTransform(uint32_t id) const = 0;
+    virtual void getCollidingPairs(std::vector<PairRec>& out, double* seconds) = 0;
+    virtual void rayCast(Ray r, uint64_t mask, std::vector<HitRec>& out) const = 0;
+    virtual void rayCast(InfiniteRay r, uint64_t mask, std::vector<HitRec>& out) const = 0;
+    virtual size_t size() const = 0;
+    virtual void clear() = 0;
+};
+
+template <PartitioningMethod Method>
+struct RegistryHolder final : IRegistry
+{
+    using Reg = Registry<uint32_t, Method>;
+    Reg reg;
+
+    RegistryHolder() requires(Method == PartitioningMethod::None) = default;
+    explicit RegistryHolder(uint32_t cell) requires(Method == PartitioningMethod::Grid) : reg(cell) {}
+
+    void createEntity(uint32_t id, BodyType type, const Transform& t) override
+    {
+        reg.createEntity(id, type, t);
+    }
+    void removeEntity(uint32_t id) override
+    {
+        reg.removeEntity(id);
+    }
+    ShapeId addShape(uint32_t e, const ShapeVariant& s, uint64_t cat, uint64_t mask) override
+    {
+        return std::visit([&](const auto& concrete) { return reg.addShape(e, concrete, cat, mask); }, s);
+    }
+    void removeShape(ShapeId s) override
+    {
+        reg.removeShape(s);
+    }
+    void setShapeActive(ShapeId s, bool a) override
+    {
+        reg.setShapeActive(s, a);
+    }
+    void teleportEntity(uint32_t id, const Transform& t) override
+    {
+        reg.teleportEntity(id, t);
+    }
+    void teleportEntity(uint32_t id, Translation t) override
+    {
+        reg.teleportEntity(id, t);
+    }
+    void moveEntity(uint32_t id, const Transform& d) override
+    {
+        reg.moveEntity(id, d);
+    }
+    void moveEntity(uint32_t id, Translation d) override
+    {
+        reg.moveEntity(id, d);
+    }
+    Transform getEntityTransform(uint32_t id) const override
+    {
+        return reg.getEntityTransform(id);
+    }
+    void getCollidingPairs(std::vector<PairRec>& out, double* seconds) override
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        auto pairs = reg.getCollidingPairs();
+        const auto t1 = std::chrono::steady_clock::now();
+        if (seconds)
+            *seconds = std::chrono::duration<double>(t1 - t0).count();
+        static_assert(sizeof(typename Reg::EntityCollision) == sizeof(PairRec));
+        out.resize(pairs.size());
+        if (!pairs.empty())
+            std::memcpy(out.data(), pairs.data(), pairs.size() * sizeof(PairRec));
+    }
+    template <typename RayT>
+    void rayCastImpl(RayT r, uint64_t mask, std::vector<HitRec>& out) const
+    {
+        const auto hits = reg.rayCast(r, mask);
+        for (const auto& h : hits)
+            out.push_back(HitRec{
+                h.id.first, h.id.second, {h.entry.x, h.entry.y}, {h.exit.x, h.exit.y}, h.entryTime, h.exitTime});
+    }
+    void rayCast(Ray r, uint64_t mask, std::vector<HitRec>& out) const override
+    {
+        rayCastImpl(r, mask, out);
+    }
+    void rayCast(InfiniteRay r, uint64_t mask, std::vector<HitRec>& out) const override
+    {
+        rayCastImpl(r, mask, out);
+    }
+    size_t size() const override
+    {
+        return reg.size();
+    }
+    void clear() override
+    {
+        reg.clear();
+    }
+};
+
+} // namespace
+
+struct rn_ctx
+{
+    std::unique_ptr<IRegistry> reg;
+    std::unordered_map<uint32_t, uint8_t> body;
+    std::unordered_map<uint32_t, Transform> prev; // bullets only (mirrors Registry.hpp:167 by observation)
+    std::vector<PairRec> pairs;
+    std::vector<HitRec> hits;
+    std::string error;
+
+    void notePrev(uint32_t id)
+    {
+        auto it = body.find(id);
+        if (it != body.end() && it->second == 2)
+            prev[id] = reg->getEntityTransform(id);
+    }
+};
+
+#define RN_TRY(ctx) try {
+#define RN_CATCH(ctx)                                                                                                  \
+    }                                                                                                                  \
+    catch (const std::exception& e)                                                                                    \
+    {                                                                                                                  \
+        (ctx)->error = e.what();                                                                                       \
+    }
+
+extern "C" {
+
+const char* rn_backend_name(void)
+{
+#if defined(RN_BACKEND_REF)
+    return "reference";
+#elif defined(RN_BACKEND_B200)
+    return "b200";
+#else
+    return "unknown";
+#endif
+}
+
+rn_ctx* rn_create(int method, uint32_t cell_size)
+{
+    auto* ctx = new rn_ctx();
+    try
+    {
+        if (method == 1)
+            ctx->reg = std::make_unique<RegistryHolder<PartitioningMethod::Grid>>(cell_size ? cell_size : 120u);
+        else
+            ctx->reg = std::make_unique<RegistryHolder<PartitioningMethod::None>>();
+    }
+    catch (const std::exception& e)
+    {
+        ctx->error = e.what();
+    }
+    return ctx;
+}
+
+void rn_destroy(rn_ctx* ctx)
+{
+    delete ctx;
+}
+
+const char* rn_last_error(rn_ctx* ctx)
+{
+    return ctx->error.c_str();
+}
+
+void rn_create_entities(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const uint8_t* body, const float* xf3)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const Transform t(Vec2{xf3[3 * i], xf3[3 * i + 1]}, xf3[3 * i + 2]);
+        ctx->reg->createEntity(ids[i], static_cast<BodyType>(body[i]), t);
+        ctx->body[ids[i]] = body[i];
+        if (body[i] == 2)
+            ctx->prev[ids[i]] = t;
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_create_entities_raw(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const uint8_t* body, const float* xf5)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const Transform t = makeRawTransform(xf5 + 5 * i);
+        ctx->reg->createEntity(ids[i], static_cast<BodyType>(body[i]), t);
+        ctx->body[ids[i]] = body[i];
+        if (body[i] == 2)
+            ctx->prev[ids[i]] = t;
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_add_shapes(rn_ctx* ctx, uint32_t n, const uint32_t* entity, const uint8_t* type, const float* geom16,
+                   const uint8_t* vcount, const uint64_t* cat, const uint64_t* mask, uint32_t* out_ids)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const ShapeVariant s = makeShape(type[i], geom16 + 16 * i, vcount[i]);
+        const ShapeId id = ctx->reg->addShape(entity[i], s, cat ? cat[i] : 1ull, mask ? mask[i] : ~0ull);
+        if (out_ids)
+            out_ids[i] = id;
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_remove_shapes(rn_ctx* ctx, uint32_t n, const uint32_t* shape_ids)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+        ctx->reg->removeShape(shape_ids[i]);
+    RN_CATCH(ctx)
+}
+
+void rn_remove_entities(rn_ctx* ctx, uint32_t n, const uint32_t* ids)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ctx->reg->removeEntity(ids[i]);
+        ctx->body.erase(ids[i]);
+        ctx->prev.erase(ids[i]);
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_set_active(rn_ctx* ctx, uint32_t n, const uint32_t* shape_ids, const uint8_t* active)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+        ctx->reg->setShapeActive(shape_ids[i], active[i] != 0);
+    RN_CATCH(ctx)
+}
+
+void rn_move_translate(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const float* dxy)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ctx->notePrev(ids[i]);
+        ctx->reg->moveEntity(ids[i], Translation{dxy[2 * i], dxy[2 * i + 1]});
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_move_transform(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const float* d)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ctx->notePrev(ids[i]);
+        ctx->reg->moveEntity(ids[i], Transform(Vec2{d[3 * i], d[3 * i + 1]}, d[3 * i + 2]));
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_teleport_transform(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const float* xf3)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ctx->notePrev(ids[i]);
+        ctx->reg->teleportEntity(ids[i], Transform(Vec2{xf3[3 * i], xf3[3 * i + 1]}, xf3[3 * i + 2]));
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_teleport_translation(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const float* xy)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ctx->notePrev(ids[i]);
+        ctx->reg->teleportEntity(ids[i], Translation{xy[2 * i], xy[2 * i + 1]});
+    }
+    RN_CATCH(ctx)
+}
+
+void rn_get_transforms(rn_ctx* ctx, uint32_t n, const uint32_t* ids, float* out)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+        storeRawTransform(ctx->reg->getEntityTransform(ids[i]), out + 5 * i);
+    RN_CATCH(ctx)
+}
+
+void rn_get_prev_transforms(rn_ctx* ctx, uint32_t n, const uint32_t* ids, float* out)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        auto it = ctx->prev.find(ids[i]);
+        if (it != ctx->prev.end())
+            storeRawTransform(it->second, out + 5 * i);
+        else
+            storeRawTransform(ctx->reg->getEntityTransform(ids[i]), out + 5 * i);
+    }
+    RN_CATCH(ctx)
+}
+
+uint64_t rn_size(rn_ctx* ctx)
+{
+    return ctx->reg->size();
+}
+
+void rn_clear(rn_ctx* ctx)
+{
+    RN_TRY(ctx)
+    ctx->reg->clear();
+    ctx->body.clear();
+    ctx->prev.clear();
+    RN_CATCH(ctx)
+}
+
+uint64_t rn_get_colliding_pairs(rn_ctx* ctx, double* seconds)
+{
+    RN_TRY(ctx)
+    ctx->reg->getCollidingPairs(ctx->pairs, seconds);
+    return ctx->pairs.size();
+    RN_CATCH(ctx)
+    return 0;
+}
+
+void rn_copy_pairs(rn_ctx* ctx, void* out84)
+{
+    if (!ctx->pairs.empty())
+        std::memcpy(out84, ctx->pairs.data(), ctx->pairs.size() * sizeof(PairRec));
+}
+
+uint64_t rn_raycast(rn_ctx* ctx, uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
+                    uint64_t* offsets, double* seconds)
+{
+    RN_TRY(ctx)
+    ctx->hits.clear();
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        offsets[i] = ctx->hits.size();
+        const float* r = ray4 + 4 * i;
+        const uint64_t mask = masks ? masks[i] : ~0ull;
+        if (infinite && infinite[i])
+            ctx->reg->rayCast(InfiniteRay{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}}, mask, ctx->hits);
+        else
+            ctx->reg->rayCast(Ray{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}}, mask, ctx->hits);
+    }
+    offsets[n] = ctx->hits.size();
+    const auto t1 = std::chrono::steady_clock::now();
+    if (seconds)
+        *seconds = std::chrono::duration<double>(t1 - t0).count();
+    return ctx->hits.size();
+    RN_CATCH(ctx)
+    return 0;
+}
+
+void rn_copy_hits(rn_ctx* ctx, void* out32)
+{
+    if (!ctx->hits.empty())
+        std::memcpy(out32, ctx->hits.data(), ctx->hits.size() * sizeof(HitRec));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// free functions
+// ---------------------------------------------------------------------------------------------------
+#if defined(RN_BACKEND_REF)
+
+void rn_collide(uint32_t n, const uint8_t* typeA, const float* geomA, const uint8_t* cntA, const float* xfA5,
+                const uint8_t* typeB, const float* geomB, const uint8_t* cntB, const float* xfB5,
+                void* out_manifold68, uint8_t* out_are_colliding)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const ShapeVariant a = makeShape(typeA[i], geomA + 16 * i, cntA[i]);
+        const ShapeVariant b = makeShape(typeB[i], geomB + 16 * i, cntB[i]);
+        const Transform ta = makeRawTransform(xfA5 + 5 * i);
+        const Transform tb = makeRawTransform(xfB5 + 5 * i);
+        std::visit(
+            [&](const auto& sa, const auto& sb)
+            {
+                if (out_manifold68)
+                    storeManifold(c2d::collide(sa, ta, sb, tb), static_cast<char*>(out_manifold68) + 68 * i);
+                if (out_are_colliding)
+                    out_are_colliding[i] = c2d::areColliding(sa, ta, sb, tb) ? 1 : 0;
+            },
+            a,
+            b);
+    }
+}
+
+void rn_sweep(uint32_t n, int mode, const uint8_t* typeA, const float* geomA, const uint8_t* cntA,
+              const float* xfA5, const float* xfA5_end, const uint8_t* typeB, const float* geomB,
+              const uint8_t* cntB, const float* xfB5, const float* xfB5_end, float* out_fraction,
+              void* out_manifold68, uint8_t* out_hit)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const ShapeVariant a = makeShape(typeA[i], geomA + 16 * i, cntA[i]);
+        const ShapeVariant b = makeShape(typeB[i], geomB + 16 * i, cntB[i]);
+        const Transform ta0 = makeRawTransform(xfA5 + 5 * i);
+        const Transform ta1 = makeRawTransform(xfA5_end + 5 * i);
+        const Transform tb0 = makeRawTransform(xfB5 + 5 * i);
+        std::visit(
+            [&](const auto& sa, const auto& sb)
+            {
+                std::optional<SweepManifold> r;
+                if (mode == 2)
+                    r = c2d::sweep(sa, ta0, ta1, sb, tb0, makeRawTransform(xfB5_end + 5 * i));
+                else
+                    r = c2d::sweep(sa, ta0, ta1, sb, tb0);
+                out_hit[i] = r ? 1 : 0;
+                Manifold m{};
+                if (r)
+                    m = r->manifold;
+                if (out_fraction)
+                    out_fraction[i] = r ? r->fraction : -1.0f;
+                if (out_manifold68)
+                    storeManifold(m, static_cast<char*>(out_manifold68) + 68 * i);
+            },
+            a,
+            b);
+    }
+}
+
+void rn_raycast_shape(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt, const float* xf5,
+                      const float* ray4, const uint8_t* infinite, float* out_times2, uint8_t* out_hit)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const ShapeVariant s = makeShape(type[i], geom + 16 * i, cnt[i]);
+        const Transform t = makeRawTransform(xf5 + 5 * i);
+        const float* r = ray4 + 4 * i;
+        std::optional<std::pair<float, float>> res;
+        std::visit(
+            [&](const auto& sc)
+            {
+                if (infinite && infinite[i])
+                    res = c2d::raycast(sc, t, InfiniteRay{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}});
+                else
+                    res = c2d::raycast(sc, t, Ray{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}});
+            },
+            s);
+        out_hit[i] = res ? 1 : 0;
+        out_times2[2 * i] = res ? res->first : 0.0f;
+        out_times2[2 * i + 1] = res ? res->second : 0.0f;
+    }
+}
+
+void rn_sweep_ray(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt, const float* xf5,
+                  const float* xf5_end, const float* ray4, const uint8_t* infinite, float* out_times2,
+                  uint8_t* out_hit)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const ShapeVariant s = makeShape(type[i], geom + 16 * i, cnt[i]);
+        const Transform t0 = makeRawTransform(xf5 + 5 * i);
+        const Transform t1 = makeRawTransform(xf5_end + 5 * i);
+        const float* r = ray4 + 4 * i;
+        std::optional<std::pair<float, float>> res;
+        std::visit(
+            [&](const auto& sc)
+            {
+                if (infinite && infinite[i])
+                    res = c2d::sweep(sc, t0, t1, InfiniteRay{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}});
+                else
+                    res = c2d::sweep(sc, t0, t1, Ray{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}});
+            },
+            s);
+        out_hit[i] = res ? 1 : 0;
+        out_times2[2 * i] = res ? res->first : 0.0f;
+        out_times2[2 * i + 1] = res ? res->second : 0.0f;
+    }
+}
+
+void rn_compute_aabb(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt, const float* xf5,
+                     float* out_aabb4)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const ShapeVariant s = makeShape(type[i], geom + 16 * i, cnt[i]);
+        const Transform t = makeRawTransform(xf5 + 5 * i);
+        const AABB box = std::visit([&](const auto& sc) { return c2d::computeAABB(sc, t); }, s);
+        out_aabb4[4 * i + 0] = box.min.x;
+        out_aabb4[4 * i + 1] = box.min.y;
+        out_aabb4[4 * i + 2] = box.max.x;
+        out_aabb4[4 * i + 3] = box.max.y;
+    }
+}
+
+#elif defined(RN_BACKEND_B200)
+
+// The B200 build evaluates the same batches on the GPU through the C-ABI; the
+// host side only packs shapes exactly as Registry::addShape does.
+namespace
+{
+void packShapes(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt, std::vector<float>& out32)
+{
+    out32.assign(size_t(n) * 32, 0.0f);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        float* o = out32.data() + size_t(i) * 32;
+        if (type[i] == 3)
+        {
+            const Polygon p = makePoly(geom + 16 * i, cnt[i]);
+            for (uint8_t k = 0; k < p.count; ++k)
+            {
+                o[2 * k] = p.vertices[k].x;
+                o[2 * k + 1] = p.vertices[k].y;
+                o[16 + 2 * k] = p.normals[k].x;
+                o[16 + 2 * k + 1] = p.normals[k].y;
+            }
+        }
+        else
+            std::memcpy(o, geom + 16 * i, 5 * sizeof(float));
+    }
+}
+void throwOnError(int rc)
+{
+    if (rc != 0)
+        throw std::runtime_error(std::string("c2d_gpu batch call failed: ") + c2d_gpu_last_error(nullptr));
+}
+} // namespace
+
+void rn_collide(uint32_t n, const uint8_t* typeA, const float* geomA, const uint8_t* cntA, const float* xfA5,
+                const uint8_t* typeB, const float* geomB, const uint8_t* cntB, const float* xfB5,
+                void* out_manifold68, uint8_t* out_are_colliding)
+{
+    std::vector<float> a, b;
+    packShapes(n, typeA, geomA, cntA, a);
+    packShapes(n, typeB, geomB, cntB, b);
+    throwOnError(c2d_gpu_collide_batch(n, typeA, a.data(), cntA, xfA5, typeB, b.data(), cntB, xfB5, out_manifold68,
+                                       out_are_colliding));
+}
+
+void rn_sweep(uint32_t n, int mode, const uint8_t* typeA, const float* geomA, const uint8_t* cntA,
+              const float* xfA5, const float* xfA5_end, const uint8_t* typeB, const float* geomB,
+              const uint8_t* cntB, const float* xfB5, const float* xfB5_end, float* out_fraction,
+              void* out_manifold68, uint8_t* out_hit)
+{
+    std::vector<float> a, b;
+    packShapes(n, typeA, geomA, cntA, a);
+    packShapes(n, typeB, geomB, cntB, b);
+    throwOnError(c2d_gpu_sweep_batch(n, mode, typeA, a.data(), cntA, xfA5, xfA5_end, typeB, b.data(), cntB, xfB5,
+                                     xfB5_end, out_fraction, out_manifold68, out_hit));
+}
+
+void rn_raycast_shape(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt, const float* xf5,
+                      const float* ray4, const uint8_t* infinite, float* out_times2, uint8_t* out_hit)
+{
+    std::vector<float> s;
+    packShapes(n, type, geom, cnt, s);
+    throwOnError(c2d_gpu_raycast_shape_batch(n, type, s.data(), cnt, xf5, nullptr, ray4, infinite, out_times2,
+                                             out_hit));
+}
+
+void rn_sweep_ray(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt, const float* xf5,
+                  const float* xf5_end, const float* ray4, const uint8_t* infinite, float* out_times2,
+                  uint8_t* out_hit)
+{
+    std::vector<float> s;
+    packShapes(n, type, geom, cnt, s);
+    throwOnError(c2d_gpu_raycast_shape_batch(n, type, s.data(), cnt, xf5, xf5_end, ray4, infinite, out_times2,
+                                             out_hit));
+}
+
+void rn_compute_aabb(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt, const float* xf5,
+                     float* out_aabb4)
+{
+    std::vector<float> s;
+    packShapes(n, type, geom, cnt, s);
+    throwOnError(c2d_gpu_compute_aabb_batch(n, type, s.data(), cnt, xf5, out_aabb4));
+}
+
+#endif
+
+void rn_polygon_normals(uint32_t n, const float* geom, const uint8_t* cnt, float* out_normals16)
+{
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const Polygon p = makePoly(geom + 16 * i, cnt[i]);
+        for (uint8_t k = 0; k < 8; ++k)
+        {
+            out_normals16[16 * i + 2 * k] = k < p.count ? p.normals[k].x : 0.0f;
+            out_normals16[16 * i + 2 * k + 1] = k < p.count ? p.normals[k].y : 0.0f;
+        }
+    }
+}
+
+} // extern "C"

@@ -1,0 +1,379 @@
+"""Backend-agnostic test harness over the flat ``rn_*`` interface (tests/cpp/runner_api.h).
+
+TEST INFRASTRUCTURE.  Three shared libraries export the same symbols:
+
+* ``oracle/libc2d_oracle.so``            plain-C restatement of the reference (the oracle)
+* ``oracle/_ref/libc2d_ref_runner.so``   the UNMODIFIED reference, compiled here from /root/reference
+* ``colli2de_b200/libc2d_b200_runner.so`` this repo's ``c2d::Registry`` (CUDA through the C-ABI)
+
+so one scripted scene can be replayed on any of them and the results compared.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+LIB_PATHS = {
+    "oracle": os.path.join(REPO, "oracle", "libc2d_oracle.so"),
+    "reference": os.path.join(REPO, "oracle", "_ref", "libc2d_ref_runner.so"),
+    "b200": os.path.join(REPO, "colli2de_b200", "libc2d_b200_runner.so"),
+}
+
+PAIR_DTYPE = np.dtype(
+    [
+        ("entityA", "<u4"),
+        ("entityB", "<u4"),
+        ("shapeA", "<u4"),
+        ("shapeB", "<u4"),
+        ("normal", "<f4", (2,)),
+        ("points", [("point", "<f4", (2,)), ("anchorA", "<f4", (2,)), ("anchorB", "<f4", (2,)), ("separation", "<f4")], (2,)),
+        ("pointCount", "u1"),
+        ("_pad", "u1", (3,)),
+    ]
+)
+assert PAIR_DTYPE.itemsize == 84
+
+MANIFOLD_DTYPE = np.dtype(
+    [
+        ("normal", "<f4", (2,)),
+        ("points", [("point", "<f4", (2,)), ("anchorA", "<f4", (2,)), ("anchorB", "<f4", (2,)), ("separation", "<f4")], (2,)),
+        ("pointCount", "u1"),
+        ("_pad", "u1", (3,)),
+    ]
+)
+assert MANIFOLD_DTYPE.itemsize == 68
+
+HIT_DTYPE = np.dtype(
+    [
+        ("entity", "<u4"),
+        ("shape", "<u4"),
+        ("entry", "<f4", (2,)),
+        ("exit", "<f4", (2,)),
+        ("entryTime", "<f4"),
+        ("exitTime", "<f4"),
+    ]
+)
+assert HIT_DTYPE.itemsize == 32
+
+STATIC, DYNAMIC, BULLET = 0, 1, 2
+CIRCLE, CAPSULE, SEGMENT, POLYGON = 0, 1, 2, 3
+
+
+def _p(a, ctype):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _u64(a):
+    return np.ascontiguousarray(a, dtype=np.uint64)
+
+
+_LIBS: dict[str, C.CDLL] = {}
+
+
+def available(name: str) -> bool:
+    return os.path.exists(LIB_PATHS[name])
+
+
+def load(name: str) -> C.CDLL:
+    if name in _LIBS:
+        return _LIBS[name]
+    path = LIB_PATHS[name]
+    if name == "b200":
+        # the runner links libc2d_gpu.so by rpath ($ORIGIN)
+        pass
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    pf, pu8, pu32, pu64 = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+    pd = C.POINTER(C.c_double)
+    sig = {
+        "rn_backend_name": (C.c_char_p, []),
+        "rn_create": (vp, [i32, u32]),
+        "rn_destroy": (None, [vp]),
+        "rn_last_error": (C.c_char_p, [vp]),
+        "rn_create_entities": (None, [vp, u32, pu32, pu8, pf]),
+        "rn_create_entities_raw": (None, [vp, u32, pu32, pu8, pf]),
+        "rn_add_shapes": (None, [vp, u32, pu32, pu8, pf, pu8, pu64, pu64, pu32]),
+        "rn_remove_shapes": (None, [vp, u32, pu32]),
+        "rn_remove_entities": (None, [vp, u32, pu32]),
+        "rn_set_active": (None, [vp, u32, pu32, pu8]),
+        "rn_move_translate": (None, [vp, u32, pu32, pf]),
+        "rn_move_transform": (None, [vp, u32, pu32, pf]),
+        "rn_teleport_transform": (None, [vp, u32, pu32, pf]),
+        "rn_teleport_translation": (None, [vp, u32, pu32, pf]),
+        "rn_get_transforms": (None, [vp, u32, pu32, pf]),
+        "rn_get_prev_transforms": (None, [vp, u32, pu32, pf]),
+        "rn_size": (u64, [vp]),
+        "rn_clear": (None, [vp]),
+        "rn_get_colliding_pairs": (u64, [vp, pd]),
+        "rn_copy_pairs": (None, [vp, vp]),
+        "rn_raycast": (u64, [vp, u32, pf, pu8, pu64, pu64, pd]),
+        "rn_copy_hits": (None, [vp, vp]),
+        "rn_collide": (None, [u32, pu8, pf, pu8, pf, pu8, pf, pu8, pf, vp, pu8]),
+        "rn_sweep": (None, [u32, i32, pu8, pf, pu8, pf, pf, pu8, pf, pu8, pf, pf, pf, vp, pu8]),
+        "rn_raycast_shape": (None, [u32, pu8, pf, pu8, pf, pf, pu8, pf, pu8]),
+        "rn_sweep_ray": (None, [u32, pu8, pf, pu8, pf, pf, pf, pu8, pf, pu8]),
+        "rn_compute_aabb": (None, [u32, pu8, pf, pu8, pf, pf]),
+        "rn_polygon_normals": (None, [u32, pf, pu8, pf]),
+    }
+    for fn, (res, args) in sig.items():
+        f = getattr(lib, fn)
+        f.restype = res
+        f.argtypes = args
+    _LIBS[name] = lib
+    return lib
+
+
+def xf5_from_xf3(xf3) -> np.ndarray:
+    """Transform(Vec2, angle): sin/cos from libm's float sinf/cosf (Transform.hpp:23-28)."""
+    xf3 = _f32(xf3).reshape(-1, 3)
+    out = np.zeros((xf3.shape[0], 5), np.float32)
+    out[:, :3] = xf3
+    libm = C.CDLL("libm.so.6")
+    libm.sinf.restype = C.c_float
+    libm.sinf.argtypes = [C.c_float]
+    libm.cosf.restype = C.c_float
+    libm.cosf.argtypes = [C.c_float]
+    for i in range(xf3.shape[0]):
+        out[i, 3] = libm.sinf(float(xf3[i, 2]))
+        out[i, 4] = libm.cosf(float(xf3[i, 2]))
+    return out
+
+
+class Backend:
+    """A Registry<uint32_t, Method> living behind one of the rn_* libraries."""
+
+    def __init__(self, name: str, method: int = 0, cell_size: int = 120):
+        self.name = name
+        self.lib = load(name)
+        self.ctx = self.lib.rn_create(method, cell_size)
+        self._check()
+
+    def close(self):
+        if self.ctx:
+            self.lib.rn_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self):
+        err = self.lib.rn_last_error(self.ctx)
+        if err:
+            raise RuntimeError(f"[{self.name}] {err.decode()}")
+
+    # -- mutation -----------------------------------------------------------------------------
+    def create_entities(self, ids, body, xf3):
+        ids, body, xf3 = _u32(ids), _u8(body), _f32(xf3)
+        self.lib.rn_create_entities(self.ctx, len(ids), _p(ids, C.c_uint32), _p(body, C.c_uint8), _p(xf3, C.c_float))
+        self._check()
+
+    def create_entities_raw(self, ids, body, xf5):
+        ids, body, xf5 = _u32(ids), _u8(body), _f32(xf5)
+        self.lib.rn_create_entities_raw(self.ctx, len(ids), _p(ids, C.c_uint32), _p(body, C.c_uint8), _p(xf5, C.c_float))
+        self._check()
+
+    def add_shapes(self, entity, stype, geom16, vcount=None, cat=None, mask=None) -> np.ndarray:
+        entity, stype, geom16 = _u32(entity), _u8(stype), _f32(geom16)
+        n = len(entity)
+        assert geom16.shape == (n, 16)
+        vcount = _u8(vcount if vcount is not None else np.zeros(n))
+        cat = _u64(cat) if cat is not None else None
+        mask = _u64(mask) if mask is not None else None
+        out = np.zeros(n, np.uint32)
+        self.lib.rn_add_shapes(
+            self.ctx, n, _p(entity, C.c_uint32), _p(stype, C.c_uint8), _p(geom16, C.c_float), _p(vcount, C.c_uint8),
+            _p(cat, C.c_uint64), _p(mask, C.c_uint64), _p(out, C.c_uint32))
+        self._check()
+        return out
+
+    def remove_shapes(self, shape_ids):
+        s = _u32(shape_ids)
+        self.lib.rn_remove_shapes(self.ctx, len(s), _p(s, C.c_uint32))
+        self._check()
+
+    def remove_entities(self, ids):
+        s = _u32(ids)
+        self.lib.rn_remove_entities(self.ctx, len(s), _p(s, C.c_uint32))
+        self._check()
+
+    def set_active(self, shape_ids, active):
+        s, a = _u32(shape_ids), _u8(active)
+        self.lib.rn_set_active(self.ctx, len(s), _p(s, C.c_uint32), _p(a, C.c_uint8))
+        self._check()
+
+    def move_translate(self, ids, dxy):
+        ids, dxy = _u32(ids), _f32(dxy)
+        self.lib.rn_move_translate(self.ctx, len(ids), _p(ids, C.c_uint32), _p(dxy, C.c_float))
+        self._check()
+
+    def move_transform(self, ids, dxf3):
+        ids, d = _u32(ids), _f32(dxf3)
+        self.lib.rn_move_transform(self.ctx, len(ids), _p(ids, C.c_uint32), _p(d, C.c_float))
+        self._check()
+
+    def teleport_transform(self, ids, xf3):
+        ids, d = _u32(ids), _f32(xf3)
+        self.lib.rn_teleport_transform(self.ctx, len(ids), _p(ids, C.c_uint32), _p(d, C.c_float))
+        self._check()
+
+    def teleport_translation(self, ids, xy):
+        ids, d = _u32(ids), _f32(xy)
+        self.lib.rn_teleport_translation(self.ctx, len(ids), _p(ids, C.c_uint32), _p(d, C.c_float))
+        self._check()
+
+    def get_transforms(self, ids) -> np.ndarray:
+        ids = _u32(ids)
+        out = np.zeros((len(ids), 5), np.float32)
+        self.lib.rn_get_transforms(self.ctx, len(ids), _p(ids, C.c_uint32), _p(out, C.c_float))
+        self._check()
+        return out
+
+    def get_prev_transforms(self, ids) -> np.ndarray:
+        ids = _u32(ids)
+        out = np.zeros((len(ids), 5), np.float32)
+        self.lib.rn_get_prev_transforms(self.ctx, len(ids), _p(ids, C.c_uint32), _p(out, C.c_float))
+        self._check()
+        return out
+
+    def size(self) -> int:
+        return int(self.lib.rn_size(self.ctx))
+
+    def clear(self):
+        self.lib.rn_clear(self.ctx)
+        self._check()
+
+    # -- queries ------------------------------------------------------------------------------
+    def get_colliding_pairs(self, with_time=False):
+        sec = C.c_double(0.0)
+        n = int(self.lib.rn_get_colliding_pairs(self.ctx, C.byref(sec)))
+        self._check()
+        out = np.zeros(n, PAIR_DTYPE)
+        if n:
+            self.lib.rn_copy_pairs(self.ctx, out.ctypes.data_as(C.c_void_p))
+        return (out, sec.value) if with_time else out
+
+    def raycast(self, ray4, infinite=None, masks=None, with_time=False):
+        ray4 = _f32(ray4).reshape(-1, 4)
+        n = ray4.shape[0]
+        infinite = _u8(infinite if infinite is not None else np.zeros(n))
+        masks = _u64(masks) if masks is not None else None
+        offsets = np.zeros(n + 1, np.uint64)
+        sec = C.c_double(0.0)
+        total = int(self.lib.rn_raycast(self.ctx, n, _p(ray4, C.c_float), _p(infinite, C.c_uint8),
+                                        _p(masks, C.c_uint64), _p(offsets, C.c_uint64), C.byref(sec)))
+        self._check()
+        hits = np.zeros(total, HIT_DTYPE)
+        if total:
+            self.lib.rn_copy_hits(self.ctx, hits.ctypes.data_as(C.c_void_p))
+        return (offsets, hits, sec.value) if with_time else (offsets, hits)
+
+
+# -- free functions (batched) ---------------------------------------------------------------------
+@dataclass
+class ShapeBatch:
+    stype: np.ndarray   # (n,) u8
+    geom: np.ndarray    # (n,16) f32
+    count: np.ndarray   # (n,) u8
+
+    def __post_init__(self):
+        self.stype = _u8(self.stype)
+        self.geom = _f32(self.geom).reshape(-1, 16)
+        self.count = _u8(self.count)
+
+    def __len__(self):
+        return len(self.stype)
+
+    def take(self, idx):
+        return ShapeBatch(self.stype[idx], self.geom[idx], self.count[idx])
+
+
+def collide(name, A: ShapeBatch, xfA5, B: ShapeBatch, xfB5):
+    lib = load(name)
+    n = len(A)
+    xfA5, xfB5 = _f32(xfA5).reshape(n, 5), _f32(xfB5).reshape(n, 5)
+    man = np.zeros(n, MANIFOLD_DTYPE)
+    flag = np.zeros(n, np.uint8)
+    lib.rn_collide(n, _p(A.stype, C.c_uint8), _p(A.geom, C.c_float), _p(A.count, C.c_uint8), _p(xfA5, C.c_float),
+                   _p(B.stype, C.c_uint8), _p(B.geom, C.c_float), _p(B.count, C.c_uint8), _p(xfB5, C.c_float),
+                   man.ctypes.data_as(C.c_void_p), _p(flag, C.c_uint8))
+    return man, flag
+
+
+def sweep(name, mode, A: ShapeBatch, xfA0, xfA1, B: ShapeBatch, xfB0, xfB1=None):
+    lib = load(name)
+    n = len(A)
+    xfA0, xfA1, xfB0 = _f32(xfA0).reshape(n, 5), _f32(xfA1).reshape(n, 5), _f32(xfB0).reshape(n, 5)
+    xfB1 = _f32(xfB1).reshape(n, 5) if xfB1 is not None else xfB0.copy()
+    frac = np.zeros(n, np.float32)
+    man = np.zeros(n, MANIFOLD_DTYPE)
+    hit = np.zeros(n, np.uint8)
+    lib.rn_sweep(n, mode, _p(A.stype, C.c_uint8), _p(A.geom, C.c_float), _p(A.count, C.c_uint8),
+                 _p(xfA0, C.c_float), _p(xfA1, C.c_float), _p(B.stype, C.c_uint8), _p(B.geom, C.c_float),
+                 _p(B.count, C.c_uint8), _p(xfB0, C.c_float), _p(xfB1, C.c_float), _p(frac, C.c_float),
+                 man.ctypes.data_as(C.c_void_p), _p(hit, C.c_uint8))
+    return frac, man, hit
+
+
+def raycast_shape(name, S: ShapeBatch, xf5, ray4, infinite):
+    lib = load(name)
+    n = len(S)
+    xf5, ray4, infinite = _f32(xf5).reshape(n, 5), _f32(ray4).reshape(n, 4), _u8(infinite)
+    times = np.zeros((n, 2), np.float32)
+    hit = np.zeros(n, np.uint8)
+    lib.rn_raycast_shape(n, _p(S.stype, C.c_uint8), _p(S.geom, C.c_float), _p(S.count, C.c_uint8),
+                         _p(xf5, C.c_float), _p(ray4, C.c_float), _p(infinite, C.c_uint8), _p(times, C.c_float),
+                         _p(hit, C.c_uint8))
+    return times, hit
+
+
+def sweep_ray(name, S: ShapeBatch, xf5_0, xf5_1, ray4, infinite):
+    lib = load(name)
+    n = len(S)
+    a, b = _f32(xf5_0).reshape(n, 5), _f32(xf5_1).reshape(n, 5)
+    ray4, infinite = _f32(ray4).reshape(n, 4), _u8(infinite)
+    times = np.zeros((n, 2), np.float32)
+    hit = np.zeros(n, np.uint8)
+    lib.rn_sweep_ray(n, _p(S.stype, C.c_uint8), _p(S.geom, C.c_float), _p(S.count, C.c_uint8), _p(a, C.c_float),
+                     _p(b, C.c_float), _p(ray4, C.c_float), _p(infinite, C.c_uint8), _p(times, C.c_float),
+                     _p(hit, C.c_uint8))
+    return times, hit
+
+
+def compute_aabb(name, S: ShapeBatch, xf5):
+    lib = load(name)
+    n = len(S)
+    xf5 = _f32(xf5).reshape(n, 5)
+    out = np.zeros((n, 4), np.float32)
+    lib.rn_compute_aabb(n, _p(S.stype, C.c_uint8), _p(S.geom, C.c_float), _p(S.count, C.c_uint8),
+                        _p(xf5, C.c_float), _p(out, C.c_float))
+    return out
+
+
+def polygon_normals(name, geom, count):
+    lib = load(name)
+    geom, count = _f32(geom).reshape(-1, 16), _u8(count)
+    out = np.zeros((len(count), 16), np.float32)
+    lib.rn_polygon_normals(len(count), _p(geom, C.c_float), _p(count, C.c_uint8), _p(out, C.c_float))
+    return out
