@@ -1,0 +1,815 @@
+// c2d_gpu.cu — context, mutation log, per-frame pipeline and the C ABI of libc2d_gpu.so (include/c2d_gpu.h).
+//
+// Host-side structure (one context per c2d::Registry):
+//   * shape state lives in HBM as SoA (ShapeArrays); the host keeps only what it needs to schedule work:
+//     body type / alive bit per shape, the member list of each of the three trees (Static, Dynamic, Bullet —
+//     the reference's mTrees[3], Registry.hpp:157-165) and the hazard stamps of the mutation log;
+//   * mutations are appended to pinned logs and replayed by the K1 kernels in "rounds": inside a round the
+//     phases run flags -> adds -> translates -> moves and a shape appears at most once per phase with
+//     strictly increasing phase, so per-shape program order is preserved without one launch per call;
+//   * a query = flush + (re)build of the dirty trees + 5 traversals + binning + narrowphase on one stream.
+#include "c2d_kernels.cuh"
+
+#include "../../include/c2d_gpu.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace c2d_dev;
+
+namespace
+{
+
+thread_local std::string g_lastError;
+
+// ---- small RAII helpers ---------------------------------------------------------------------------
+template <typename T>
+struct PinnedVec
+{
+    T* data = nullptr;
+    size_t size = 0;
+    size_t capacity = 0;
+
+    ~PinnedVec()
+    {
+        if (data)
+            cudaFreeHost(data);
+    }
+    bool reserve(size_t want)
+    {
+        if (want <= capacity)
+            return true;
+        size_t cap = capacity ? capacity : 1024;
+        while (cap < want)
+            cap *= 2;
+        T* fresh = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&fresh), cap * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
+            return false;
+        if (size)
+            std::memcpy(fresh, data, size * sizeof(T));
+        if (data)
+            cudaFreeHost(data);
+        data = fresh;
+        capacity = cap;
+        return true;
+    }
+    T* push()
+    {
+        if (size == capacity && !reserve(size + 1))
+            return nullptr;
+        return &data[size++];
+    }
+};
+
+template <typename T>
+struct DevBuf
+{
+    T* ptr = nullptr;
+    size_t capacity = 0;
+    ~DevBuf()
+    {
+        if (ptr)
+            cudaFree(ptr);
+    }
+    // contents are NOT preserved
+    cudaError_t reserve(size_t want)
+    {
+        if (want <= capacity)
+            return cudaSuccess;
+        size_t cap = capacity ? capacity : 1024;
+        while (cap < want)
+            cap *= 2;
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        capacity = 0;
+        const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), cap * sizeof(T));
+        if (e == cudaSuccess)
+            capacity = cap;
+        return e;
+    }
+};
+
+enum Phase : uint32_t
+{
+    PH_FLAG = 0,
+    PH_ADD = 1,
+    PH_TRANS = 2,
+    PH_MOVE = 3
+};
+
+struct Round
+{
+    size_t f0, a0, t0, m0; // begin offsets in the four logs; the end is the next round's begin (or the log size)
+};
+
+struct TreeBuf
+{
+    DevBuf<uint32_t> members; // shape ids, host order
+    DevBuf<uint32_t> keys, vals, keysTmp, valsTmp;
+    DevBuf<BvhNode> nodes;
+    DevBuf<int> nodeParent, leafParent;
+    DevBuf<uint32_t> arrival;
+    DevBuf<unsigned char> sortWs;
+    uint32_t n = 0; // leaves in the built tree
+};
+
+} // namespace
+
+struct c2d_gpu_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string error;
+
+    // shapes
+    uint32_t capacity = 0;
+    uint32_t shapeSlots = 0; // 1 + highest shape id ever added
+    ShapeArrays d{};
+    std::vector<uint32_t> hostMeta; // body / alive per shape
+    std::vector<uint32_t> stamp;    // (round << 2) | phase of the last logged op
+    std::vector<uint32_t> memberPos;
+    std::vector<uint32_t> members[3];
+    bool membersDirty[3] = {false, false, false};
+    bool treeDirty[3] = {false, false, false};
+
+    // mutation log
+    uint32_t round = 1;
+    PinnedVec<FlagRec> flagLog;
+    PinnedVec<AddRec> addLog;
+    PinnedVec<TransRec> transLog;
+    PinnedVec<MoveRec> moveLog;
+    std::vector<Round> rounds;
+    DevBuf<FlagRec> dFlagLog;
+    DevBuf<AddRec> dAddLog;
+    DevBuf<TransRec> dTransLog;
+    DevBuf<MoveRec> dMoveLog;
+
+    // trees
+    TreeBuf tree[3];
+    int broadphase = C2D_BROADPHASE_LBVH;
+    uint32_t cellSize = 120;
+    uint32_t shardRank = 0, shardWorld = 1;
+
+    // frame
+    FrameScratch* dScratch = nullptr;
+    FrameScratch* hScratch = nullptr; // pinned
+    DevBuf<uint2> cand, binned;
+    DevBuf<PairOut> out;
+    PinnedVec<PairOut> hostOut;
+    uint64_t lastCandidates = 0;
+    uint32_t launches = 0;
+    uint64_t h2dBytes = 0;
+};
+
+namespace
+{
+
+int fail(c2d_gpu_ctx* ctx, const std::string& msg)
+{
+    if (ctx)
+        ctx->error = msg;
+    g_lastError = msg;
+    return 1;
+}
+
+#define C2D_CUDA(ctx, call)                                                                                            \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        const cudaError_t _e = (call);                                                                                 \
+        if (_e != cudaSuccess)                                                                                         \
+            return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(_e));                                      \
+    } while (0)
+
+inline uint32_t blocks_for(size_t n, uint32_t threads)
+{
+    return static_cast<uint32_t>((n + threads - 1) / threads);
+}
+
+template <typename T>
+cudaError_t grow_array(T*& ptr, uint32_t oldCap, uint32_t newCap, size_t perShape, cudaStream_t stream)
+{
+    T* fresh = nullptr;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&fresh), static_cast<size_t>(newCap) * perShape * sizeof(T));
+    if (e != cudaSuccess)
+        return e;
+    e = cudaMemsetAsync(fresh, 0, static_cast<size_t>(newCap) * perShape * sizeof(T), stream);
+    if (e != cudaSuccess)
+        return e;
+    if (ptr && oldCap)
+    {
+        e = cudaMemcpyAsync(fresh, ptr, static_cast<size_t>(oldCap) * perShape * sizeof(T), cudaMemcpyDeviceToDevice,
+                            stream);
+        if (e != cudaSuccess)
+            return e;
+    }
+    e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess)
+        return e;
+    if (ptr)
+        cudaFree(ptr);
+    ptr = fresh;
+    return cudaSuccess;
+}
+
+int ensure_shape_capacity(c2d_gpu_ctx* ctx, uint32_t want)
+{
+    if (want <= ctx->capacity)
+        return 0;
+    uint32_t cap = ctx->capacity ? ctx->capacity : 4096;
+    while (cap < want)
+        cap *= 2;
+    const uint32_t old = ctx->capacity;
+    cudaStream_t s = ctx->stream;
+    C2D_CUDA(ctx, grow_array(ctx->d.xf, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.xa, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.pxf, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.pxa, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.tight, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.fat, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.meta, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.entity, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.category, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.mask, old, cap, 1, s));
+    C2D_CUDA(ctx, grow_array(ctx->d.geom, old, cap, 32, s));
+    ctx->capacity = cap;
+    return 0;
+}
+
+// ---- mutation log ----------------------------------------------------------------------------------
+void begin_round(c2d_gpu_ctx* ctx)
+{
+    ++ctx->round;
+    ctx->rounds.push_back(Round{ctx->flagLog.size, ctx->addLog.size, ctx->transLog.size, ctx->moveLog.size});
+}
+
+// Makes sure an op of `phase` on `shape` can join the current round (strictly increasing phase per shape).
+inline void claim(c2d_gpu_ctx* ctx, uint32_t shape, Phase phase)
+{
+    if (shape >= ctx->stamp.size())
+    {
+        ctx->stamp.resize(std::max<size_t>(shape + 1, ctx->stamp.size() * 2), 0);
+        ctx->hostMeta.resize(ctx->stamp.size(), 0);
+        ctx->memberPos.resize(ctx->stamp.size(), 0);
+    }
+    if (ctx->rounds.empty())
+        begin_round(ctx);
+    const uint32_t st = ctx->stamp[shape];
+    if ((st >> 2) == ctx->round && (st & 3u) >= static_cast<uint32_t>(phase))
+        begin_round(ctx);
+    ctx->stamp[shape] = (ctx->round << 2) | static_cast<uint32_t>(phase);
+}
+
+void member_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
+{
+    ctx->memberPos[shape] = static_cast<uint32_t>(ctx->members[body].size());
+    ctx->members[body].push_back(shape);
+    ctx->membersDirty[body] = ctx->treeDirty[body] = true;
+}
+
+void member_remove(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
+{
+    auto& list = ctx->members[body];
+    const uint32_t pos = ctx->memberPos[shape];
+    const uint32_t last = list.back();
+    list[pos] = last;
+    ctx->memberPos[last] = pos;
+    list.pop_back();
+    ctx->membersDirty[body] = ctx->treeDirty[body] = true;
+}
+
+int flush(c2d_gpu_ctx* ctx)
+{
+    if (ctx->rounds.empty())
+        return 0;
+    cudaStream_t s = ctx->stream;
+    if (int rc = ensure_shape_capacity(ctx, ctx->shapeSlots))
+        return rc;
+    const size_t nf = ctx->flagLog.size, na = ctx->addLog.size, nt = ctx->transLog.size, nm = ctx->moveLog.size;
+    if (nf)
+    {
+        C2D_CUDA(ctx, ctx->dFlagLog.reserve(nf));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dFlagLog.ptr, ctx->flagLog.data, nf * sizeof(FlagRec), cudaMemcpyHostToDevice, s));
+    }
+    if (na)
+    {
+        C2D_CUDA(ctx, ctx->dAddLog.reserve(na));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dAddLog.ptr, ctx->addLog.data, na * sizeof(AddRec), cudaMemcpyHostToDevice, s));
+    }
+    if (nt)
+    {
+        C2D_CUDA(ctx, ctx->dTransLog.reserve(nt));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dTransLog.ptr, ctx->transLog.data, nt * sizeof(TransRec), cudaMemcpyHostToDevice, s));
+    }
+    if (nm)
+    {
+        C2D_CUDA(ctx, ctx->dMoveLog.reserve(nm));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dMoveLog.ptr, ctx->moveLog.data, nm * sizeof(MoveRec), cudaMemcpyHostToDevice, s));
+    }
+    ctx->h2dBytes += nf * sizeof(FlagRec) + na * sizeof(AddRec) + nt * sizeof(TransRec) + nm * sizeof(MoveRec);
+
+    for (size_t r = 0; r < ctx->rounds.size(); ++r)
+    {
+        const Round& cur = ctx->rounds[r];
+        const bool lastRound = r + 1 == ctx->rounds.size();
+        const size_t f1 = lastRound ? nf : ctx->rounds[r + 1].f0;
+        const size_t a1 = lastRound ? na : ctx->rounds[r + 1].a0;
+        const size_t t1 = lastRound ? nt : ctx->rounds[r + 1].t0;
+        const size_t m1 = lastRound ? nm : ctx->rounds[r + 1].m0;
+        if (f1 > cur.f0)
+        {
+            const uint32_t n = static_cast<uint32_t>(f1 - cur.f0);
+            k_apply_flags<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dFlagLog.ptr + cur.f0, n, ctx->d);
+            ++ctx->launches;
+        }
+        if (a1 > cur.a0)
+        {
+            const uint32_t n = static_cast<uint32_t>(a1 - cur.a0);
+            k_apply_adds<<<blocks_for(static_cast<size_t>(n) * 32, 128), 128, 0, s>>>(ctx->dAddLog.ptr + cur.a0, n, ctx->d);
+            ++ctx->launches;
+        }
+        if (t1 > cur.t0)
+        {
+            const uint32_t n = static_cast<uint32_t>(t1 - cur.t0);
+            k_apply_translates<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dTransLog.ptr + cur.t0, n, ctx->d);
+            ++ctx->launches;
+        }
+        if (m1 > cur.m0)
+        {
+            const uint32_t n = static_cast<uint32_t>(m1 - cur.m0);
+            k_apply_moves<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dMoveLog.ptr + cur.m0, n, ctx->d);
+            ++ctx->launches;
+        }
+    }
+    C2D_CUDA(ctx, cudaGetLastError());
+    // the pinned logs are reused by the next frame: the copies above must have been consumed
+    C2D_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->flagLog.size = ctx->addLog.size = ctx->transLog.size = ctx->moveLog.size = 0;
+    ctx->rounds.clear();
+    return 0;
+}
+
+// ---- tree build --------------------------------------------------------------------------------------
+int build_tree(c2d_gpu_ctx* ctx, int body)
+{
+    TreeBuf& t = ctx->tree[body];
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = static_cast<uint32_t>(ctx->members[body].size());
+    if (ctx->membersDirty[body])
+    {
+        if (n)
+        {
+            C2D_CUDA(ctx, t.members.reserve(n));
+            C2D_CUDA(ctx, cudaMemcpyAsync(t.members.ptr, ctx->members[body].data(), n * sizeof(uint32_t),
+                                          cudaMemcpyHostToDevice, s));
+            // the host vector may be modified right after this call returns
+            C2D_CUDA(ctx, cudaStreamSynchronize(s));
+            ctx->h2dBytes += n * sizeof(uint32_t);
+        }
+        ctx->membersDirty[body] = false;
+    }
+    t.n = n;
+    ctx->treeDirty[body] = false;
+    if (n == 0)
+        return 0;
+    C2D_CUDA(ctx, t.keys.reserve(n));
+    C2D_CUDA(ctx, t.vals.reserve(n));
+    C2D_CUDA(ctx, t.keysTmp.reserve(n));
+    C2D_CUDA(ctx, t.valsTmp.reserve(n));
+    C2D_CUDA(ctx, t.nodes.reserve(n));
+    C2D_CUDA(ctx, t.nodeParent.reserve(n));
+    C2D_CUDA(ctx, t.leafParent.reserve(n));
+    C2D_CUDA(ctx, t.arrival.reserve(n));
+    C2D_CUDA(ctx, t.sortWs.reserve(sort_workspace_bytes(n, 4)));
+
+    uint32_t* bounds = &ctx->dScratch->bounds[body][0];
+    uint32_t rb = blocks_for(n, 256);
+    if (rb > 148 * 8)
+        rb = 148 * 8;
+    k_bounds<<<rb, 256, 0, s>>>(t.members.ptr, n, ctx->d.fat, bounds);
+    k_morton<<<blocks_for(n, 256), 256, 0, s>>>(t.members.ptr, n, ctx->d.fat, bounds, t.keys.ptr, t.vals.ptr);
+    ctx->launches += 2;
+    ctx->launches += radix_sort_pairs(s, t.keys.ptr, t.vals.ptr, t.keysTmp.ptr, t.valsTmp.ptr, n, 4, t.sortWs.ptr);
+    if (n > 1)
+    {
+        C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
+        k_karras_build<<<blocks_for(n - 1, 256), 256, 0, s>>>(t.keys.ptr, static_cast<int>(n), t.nodes.ptr,
+                                                             t.nodeParent.ptr, t.leafParent.ptr);
+        k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
+                                                 t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr);
+        ctx->launches += 2;
+    }
+    C2D_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
+template <bool SELF>
+void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)
+{
+    const TreeBuf& q = ctx->tree[qBody];
+    const TreeBuf& t = ctx->tree[tBody];
+    if (q.n == 0 || t.n == 0 || (SELF && q.n < 2))
+        return;
+    // multi-GPU: this context owns the query leaves of Morton-rank slab [lo, hi)
+    const uint32_t lo = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * ctx->shardRank / ctx->shardWorld);
+    const uint32_t hi = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * (ctx->shardRank + 1) / ctx->shardWorld);
+    if (hi <= lo)
+        return;
+    k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+        q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
+        static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount);
+    ++ctx->launches;
+}
+
+int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRecords, uint64_t* outCount,
+                 c2d_gpu_stats* stats)
+{
+    const auto wall0 = std::chrono::steady_clock::now();
+    cudaStream_t s = ctx->stream;
+    ctx->launches = 0;
+    ctx->h2dBytes = 0;
+    uint32_t retries = 0;
+    uint64_t d2h = 0;
+
+    C2D_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
+    if (int rc = flush(ctx))
+        return rc;
+    C2D_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+
+    k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch);
+    ++ctx->launches;
+    for (int body = 0; body < 3; ++body)
+        if (ctx->treeDirty[body])
+            if (int rc = build_tree(ctx, body))
+                return rc;
+    C2D_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
+
+    if (ctx->cand.capacity == 0)
+    {
+        C2D_CUDA(ctx, ctx->cand.reserve(1u << 16));
+        C2D_CUDA(ctx, ctx->binned.reserve(1u << 16));
+    }
+    if (ctx->out.capacity == 0)
+        C2D_CUDA(ctx, ctx->out.reserve(1u << 15));
+
+    uint32_t candCount = 0, pairCount = 0;
+    while (true)
+    {
+        // groups in the reference's order (Registry.hpp:487-545)
+        launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC);
+        launch_traverse<true>(ctx, C2D_DYNAMIC, C2D_DYNAMIC);
+        launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
+        launch_traverse<false>(ctx, C2D_BULLET, C2D_DYNAMIC);
+        launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
+        C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+
+        const uint32_t cap = static_cast<uint32_t>(ctx->cand.capacity);
+        const uint32_t grid = 148 * 4;
+        k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch);
+        k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch);
+        k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr);
+        k_narrow<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                         static_cast<uint32_t>(ctx->out.capacity));
+        ctx->launches += 4;
+        C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
+        C2D_CUDA(ctx, cudaStreamSynchronize(s));
+        C2D_CUDA(ctx, cudaGetLastError());
+        d2h += sizeof(FrameScratch);
+        candCount = ctx->hScratch->candCount;
+        pairCount = ctx->hScratch->outCount;
+        if (ctx->hScratch->clipOverflow)
+            return fail(ctx, "polygon clip scratch overflow (non-convex polygon input?)");
+        const bool candOverflow = candCount > ctx->cand.capacity;
+        const bool outOverflow = pairCount > ctx->out.capacity;
+        if (!candOverflow && !outOverflow)
+            break;
+        // pair-list overflow: grow and re-run traversal + narrowphase (boxes and trees are unchanged)
+        ++retries;
+        if (candOverflow)
+        {
+            C2D_CUDA(ctx, ctx->cand.reserve(static_cast<size_t>(candCount) + candCount / 4));
+            C2D_CUDA(ctx, ctx->binned.reserve(ctx->cand.capacity));
+        }
+        if (outOverflow)
+            C2D_CUDA(ctx, ctx->out.reserve(static_cast<size_t>(pairCount) + pairCount / 4));
+        k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch);
+        ++ctx->launches;
+    }
+    ctx->lastCandidates = candCount;
+
+    if (download && pairCount)
+    {
+        if (!ctx->hostOut.reserve(pairCount))
+            return fail(ctx, "pinned host allocation failed");
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hostOut.data, ctx->out.ptr, static_cast<size_t>(pairCount) * sizeof(PairOut),
+                                      cudaMemcpyDeviceToHost, s));
+        C2D_CUDA(ctx, cudaStreamSynchronize(s));
+        d2h += static_cast<uint64_t>(pairCount) * sizeof(PairOut);
+    }
+    if (outRecords)
+        *outRecords = reinterpret_cast<const c2d_pair_record*>(ctx->hostOut.data);
+    if (outCount)
+        *outCount = pairCount;
+
+    if (stats)
+    {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->shapes_alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
+        stats->candidates = candCount;
+        stats->pairs = pairCount;
+        stats->h2d_bytes = ctx->h2dBytes;
+        stats->d2h_bytes = d2h;
+        stats->kernel_launches = ctx->launches;
+        stats->retries = retries;
+        cudaEventElapsedTime(&stats->ms_refit, ctx->ev[0], ctx->ev[1]);
+        cudaEventElapsedTime(&stats->ms_build, ctx->ev[1], ctx->ev[2]);
+        cudaEventElapsedTime(&stats->ms_broad, ctx->ev[2], ctx->ev[3]);
+        cudaEventElapsedTime(&stats->ms_narrow, ctx->ev[3], ctx->ev[4]);
+        cudaEventElapsedTime(&stats->ms_device, ctx->ev[0], ctx->ev[4]);
+        stats->ms_total =
+            std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    }
+    return 0;
+}
+
+} // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+// shared with c2d_batch.cu: the message returned by c2d_gpu_last_error(NULL)
+void c2d_gpu_internal_set_error(const char* msg)
+{
+    g_lastError = msg ? msg : "";
+}
+
+int c2d_gpu_create(int device, c2d_gpu_ctx** out_ctx)
+{
+    if (!out_ctx)
+        return fail(nullptr, "c2d_gpu_create: out_ctx is NULL");
+    *out_ctx = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, std::string("c2d_gpu_create: no CUDA device (") + cudaGetErrorString(e) +
+                                 "); libc2d_gpu has no CPU fallback");
+    if (device < 0)
+        cudaGetDevice(&device);
+    C2D_CUDA(nullptr, cudaSetDevice(device));
+    c2d_gpu_ctx* ctx = new c2d_gpu_ctx();
+    ctx->device = device;
+    e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 6 && e == cudaSuccess; ++i)
+        e = cudaEventCreate(&ctx->ev[i]);
+    if (e == cudaSuccess)
+        e = cudaMalloc(reinterpret_cast<void**>(&ctx->dScratch), sizeof(FrameScratch));
+    if (e == cudaSuccess)
+        e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->hScratch), sizeof(FrameScratch), cudaHostAllocDefault);
+    if (e != cudaSuccess)
+    {
+        fail(nullptr, std::string("c2d_gpu_create: ") + cudaGetErrorString(e));
+        delete ctx;
+        return 1;
+    }
+    *out_ctx = ctx;
+    return 0;
+}
+
+void c2d_gpu_destroy(c2d_gpu_ctx* ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d.xf);
+    cudaFree(ctx->d.xa);
+    cudaFree(ctx->d.pxf);
+    cudaFree(ctx->d.pxa);
+    cudaFree(ctx->d.tight);
+    cudaFree(ctx->d.fat);
+    cudaFree(ctx->d.meta);
+    cudaFree(ctx->d.entity);
+    cudaFree(ctx->d.category);
+    cudaFree(ctx->d.mask);
+    cudaFree(ctx->d.geom);
+    cudaFree(ctx->dScratch);
+    cudaFreeHost(ctx->hScratch);
+    for (auto& ev : ctx->ev)
+        if (ev)
+            cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* c2d_gpu_last_error(c2d_gpu_ctx* ctx)
+{
+    return ctx ? ctx->error.c_str() : g_lastError.c_str();
+}
+
+int c2d_gpu_clear(c2d_gpu_ctx* ctx)
+{
+    cudaSetDevice(ctx->device);
+    C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->flagLog.size = ctx->addLog.size = ctx->transLog.size = ctx->moveLog.size = 0;
+    ctx->rounds.clear();
+    std::fill(ctx->hostMeta.begin(), ctx->hostMeta.end(), 0u);
+    std::fill(ctx->stamp.begin(), ctx->stamp.end(), 0u);
+    ctx->shapeSlots = 0;
+    for (int b = 0; b < 3; ++b)
+    {
+        ctx->members[b].clear();
+        ctx->membersDirty[b] = true;
+        ctx->treeDirty[b] = true;
+        ctx->tree[b].n = 0;
+    }
+    if (ctx->capacity)
+        C2D_CUDA(ctx, cudaMemsetAsync(ctx->d.meta, 0, ctx->capacity * sizeof(uint32_t), ctx->stream));
+    return 0;
+}
+
+int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size)
+{
+    if (mode != C2D_BROADPHASE_LBVH && mode != C2D_BROADPHASE_GRID)
+        return fail(ctx, "c2d_gpu_set_broadphase: unknown mode");
+    ctx->broadphase = mode;
+    ctx->cellSize = cell_size ? cell_size : 120;
+    return 0;
+}
+
+int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world)
+{
+    if (world == 0 || rank >= world)
+        return fail(ctx, "c2d_gpu_set_shard: rank must be < world");
+    ctx->shardRank = rank;
+    ctx->shardWorld = world;
+    return 0;
+}
+
+int c2d_gpu_shape_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t entity_tag, uint32_t type, uint32_t body,
+                      uint32_t vertex_count, uint64_t category, uint64_t mask, const float* geom32, const c2d_xf* xf,
+                      const c2d_xf* prev)
+{
+    if (type > 3 || body > 2 || vertex_count > 8 || !geom32 || !xf)
+        return fail(ctx, "c2d_gpu_shape_add: bad argument");
+    claim(ctx, shape, PH_ADD);
+    if (ctx->hostMeta[shape] & META_ALIVE)
+        return fail(ctx, "c2d_gpu_shape_add: shape id is already in use");
+    AddRec* r = ctx->addLog.push();
+    if (!r)
+        return fail(ctx, "pinned host allocation failed");
+    const uint32_t meta = type | (body << META_BODY_SHIFT) | META_ACTIVE | META_ALIVE | (vertex_count << META_COUNT_SHIFT);
+    r->shape = shape;
+    r->entity = entity_tag;
+    r->meta = meta;
+    r->_pad = 0;
+    r->category = category;
+    r->mask = mask;
+    std::memcpy(r->xf, xf, sizeof(c2d_xf));
+    std::memcpy(r->prev, prev ? prev : xf, sizeof(c2d_xf));
+    std::memcpy(r->geom, geom32, sizeof(r->geom));
+    ctx->hostMeta[shape] = meta;
+    if (shape + 1 > ctx->shapeSlots)
+        ctx->shapeSlots = shape + 1;
+    member_add(ctx, shape, body);
+    return 0;
+}
+
+int c2d_gpu_shape_remove(c2d_gpu_ctx* ctx, uint32_t shape)
+{
+    if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
+        return fail(ctx, "c2d_gpu_shape_remove: unknown shape");
+    claim(ctx, shape, PH_FLAG);
+    FlagRec* r = ctx->flagLog.push();
+    if (!r)
+        return fail(ctx, "pinned host allocation failed");
+    r->shape = shape;
+    r->op = 0;
+    member_remove(ctx, shape, meta_body(ctx->hostMeta[shape]));
+    ctx->hostMeta[shape] &= ~META_ALIVE;
+    return 0;
+}
+
+int c2d_gpu_shape_set_active(c2d_gpu_ctx* ctx, uint32_t shape, int active)
+{
+    // like the reference (Registry.hpp:353-358) this also works on a removed shape's stale slot
+    if (shape >= ctx->hostMeta.size())
+        return fail(ctx, "c2d_gpu_shape_set_active: unknown shape");
+    claim(ctx, shape, PH_FLAG);
+    FlagRec* r = ctx->flagLog.push();
+    if (!r)
+        return fail(ctx, "pinned host allocation failed");
+    r->shape = shape;
+    r->op = active ? 1u : 2u;
+    return 0;
+}
+
+int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy)
+{
+    if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
+        return fail(ctx, "c2d_gpu_shape_translate: unknown shape");
+    claim(ctx, shape, PH_TRANS);
+    TransRec* r = ctx->transLog.push();
+    if (!r)
+        return fail(ctx, "pinned host allocation failed");
+    r->shape = shape;
+    r->dx = dx;
+    r->dy = dy;
+    r->_pad = 0;
+    ctx->treeDirty[meta_body(ctx->hostMeta[shape])] = true;
+    return 0;
+}
+
+int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy)
+{
+    if (!ctx->transLog.reserve(ctx->transLog.size + n))
+        return fail(ctx, "pinned host allocation failed");
+    for (uint32_t i = 0; i < n; ++i)
+        if (int rc = c2d_gpu_shape_translate(ctx, shapes[i], dxy[2 * i], dxy[2 * i + 1]))
+            return rc;
+    return 0;
+}
+
+int c2d_gpu_shape_move(c2d_gpu_ctx* ctx, uint32_t shape, const c2d_xf* xf)
+{
+    if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE) || !xf)
+        return fail(ctx, "c2d_gpu_shape_move: unknown shape");
+    claim(ctx, shape, PH_MOVE);
+    MoveRec* r = ctx->moveLog.push();
+    if (!r)
+        return fail(ctx, "pinned host allocation failed");
+    r->shape = shape;
+    r->tx = xf->tx;
+    r->ty = xf->ty;
+    r->angle = xf->angle;
+    r->sin = xf->sin;
+    r->cos = xf->cos;
+    r->csin = xf->csin;
+    r->ccos = xf->ccos;
+    ctx->treeDirty[meta_body(ctx->hostMeta[shape])] = true;
+    return 0;
+}
+
+int c2d_gpu_flush(c2d_gpu_ctx* ctx)
+{
+    cudaSetDevice(ctx->device);
+    return flush(ctx);
+}
+
+int c2d_gpu_collide(c2d_gpu_ctx* ctx, const c2d_pair_record** out_records, uint64_t* out_count, c2d_gpu_stats* stats)
+{
+    cudaSetDevice(ctx->device);
+    return run_pipeline(ctx, true, out_records, out_count, stats);
+}
+
+int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* stats)
+{
+    cudaSetDevice(ctx->device);
+    return run_pipeline(ctx, false, nullptr, out_count, stats);
+}
+
+#ifndef C2D_HAVE_RAYS
+int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t, const c2d_ray*, const c2d_hit_record**, const uint64_t**, c2d_gpu_stats*)
+{
+    return fail(ctx, "c2d_gpu_raycast: not built");
+}
+#endif
+
+int c2d_gpu_read_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* out_tight4, float* out_fat4)
+{
+    cudaSetDevice(ctx->device);
+    if (int rc = flush(ctx))
+        return rc;
+    if (static_cast<uint64_t>(first) + count > ctx->capacity)
+        return fail(ctx, "c2d_gpu_read_boxes: range out of bounds");
+    if (out_tight4)
+        C2D_CUDA(ctx, cudaMemcpyAsync(out_tight4, ctx->d.tight + first, count * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    if (out_fat4)
+        C2D_CUDA(ctx, cudaMemcpyAsync(out_fat4, ctx->d.fat + first, count * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+int c2d_gpu_read_candidates(c2d_gpu_ctx* ctx, uint64_t capacity, uint32_t* out_pairs2, uint64_t* out_count)
+{
+    cudaSetDevice(ctx->device);
+    if (out_count)
+        *out_count = ctx->lastCandidates;
+    const uint64_t n = std::min<uint64_t>(capacity, ctx->lastCandidates);
+    if (n && out_pairs2)
+    {
+        C2D_CUDA(ctx, cudaMemcpyAsync(out_pairs2, ctx->cand.ptr, n * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+        C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return 0;
+}
+
+} // extern "C"

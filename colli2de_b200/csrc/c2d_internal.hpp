@@ -1,0 +1,94 @@
+// c2d_internal.hpp — declarations shared by the translation units of libc2d_gpu.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace c2d_dev
+{
+
+// ---- per-shape meta word -------------------------------------------------------------------------
+// bits 0-1 ShapeType, 2-3 BodyType, 4 active (ShapeInstance::mIsActive), 5 alive (has a tree proxy),
+// bits 8-11 polygon vertex count.
+constexpr uint32_t META_TYPE_MASK = 0x3u;
+constexpr uint32_t META_BODY_SHIFT = 2;
+constexpr uint32_t META_ACTIVE = 1u << 4;
+constexpr uint32_t META_ALIVE = 1u << 5;
+constexpr uint32_t META_COUNT_SHIFT = 8;
+
+__host__ __device__ inline uint32_t meta_type(uint32_t m) { return m & META_TYPE_MASK; }
+__host__ __device__ inline uint32_t meta_body(uint32_t m) { return (m >> META_BODY_SHIFT) & 0x3u; }
+__host__ __device__ inline uint32_t meta_count(uint32_t m) { return (m >> META_COUNT_SHIFT) & 0xfu; }
+
+// ---- mutation log records (pinned host -> device) ---------------------------------------------------
+struct FlagRec // 8 B: remove / activate / deactivate
+{
+    uint32_t shape;
+    uint32_t op; // 0 remove, 1 activate, 2 deactivate
+};
+struct TransRec // 16 B: moveEntity(id, Translation) for one shape
+{
+    uint32_t shape;
+    float dx, dy;
+    uint32_t _pad;
+};
+struct MoveRec // 32 B: moveEntity(id, Transform) / teleportEntity(id, Transform) for one shape
+{
+    uint32_t shape;
+    float tx, ty, angle, sin, cos, csin, ccos;
+};
+struct AddRec // 224 B: addShape
+{
+    uint32_t shape, entity, meta, _pad;
+    uint64_t category, mask;
+    float xf[8];   // tx, ty, angle, sin, cos, csin, ccos, -
+    float prev[8]; // previous transform (bullets)
+    float geom[32];
+};
+static_assert(sizeof(FlagRec) == 8 && sizeof(TransRec) == 16 && sizeof(MoveRec) == 32 && sizeof(AddRec) == 224,
+              "log record layout");
+
+// ---- per-shape state in HBM (SoA) ---------------------------------------------------------------------
+struct ShapeArrays
+{
+    float4* xf;    // tx, ty, sin, cos          (entity transform, as stored by the reference)
+    float4* xa;    // angle, csin, ccos, 0
+    float4* pxf;   // previous transform (bullets): tx, ty, sin, cos
+    float4* pxa;   // previous: angle, csin, ccos, 0
+    float4* tight; // ShapeInstance::mBoundingBox   (minx, miny, maxx, maxy)
+    float4* fat;   // leaf box of the reference's DynamicBVH
+    uint32_t* meta;
+    uint32_t* entity;
+    uint64_t* category;
+    uint64_t* mask;
+    float* geom; // 32 floats per shape
+};
+
+// ---- LBVH node: both children's boxes live in the parent so one 64 B read serves both tests -------------
+struct __align__(16) BvhNode
+{
+    float4 boxL;
+    float4 boxR;
+    int left;  // >= 0: internal node index; < 0: leaf, sorted position = ~left
+    int right;
+    int lastL; // last sorted leaf position covered by the left / right subtree
+    int lastR;
+    uint64_t catL; // OR of the category bits below (BVHNode::mCategoryBits, DynamicBVH.hpp:440,478)
+    uint64_t catR;
+};
+static_assert(sizeof(BvhNode) == 64, "node is one 64-byte record");
+
+struct Tree
+{
+    uint32_t n;          // leaves
+    uint32_t* sorted;    // shape id by Morton rank
+    BvhNode* nodes;      // n - 1 internal nodes, root = 0
+};
+
+// radix sort (c2d_sort.cu)
+size_t sort_workspace_bytes(uint32_t n, int passes);
+int radix_sort_pairs(cudaStream_t stream, uint32_t* keys, uint32_t* vals, uint32_t* keysTmp, uint32_t* valsTmp,
+                     uint32_t n, int passes, void* workspace);
+
+} // namespace c2d_dev

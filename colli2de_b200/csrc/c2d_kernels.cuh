@@ -1,0 +1,632 @@
+// c2d_kernels.cuh — the sm_100a kernels of the getCollidingPairs pipeline.
+//
+//   K1  k_apply_flags / k_apply_adds / k_apply_translates / k_apply_moves   (mutation replay = AABB refit)
+//   K2  k_bounds / k_morton                                                (scene bounds, Morton keys)
+//   K3  radix sort                                                         (c2d_sort.cu)
+//   K4  k_karras_build / k_fit                                             (LBVH topology, bottom-up boxes)
+//   K5  k_traverse<SELF>                                                   (candidate pairs)
+//   K6  k_bin_* / k_narrow                                                 (binning by code path, manifolds, sweeps)
+//
+// All floating point on the parity path is binary32 without FMA contraction (-fmad=false).
+#pragma once
+
+#include "c2d_internal.hpp"
+#include "c2d_narrow.cuh"
+
+#include <cooperative_groups.h>
+
+namespace c2d_dev
+{
+
+namespace cg = cooperative_groups;
+
+// ---------------------------------------------------------------------------------------------------
+// K1 — mutation replay.  One thread per log record; records of one launch touch distinct shapes.
+// ---------------------------------------------------------------------------------------------------
+
+// DynamicBVH::moveProxy leaf rule with margin 0 (reference DynamicBVH.hpp:386-400, AABB.cpp:212-228):
+// keep the fat box if it still contains the target, else target grown by 2.2 x (target.min - fat.min)
+// in the direction of motion.
+__device__ __forceinline__ void fat_leaf_rule(float4* fatSlot, const Box& target)
+{
+    const Box fat = box_from(*fatSlot);
+    if (box_contains(fat, target))
+        return;
+    const float dispx = (target.minx - fat.minx) * 2.2f;
+    const float dispy = (target.miny - fat.miny) * 2.2f;
+    Box nf = target; // fattened(margin = 0)
+    if (dispx < 0.0f)
+        nf.minx += dispx;
+    else
+        nf.maxx += dispx;
+    if (dispy < 0.0f)
+        nf.miny += dispy;
+    else
+        nf.maxy += dispy;
+    *fatSlot = box_to(nf);
+}
+
+__global__ void __launch_bounds__(256) k_apply_flags(const FlagRec* __restrict__ log, uint32_t n, ShapeArrays s)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const FlagRec r = log[i];
+    uint32_t m = s.meta[r.shape];
+    if (r.op == 0)
+        m &= ~META_ALIVE;
+    else if (r.op == 1)
+        m |= META_ACTIVE;
+    else
+        m &= ~META_ACTIVE;
+    s.meta[r.shape] = m;
+}
+
+// Registry::addShape (reference Registry.hpp:272-330) + DynamicBVH::addProxy (DynamicBVH.hpp:352-365)
+__global__ void __launch_bounds__(128) k_apply_adds(const AddRec* __restrict__ log, uint32_t n, ShapeArrays s)
+{
+    // one warp per record: the 224-byte record is copied with coalesced loads, lane 0 finishes the boxes
+    const uint32_t warpId = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (warpId >= n)
+        return;
+    const AddRec* r = log + warpId;
+    const uint32_t shape = r->shape;
+    s.geom[static_cast<size_t>(shape) * 32 + lane] = r->geom[lane];
+    if (lane == 0)
+    {
+        const uint32_t meta = r->meta;
+        s.meta[shape] = meta;
+        s.entity[shape] = r->entity;
+        s.category[shape] = r->category;
+        s.mask[shape] = r->mask;
+        XF t;
+        t.tx = r->xf[0];
+        t.ty = r->xf[1];
+        t.s = r->xf[3];
+        t.c = r->xf[4];
+        s.xf[shape] = make_float4(t.tx, t.ty, t.s, t.c);
+        s.xa[shape] = make_float4(r->xf[2], r->xf[5], r->xf[6], 0.0f);
+        s.pxf[shape] = make_float4(r->prev[0], r->prev[1], r->prev[3], r->prev[4]);
+        s.pxa[shape] = make_float4(r->prev[2], r->prev[5], r->prev[6], 0.0f);
+        const Box b = compute_aabb(meta_type(meta), meta_count(meta), r->geom, t);
+        s.tight[shape] = box_to(b);
+        s.fat[shape] = box_to(b); // boundingBox.fattened(mFatAABBMargin = 0)
+    }
+}
+
+// Registry::moveEntity(id, Translation) (reference Registry.hpp:434-453, 214-231)
+__global__ void __launch_bounds__(256) k_apply_translates(const TransRec* __restrict__ log, uint32_t n, ShapeArrays s)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float4 raw = reinterpret_cast<const float4*>(log)[i];
+    const uint32_t shape = __float_as_uint(raw.x);
+    const float dx = raw.y, dy = raw.z;
+    const bool bullet = meta_body(s.meta[shape]) == 2u;
+
+    const Box old = box_from(s.tight[shape]);
+    Box nt; // AABB::translate: min += d; max += d (AABB.cpp:248-252)
+    nt.minx = old.minx + dx;
+    nt.miny = old.miny + dy;
+    nt.maxx = old.maxx + dx;
+    nt.maxy = old.maxy + dy;
+    s.tight[shape] = box_to(nt);
+    fat_leaf_rule(&s.fat[shape], bullet ? box_combine(old, nt) : nt);
+
+    float4 t = s.xf[shape];
+    if (bullet)
+    {
+        s.pxf[shape] = t; // mBulletPreviousTransforms[id] = entity.mTransform
+        s.pxa[shape] = s.xa[shape];
+    }
+    t.x += dx;
+    t.y += dy;
+    s.xf[shape] = t;
+}
+
+// Registry::moveEntity(id, Transform) / teleportEntity(id, Transform) (reference Registry.hpp:382-432, 191-212)
+__global__ void __launch_bounds__(256) k_apply_moves(const MoveRec* __restrict__ log, uint32_t n, ShapeArrays s)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float4 r0 = reinterpret_cast<const float4*>(log)[2 * i];
+    const float4 r1 = reinterpret_cast<const float4*>(log)[2 * i + 1];
+    const uint32_t shape = __float_as_uint(r0.x);
+    XF t;
+    t.tx = r0.y;
+    t.ty = r0.z;
+    t.s = r1.x;
+    t.c = r1.y;
+    const uint32_t meta = s.meta[shape];
+    const bool bullet = meta_body(meta) == 2u;
+
+    const Box old = box_from(s.tight[shape]);
+    const Box nt = compute_aabb(meta_type(meta), meta_count(meta), s.geom + static_cast<size_t>(shape) * 32, t);
+    s.tight[shape] = box_to(nt);
+    fat_leaf_rule(&s.fat[shape], bullet ? box_combine(old, nt) : nt);
+    if (bullet)
+    {
+        s.pxf[shape] = s.xf[shape];
+        s.pxa[shape] = s.xa[shape];
+    }
+    s.xf[shape] = make_float4(t.tx, t.ty, t.s, t.c);
+    s.xa[shape] = make_float4(r0.w, r1.z, r1.w, 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2 — bounds of the leaf-box centres and Morton keys
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t float_to_ordered(float f)
+{
+    const uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+// frame scratch: [0..3] bounds tree 0 (minx, miny, maxx, maxy as ordered uints), [4..7] tree 1, [8..11] tree 2,
+// then counters.
+struct FrameScratch
+{
+    uint32_t bounds[3][4];
+    uint32_t candCount;
+    uint32_t outCount;
+    uint32_t clipOverflow;
+    uint32_t _pad;
+    uint32_t binCount[16];
+    uint32_t binOffset[16];
+    uint32_t binCursor[16];
+};
+
+__global__ void k_frame_init(FrameScratch* fs)
+{
+    const int t = threadIdx.x;
+    if (t < 12)
+        fs->bounds[t / 4][t % 4] = (t % 4) < 2 ? 0xffffffffu : 0u;
+    if (t == 12)
+        fs->candCount = 0;
+    if (t == 13)
+        fs->outCount = 0;
+    if (t == 14)
+        fs->clipOverflow = 0;
+    if (t >= 16 && t < 32)
+    {
+        fs->binCount[t - 16] = 0;
+        fs->binOffset[t - 16] = 0;
+        fs->binCursor[t - 16] = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bounds(const uint32_t* __restrict__ members, uint32_t n,
+                                                const float4* __restrict__ fat, uint32_t* bounds4)
+{
+    float minx = FLT_MAX, miny = FLT_MAX, maxx = -FLT_MAX, maxy = -FLT_MAX;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4 b = fat[members[i]];
+        const float cx = 0.5f * (b.x + b.z), cy = 0.5f * (b.y + b.w);
+        minx = fminf(minx, cx);
+        miny = fminf(miny, cy);
+        maxx = fmaxf(maxx, cx);
+        maxy = fmaxf(maxy, cy);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, o));
+        miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, o));
+        maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, o));
+        maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, o));
+    }
+    if ((threadIdx.x & 31) == 0 && minx <= maxx)
+    {
+        atomicMin(&bounds4[0], float_to_ordered(minx));
+        atomicMin(&bounds4[1], float_to_ordered(miny));
+        atomicMax(&bounds4[2], float_to_ordered(maxx));
+        atomicMax(&bounds4[3], float_to_ordered(maxy));
+    }
+}
+
+__device__ __forceinline__ uint32_t spread16(uint32_t v)
+{
+    v &= 0xffffu;
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const uint32_t* __restrict__ members, uint32_t n,
+                                                const float4* __restrict__ fat, const uint32_t* __restrict__ bounds4,
+                                                uint32_t* __restrict__ keys, uint32_t* __restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float minx = ordered_to_float(bounds4[0]), miny = ordered_to_float(bounds4[1]);
+    const float maxx = ordered_to_float(bounds4[2]), maxy = ordered_to_float(bounds4[3]);
+    const float ex = maxx - minx, ey = maxy - miny;
+    const float sx = ex > 0.0f ? 65535.0f / ex : 0.0f;
+    const float sy = ey > 0.0f ? 65535.0f / ey : 0.0f;
+    const uint32_t shape = members[i];
+    const float4 b = fat[shape];
+    const float cx = 0.5f * (b.x + b.z), cy = 0.5f * (b.y + b.w);
+    const uint32_t qx = static_cast<uint32_t>(fminf(fmaxf((cx - minx) * sx, 0.0f), 65535.0f));
+    const uint32_t qy = static_cast<uint32_t>(fminf(fmaxf((cy - miny) * sy, 0.0f), 65535.0f));
+    keys[i] = spread16(qx) | (spread16(qy) << 1);
+    vals[i] = shape;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4 — LBVH topology (Karras 2012) and bottom-up fit
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int karras_delta(const uint32_t* __restrict__ keys, int n, int i, uint32_t ki, int j)
+{
+    if (j < 0 || j >= n)
+        return -1;
+    const uint32_t kj = keys[j];
+    if (ki == kj)
+        return 32 + __clz(static_cast<uint32_t>(i) ^ static_cast<uint32_t>(j));
+    return __clz(ki ^ kj);
+}
+
+// parent code: (parent index << 1) | (1 if right child)
+__global__ void __launch_bounds__(256) k_karras_build(const uint32_t* __restrict__ keys, int n, BvhNode* nodes,
+                                                      int* __restrict__ nodeParent, int* __restrict__ leafParent)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n - 1)
+        return;
+    const uint32_t ki = keys[i];
+    const int d = (karras_delta(keys, n, i, ki, i + 1) - karras_delta(keys, n, i, ki, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = karras_delta(keys, n, i, ki, i - d);
+    int lmax = 2;
+    while (karras_delta(keys, n, i, ki, i + lmax * d) > dmin)
+        lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (karras_delta(keys, n, i, ki, i + (l + t) * d) > dmin)
+            l += t;
+    const int j = i + l * d;
+    const int dnode = karras_delta(keys, n, i, ki, j);
+    int s = 0;
+    int t = l;
+    do
+    {
+        t = (t + 1) >> 1;
+        if (karras_delta(keys, n, i, ki, i + (s + t) * d) > dnode)
+            s += t;
+    } while (t > 1);
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+
+    int left, right;
+    if (lo == gamma)
+    {
+        left = ~gamma;
+        leafParent[gamma] = (i << 1);
+    }
+    else
+    {
+        left = gamma;
+        nodeParent[gamma] = (i << 1);
+    }
+    if (hi == gamma + 1)
+    {
+        right = ~(gamma + 1);
+        leafParent[gamma + 1] = (i << 1) | 1;
+    }
+    else
+    {
+        right = gamma + 1;
+        nodeParent[gamma + 1] = (i << 1) | 1;
+    }
+    nodes[i].left = left;
+    nodes[i].right = right;
+    nodes[i].lastL = gamma;
+    nodes[i].lastR = hi;
+    if (i == 0)
+        nodeParent[0] = -1;
+}
+
+__global__ void __launch_bounds__(256) k_fit(int n, const uint32_t* __restrict__ sorted, const float4* __restrict__ fat,
+                                             const uint64_t* __restrict__ category, BvhNode* nodes,
+                                             const int* __restrict__ nodeParent, const int* __restrict__ leafParent,
+                                             uint32_t* arrival)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n)
+        return;
+    const uint32_t shape = sorted[p];
+    float4 box = fat[shape];
+    uint64_t cat = category[shape];
+    int code = leafParent[p];
+    while (true)
+    {
+        const int q = code >> 1;
+        const bool right = code & 1;
+        BvhNode* node = nodes + q;
+        if (right)
+        {
+            node->boxR = box;
+            node->catR = cat;
+        }
+        else
+        {
+            node->boxL = box;
+            node->catL = cat;
+        }
+        __threadfence();
+        const uint32_t old = atomicAdd(&arrival[q], 1u);
+        if (old == 0)
+            return; // the sibling subtree is not finished: its last thread continues upward
+        __threadfence();
+        const float4 sib = __ldcg(right ? &node->boxL : &node->boxR);
+        const uint64_t sibCat = __ldcg(reinterpret_cast<const unsigned long long*>(right ? &node->catL : &node->catR));
+        box.x = fminf(box.x, sib.x);
+        box.y = fminf(box.y, sib.y);
+        box.z = fmaxf(box.z, sib.z);
+        box.w = fmaxf(box.w, sib.w);
+        cat |= sibCat;
+        if (q == 0)
+            return;
+        code = nodeParent[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5 — traversal: one query leaf per thread, candidate pairs appended with warp-aggregated atomics.
+// Replaces DynamicBVH::findAllCollisions self / cross (reference DynamicBVH.hpp:931-1031): a pair is a
+// candidate iff (categoryA & categoryB) != 0 (matchesMask, DynamicBVH.hpp:50-53,955) and the two LEAF
+// (fat) boxes intersect, all four comparisons non-strict (AABB.cpp:34-37).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit_pair(uint32_t a, uint32_t b, uint2* __restrict__ out, uint32_t capacity,
+                                          uint32_t* counter)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0)
+        base = atomicAdd(counter, g.size());
+    base = g.shfl(base, 0);
+    const uint32_t idx = base + g.thread_rank();
+    if (idx < capacity)
+        out[idx] = make_uint2(a, b);
+}
+
+template <bool SELF>
+__global__ void __launch_bounds__(128)
+    k_traverse(const uint32_t* __restrict__ qSorted, uint32_t qn, uint32_t qLo, uint32_t qHi,
+               const uint32_t* __restrict__ tSorted, uint32_t tn, const BvhNode* __restrict__ nodes,
+               const float4* __restrict__ fat, const uint64_t* __restrict__ category, uint2* __restrict__ out,
+               uint32_t capacity, uint32_t* counter)
+{
+    const uint32_t i = qLo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= qHi || i >= qn || tn == 0)
+        return;
+    const uint32_t qs = qSorted[i];
+    const float4 qb = fat[qs];
+    const uint64_t qc = category[qs];
+
+    if (tn == 1)
+    {
+        if (!SELF)
+        {
+            const uint32_t ts = tSorted[0];
+            if ((qc & category[ts]) != 0 && box_overlap(qb, fat[ts]))
+                emit_pair(qs, ts, out, capacity, counter);
+        }
+        return;
+    }
+
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    while (true)
+    {
+        const float4* np = reinterpret_cast<const float4*>(nodes + node);
+        const float4 boxL = __ldg(np);
+        const float4 boxR = __ldg(np + 1);
+        const int4 links = __ldg(reinterpret_cast<const int4*>(np + 2));
+        const ulonglong2 cats = __ldg(reinterpret_cast<const ulonglong2*>(np + 3));
+        bool hitL = box_overlap(qb, boxL) && (qc & cats.x) != 0 && (!SELF || links.z > static_cast<int>(i));
+        bool hitR = box_overlap(qb, boxR) && (qc & cats.y) != 0 && (!SELF || links.w > static_cast<int>(i));
+        if (hitL && links.x < 0)
+        {
+            const uint32_t ts = tSorted[~links.x];
+            if (SELF)
+                emit_pair(min(qs, ts), max(qs, ts), out, capacity, counter);
+            else
+                emit_pair(qs, ts, out, capacity, counter);
+            hitL = false;
+        }
+        if (hitR && links.y < 0)
+        {
+            const uint32_t ts = tSorted[~links.y];
+            if (SELF)
+                emit_pair(min(qs, ts), max(qs, ts), out, capacity, counter);
+            else
+                emit_pair(qs, ts, out, capacity, counter);
+            hitR = false;
+        }
+        if (hitL)
+        {
+            if (hitR && sp < 64)
+                stack[sp++] = links.y;
+            node = links.x;
+        }
+        else if (hitR)
+        {
+            node = links.y;
+        }
+        else
+        {
+            if (sp == 0)
+                break;
+            node = stack[--sp];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K6 — narrowphase.  Candidates are binned by (mode, core) so a warp runs one code path:
+//   mode 0 collide (no bullet), 1 sweep with A = bullet moving, 2 sweep with both moving
+//   (narrowPhaseCollision, reference Registry.hpp:608-710).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pair_bin(uint32_t ma, uint32_t mb)
+{
+    const bool ba = meta_body(ma) == 2u, bb = meta_body(mb) == 2u;
+    const int mode = (ba && bb) ? 2 : ((ba || bb) ? 1 : 0);
+    return mode * CORE_COUNT + core_of(static_cast<int>(meta_type(ma)), static_cast<int>(meta_type(mb)));
+}
+
+__global__ void __launch_bounds__(256) k_bin_count(const uint2* __restrict__ cand, uint32_t capacity,
+                                                   const uint32_t* __restrict__ meta, FrameScratch* fs)
+{
+    __shared__ uint32_t sh[16];
+    if (threadIdx.x < 16)
+        sh[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t n = min(fs->candCount, capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint2 p = cand[i];
+        atomicAdd(&sh[pair_bin(meta[p.x], meta[p.y])], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 16 && sh[threadIdx.x])
+        atomicAdd(&fs->binCount[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void k_bin_scan(FrameScratch* fs)
+{
+    if (threadIdx.x == 0)
+    {
+        uint32_t run = 0;
+        for (int b = 0; b < 16; ++b)
+        {
+            fs->binOffset[b] = run;
+            run += fs->binCount[b];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(const uint2* __restrict__ cand, uint32_t capacity,
+                                                     const uint32_t* __restrict__ meta, FrameScratch* fs,
+                                                     uint2* __restrict__ binned)
+{
+    const uint32_t n = min(fs->candCount, capacity);
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count so the full-mask match below is always convergent
+    for (uint32_t base0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base0 < n; base0 += gridDim.x * blockDim.x)
+    {
+        const uint32_t i = base0 + lane;
+        const bool valid = i < n;
+        uint2 p = make_uint2(0, 0);
+        int bin = 31;
+        if (valid)
+        {
+            p = cand[i];
+            bin = pair_bin(meta[p.x], meta[p.y]);
+        }
+        // warp-aggregated cursor bump per bin
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (valid && lane == leader)
+            base = atomicAdd(&fs->binCursor[bin], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid)
+            binned[fs->binOffset[bin] + base + __popc(peers & ((1u << lane) - 1u))] = p;
+    }
+}
+
+__device__ __forceinline__ XF xf_from(float4 f)
+{
+    XF t;
+    t.tx = f.x;
+    t.ty = f.y;
+    t.s = f.z;
+    t.c = f.w;
+    return t;
+}
+
+struct PairOut // 84 bytes, = Registry<uint32_t>::EntityCollision
+{
+    uint32_t entityA, entityB, shapeA, shapeB;
+    float manifold[17];
+};
+
+__global__ void __launch_bounds__(128) k_narrow(const uint2* __restrict__ binned, uint32_t capacity, ShapeArrays s,
+                                                FrameScratch* fs, PairOut* __restrict__ out, uint32_t outCapacity)
+{
+    const uint32_t n = min(fs->candCount, capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint2 p = binned[i];
+        const uint32_t ma = s.meta[p.x], mb = s.meta[p.y];
+        const uint32_t ea = s.entity[p.x], eb = s.entity[p.y];
+        // self-collision and inactive shapes are rejected here, not in the broadphase (Registry.hpp:619-624)
+        if (ea == eb || !(ma & META_ACTIVE) || !(mb & META_ACTIVE))
+            continue;
+        ShapeRef A, B;
+        A.type = static_cast<int>(meta_type(ma));
+        A.count = static_cast<int>(meta_count(ma));
+        A.g = s.geom + static_cast<size_t>(p.x) * 32;
+        B.type = static_cast<int>(meta_type(mb));
+        B.count = static_cast<int>(meta_count(mb));
+        B.g = s.geom + static_cast<size_t>(p.y) * 32;
+        const XF xa = xf_from(s.xf[p.x]);
+        const XF xb = xf_from(s.xf[p.y]);
+        const bool ba = meta_body(ma) == 2u, bb = meta_body(mb) == 2u;
+
+        Manifold m;
+        bool hit;
+        if (!ba && !bb)
+        {
+            hit = narrow_test<true>(A, xa, B, xb, m);
+        }
+        else
+        {
+            // A is the bullet whenever exactly one side is (cross-tree pairs are emitted bullet-first)
+            const float4 pa = s.pxf[p.x], paa = s.pxa[p.x], ca = s.xa[p.x];
+            const Motion moA = motion_between(xf_from(pa), paa.x, paa.y, paa.z, xa, ca.x);
+            Motion moB;
+            if (bb)
+            {
+                const float4 pb = s.pxf[p.y], pba = s.pxa[p.y], cb = s.xa[p.y];
+                moB = motion_between(xf_from(pb), pba.x, pba.y, pba.z, xb, cb.x);
+            }
+            else
+                moB = motion_fixed(xb);
+            float fraction;
+            // a sweep hit is reported even if the final collide() yields no point (Registry.hpp:644,709:
+            // the optional holds the manifold as soon as sweep() returned a value)
+            hit = narrow_sweep(A, moA, B, moB, fraction, m);
+        }
+        if (!hit)
+            continue;
+        cg::coalesced_group g = cg::coalesced_threads();
+        uint32_t base = 0;
+        if (g.thread_rank() == 0)
+            base = atomicAdd(&fs->outCount, g.size());
+        base = g.shfl(base, 0);
+        const uint32_t idx = base + g.thread_rank();
+        if (idx < outCapacity)
+        {
+            PairOut* o = out + idx;
+            o->entityA = ea;
+            o->entityB = eb;
+            o->shapeA = p.x;
+            o->shapeB = p.y;
+            manifold_store(m, o->manifold);
+        }
+    }
+}
+
+} // namespace c2d_dev

@@ -1,0 +1,199 @@
+/*
+ * c2d_gpu.h — the C ABI of libc2d_gpu.so: the B200 (sm_100a) implementation of
+ * Colli2De's per-frame collision query path.
+ *
+ * The reference has no FFI/plugin interface: its boundary is the C++ class
+ * c2d::Registry<EntityId, Method> (reference include/colli2de/Registry.hpp:40-106).
+ * In this repo that class (include/colli2de/Registry.hpp) is a host-side mirror
+ * that owns ids and transform arithmetic and forwards everything else through
+ * the entry points below.  Every entry point cites the reference code it
+ * replaces.  All functions return 0 on success and a non-zero code on failure
+ * (c2d_gpu_last_error gives the message); no exceptions cross this boundary.
+ * Plain pointers and sizes only.  One context per Registry; calls on one
+ * context must be serialised by the caller (the reference Registry is not
+ * thread safe for mutation either, README.md:142).
+ *
+ * Shapes are addressed by the Registry's ShapeId (dense, recycled LIFO by the
+ * host, Registry.hpp:283-289).  The device keeps, per shape: type, body type,
+ * active/alive bits, entity tag, category bits, the entity transform
+ * (tx, ty, angle, sin, cos) and - for bullets - the previous transform, the
+ * tight AABB (ShapeInstance::mBoundingBox, Registry.hpp:117) and the fat leaf
+ * AABB (BVHNode::mBoundingBox of the leaf, DynamicBVH.hpp:31), plus geometry.
+ *
+ * Mutations are LOGGED on the host in pinned memory and replayed on the device
+ * by the refit kernels at the next query (or c2d_gpu_flush), in an order that
+ * preserves per-shape program order.
+ */
+#ifndef C2D_GPU_H
+#define C2D_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct c2d_gpu_ctx c2d_gpu_ctx;
+
+/* Shape / body codes: c2d::ShapeType (Shapes.hpp:15-21) and c2d::BodyType (Registry.hpp:27-32). */
+enum { C2D_CIRCLE = 0, C2D_CAPSULE = 1, C2D_SEGMENT = 2, C2D_POLYGON = 3 };
+enum { C2D_STATIC = 0, C2D_DYNAMIC = 1, C2D_BULLET = 2 };
+/* Broadphase: LBVH (PartitioningMethod::None, the parity target) or uniform grid (PartitioningMethod::Grid). */
+enum { C2D_BROADPHASE_LBVH = 0, C2D_BROADPHASE_GRID = 1 };
+
+/* Transform as uploaded: the raw fields of c2d::Transform (Transform.hpp:122-126) plus the libm
+ * sinf/cosf of `angle` (`csin`, `ccos`) that Transform(Vec2, float) would produce; sweeps re-derive
+ * sin/cos from the angle (Collision.hpp:89-91) while collide() uses the stored, possibly drifted,
+ * sin/cos.  32 bytes. */
+typedef struct c2d_xf
+{
+    float tx, ty, angle, sin, cos, csin, ccos, _pad;
+} c2d_xf;
+
+/* Geometry slot, 32 floats:
+ *   circle  : cx, cy, r                      (Shapes.hpp:39-43)
+ *   capsule : c1x, c1y, c2x, c2y, r          (Shapes.hpp:64-69)
+ *   segment : sx, sy, ex, ey                 (Shapes.hpp:93-96)
+ *   polygon : v[0..7] (x,y) in [0,16), normals[0..7] (x,y) in [16,32)   (Shapes.hpp:118-122) */
+#define C2D_GEOM_FLOATS 32
+
+/* Output record of getCollidingPairs: byte-identical to
+ * Registry<uint32_t>::EntityCollision (Registry.hpp:44-51) = 84 bytes. */
+typedef struct c2d_manifold_point
+{
+    float point[2], anchorA[2], anchorB[2], separation;
+} c2d_manifold_point;
+typedef struct c2d_manifold
+{
+    float normal[2];
+    c2d_manifold_point points[2];
+    uint8_t pointCount;
+    uint8_t _pad[3];
+} c2d_manifold;
+typedef struct c2d_pair_record
+{
+    uint32_t entityA, entityB; /* the entity tags given to c2d_gpu_shape_add */
+    uint32_t shapeA, shapeB;
+    c2d_manifold manifold;
+} c2d_pair_record;
+
+/* Output record of rayCast: RaycastHit<pair<uint32_t, ShapeId>> (Ray.hpp:22-30) = 32 bytes. */
+typedef struct c2d_hit_record
+{
+    uint32_t entity, shape;
+    float entry[2], exit[2], entryTime, exitTime;
+} c2d_hit_record;
+
+/* Ray as uploaded: start, then end (finite, Ray.hpp:10-14) or direction (infinite, Ray.hpp:16-20). */
+typedef struct c2d_ray
+{
+    float sx, sy, ex, ey;
+    uint64_t mask; /* maskBits of rayCast (Registry.hpp:1052) */
+    uint32_t infinite;
+    uint32_t _pad;
+} c2d_ray;
+
+/* Per-query statistics.  Times are CUDA-event milliseconds on the context's stream. */
+typedef struct c2d_gpu_stats
+{
+    uint64_t shapes_alive;    /* proxies in the three trees */
+    uint64_t candidates;      /* broadphase pairs (fat AABB overlap & category match) */
+    uint64_t pairs;           /* colliding pairs returned */
+    uint64_t h2d_bytes;       /* mutation log bytes uploaded by this call */
+    uint64_t d2h_bytes;       /* result bytes downloaded by this call */
+    uint32_t kernel_launches; /* kernels launched by this call */
+    uint32_t retries;         /* pair-buffer overflow re-runs */
+    float ms_refit;           /* mutation replay (K1) */
+    float ms_build;           /* bounds + morton + sort + tree build + fit (K2-K4) */
+    float ms_broad;           /* traversal (K5) */
+    float ms_narrow;          /* binning + narrowphase/sweeps (K6/K7) */
+    float ms_device;          /* first kernel -> last kernel */
+    float ms_total;           /* host wall clock of the call incl. copies */
+} c2d_gpu_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+/* Registry() / Registry(cellSize) (Registry.hpp:53-59).  `device` < 0 selects the current device. */
+int c2d_gpu_create(int device, c2d_gpu_ctx** out_ctx);
+void c2d_gpu_destroy(c2d_gpu_ctx* ctx);
+/* Message of the last failure on `ctx` (or of the last stateless/creation failure when ctx is NULL). */
+const char* c2d_gpu_last_error(c2d_gpu_ctx* ctx);
+/* Registry::clear (Registry.hpp:1190-1203). */
+int c2d_gpu_clear(c2d_gpu_ctx* ctx);
+/* PartitioningMethod::None -> LBVH; PartitioningMethod::Grid(cellSize) -> uniform grid (BroadPhaseTree.hpp:96). */
+int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size);
+/* Multi-GPU sharding of the query leaves: this context emits only the pairs whose
+ * query leaf lies in Morton-rank slab `rank` of `world`.  Default 0 of 1. */
+int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world);
+
+/* ---- mutation log ----------------------------------------------------------------------------- */
+/* Registry::addShape (Registry.hpp:272-330): tight AABB = computeAABB(shape, xf) (ShapesUtils.hpp:13-60),
+ * leaf AABB = tight.fattened(0) (DynamicBVH.hpp:352-365).  `prev` is the bullet's previous transform
+ * (Registry.hpp:167); pass NULL for `prev` to use `xf`. */
+int c2d_gpu_shape_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t entity_tag, uint32_t type, uint32_t body,
+                      uint32_t vertex_count, uint64_t category, uint64_t mask, const float* geom32,
+                      const c2d_xf* xf, const c2d_xf* prev);
+/* Registry::removeShape / removeEntity (Registry.hpp:332-380): the proxy leaves its tree. */
+int c2d_gpu_shape_remove(c2d_gpu_ctx* ctx, uint32_t shape);
+/* Registry::setShapeActive (Registry.hpp:353-358). */
+int c2d_gpu_shape_set_active(c2d_gpu_ctx* ctx, uint32_t shape, int active);
+/* Registry::moveEntity(id, Translation) per shape (Registry.hpp:434-453 -> translateDynamicShape /
+ * translateBulletShape 214-231 -> DynamicBVH::moveProxy 386-417): tight box shifted, bullets sweep
+ * combine(old, new), fat-leaf rule, previous transform captured for bullets, translation += d. */
+int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy);
+int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy);
+/* Registry::moveEntity(id, Transform) / teleportEntity(id, Transform) per shape (Registry.hpp:382-432 ->
+ * moveDynamicShape / moveBulletShape 191-212): tight = computeAABB at the new transform `xf`
+ * (the host has already applied Transform += delta), same leaf rule. */
+int c2d_gpu_shape_move(c2d_gpu_ctx* ctx, uint32_t shape, const c2d_xf* xf);
+/* Replays the log on the device now (otherwise done by the next query). */
+int c2d_gpu_flush(c2d_gpu_ctx* ctx);
+
+/* ---- queries ---------------------------------------------------------------------------------- */
+/* Registry::getCollidingPairs (Registry.hpp:464-549): broadphase (DynamicBVH::findAllCollisions x5,
+ * DynamicBVH.hpp:931-1031) + narrowphase (narrowPhaseCollision, Registry.hpp:608-710; collide / sweep).
+ * *out_records points at context-owned pinned host memory valid until the next call on ctx.
+ * Same-tree pairs are emitted with shapeA < shapeB; cross-tree pairs with A on the Dynamic/Bullet side.
+ * Groups appear in the reference's order (Dyn x Static, Dyn x Dyn, Bullet x Static, Bullet x Dyn,
+ * Bullet x Bullet), each sorted by (shapeA, shapeB).  `stats` may be NULL. */
+int c2d_gpu_collide(c2d_gpu_ctx* ctx, const c2d_pair_record** out_records, uint64_t* out_count,
+                    c2d_gpu_stats* stats);
+/* Same pipeline, results left on the device (no D2H of records): used to time the device-resident path.
+ * out_count receives the number of colliding pairs. */
+int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* stats);
+/* Registry::rayCast x n (Registry.hpp:1050-1182; DynamicBVH::piercingRaycast 775-806/853-884;
+ * raycast(shape) RaycastShapes.cpp; sweep(shape, ray) Collision.hpp:323-344).  Hits of ray i are
+ * out_hits[out_offsets[i] .. out_offsets[i+1]) ordered by (entryTime, exitTime) with exact-key
+ * duplicates dropped like std::set does.  Buffers are context-owned pinned memory. */
+int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, const c2d_hit_record** out_hits,
+                    const uint64_t** out_offsets, c2d_gpu_stats* stats);
+
+/* ---- introspection (secondary oracles) --------------------------- */
+/* Tight (ShapeInstance::mBoundingBox) and fat (leaf) AABBs as (minx, miny, maxx, maxy); flushes first. */
+int c2d_gpu_read_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* out_tight4, float* out_fat4);
+/* Broadphase candidate pairs of the last c2d_gpu_collide call (shapeA, shapeB), unsorted. */
+int c2d_gpu_read_candidates(c2d_gpu_ctx* ctx, uint64_t capacity, uint32_t* out_pairs2, uint64_t* out_count);
+
+/* ---- stateless batches of the narrowphase free functions ----------------------------------------- */
+/* geom: n x 32 floats (layout above); xf5: n x (tx, ty, angle, sin, cos); out arrays may be NULL. */
+/* c2d::collide / c2d::areColliding for all 16 type pairs (Collision.cpp:15-748). */
+int c2d_gpu_collide_batch(uint32_t n, const uint8_t* typeA, const float* geomA, const uint8_t* cntA,
+                          const float* xfA5, const uint8_t* typeB, const float* geomB, const uint8_t* cntB,
+                          const float* xfB5, void* out_manifold68, uint8_t* out_are_colliding);
+/* c2d::sweep one-moving (mode 1, Collision.hpp:246-265) / two-moving (mode 2, Collision.hpp:280-307). */
+int c2d_gpu_sweep_batch(uint32_t n, int mode, const uint8_t* typeA, const float* geomA, const uint8_t* cntA,
+                        const float* xfA5, const float* xfA5_end, const uint8_t* typeB, const float* geomB,
+                        const uint8_t* cntB, const float* xfB5, const float* xfB5_end, float* out_fraction,
+                        void* out_manifold68, uint8_t* out_hit);
+/* c2d::raycast(shape, T, ray) (RaycastShapes.cpp:11-320); with xf5_end != NULL: c2d::sweep(shape, T0, T1, ray)
+ * (Collision.hpp:323-344).  ray4 = start.xy + end.xy | direction.xy. */
+int c2d_gpu_raycast_shape_batch(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt,
+                                const float* xf5, const float* xf5_end, const float* ray4,
+                                const uint8_t* infinite, float* out_times2, uint8_t* out_hit);
+/* c2d::computeAABB (ShapesUtils.hpp:13-60). */
+int c2d_gpu_compute_aabb_batch(uint32_t n, const uint8_t* type, const float* geom, const uint8_t* cnt,
+                               const float* xf5, float* out_aabb4);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2D_GPU_H */

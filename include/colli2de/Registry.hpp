@@ -1,0 +1,648 @@
+// colli2de-b200 — c2d::Registry<EntityId, Method>: the drop-in front end of the B200 collision query path.
+//
+// Same public signatures as the reference's include/colli2de/Registry.hpp:40-106, but the class is a
+// HOST-SIDE MIRROR: it owns what must stay on the host —
+//   * the EntityId -> dense entity index map and the entity transforms, with the reference's exact
+//     transform arithmetic (Transform += delta incl. the Rotation::operator+= quirk, SURVEY.md D5;
+//     bullet previous-transform capture, Registry.hpp:167,396-397,419-420,449-450),
+//   * ShapeId allocation with LIFO recycling (Registry.hpp:283-289,345,372),
+// and forwards everything else through the C ABI of libc2d_gpu.so (include/c2d_gpu.h): per-shape mutation
+// records are logged and replayed by the sm_100a refit kernels, getCollidingPairs()/rayCast() run the
+// LBVH broadphase + narrowphase kernels and return the reference's value types.
+//
+// There is NO CPU fallback: constructing a Registry without a CUDA device throws std::runtime_error.
+//
+// Differences a caller can observe (all documented in DESIGN.md):
+//   * the Registry is movable but not copyable (it owns device state);
+//   * inside one group of getCollidingPairs() the order of the pairs is by (shapeA, shapeB) as in the
+//     reference, but same-tree pairs always come out with shapeA < shapeB (the reference's A/B for those
+//     depends on its tree topology);
+//   * extensions: moveEntities() (batched moveEntity), lastQueryStats().
+#pragma once
+
+#include <colli2de/Manifold.hpp>
+#include <colli2de/Ray.hpp>
+#include <colli2de/Shapes.hpp>
+#include <colli2de/Transform.hpp>
+#include <colli2de/internal/utils/Debug.hpp>
+
+#include <c2d_gpu.h>
+
+#include <bit>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <optional>
+#include <set>
+#include <span>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+namespace c2d
+{
+
+using ShapeId = uint32_t;
+using BitMaskType = uint64_t;
+
+inline constexpr uint8_t bodyTypesCount = 3;
+enum class BodyType : uint8_t
+{
+    Static = 0,
+    Dynamic,
+    Bullet,
+};
+
+enum class PartitioningMethod
+{
+    None = 0, // LBVH broadphase (the parity target)
+    Grid,     // uniform-grid broadphase
+};
+
+namespace detail
+{
+
+// EntityId -> dense index.  Open addressing over 32-bit slots; the keys themselves live in the entity array,
+// so a lookup touches one slot run plus one entity record.
+template <typename EntityId, typename KeyOf>
+class IndexMap
+{
+  public:
+    static constexpr uint32_t npos = 0xffffffffu;
+
+    uint32_t find(const EntityId& id, const KeyOf& keyOf) const
+    {
+        if (mSlots.empty())
+            return npos;
+        for (size_t pos = home(id);; pos = (pos + 1) & mMask)
+        {
+            const uint32_t slot = mSlots[pos];
+            if (slot == kEmpty)
+                return npos;
+            if (slot != kTomb && keyOf(slot - 2) == id)
+                return slot - 2;
+        }
+    }
+
+    // precondition: !needsRehash()
+    void insert(const EntityId& id, uint32_t index)
+    {
+        size_t pos = home(id);
+        while (mSlots[pos] != kEmpty && mSlots[pos] != kTomb)
+            pos = (pos + 1) & mMask;
+        if (mSlots[pos] == kEmpty)
+            ++mUsed;
+        mSlots[pos] = index + 2;
+    }
+
+    bool needsRehash() const { return mSlots.empty() || (mUsed + 1) * 10 >= mSlots.size() * 7; }
+
+    // rebuilds the table (dropping tombstones) with room for twice the live entries
+    void rehash(const KeyOf& keyOf, const std::vector<uint32_t>& liveIndices)
+    {
+        size_t cap = 16;
+        while (cap * 7 < (liveIndices.size() + 1) * 2 * 10)
+            cap *= 2;
+        mSlots.assign(cap, kEmpty);
+        mMask = cap - 1;
+        mShift = 64 - std::countr_zero(cap);
+        mUsed = 0;
+        for (uint32_t idx : liveIndices)
+            insert(keyOf(idx), idx);
+    }
+
+    void erase(const EntityId& id, const KeyOf& keyOf)
+    {
+        for (size_t pos = home(id);; pos = (pos + 1) & mMask)
+        {
+            const uint32_t slot = mSlots[pos];
+            if (slot == kEmpty)
+                return;
+            if (slot != kTomb && keyOf(slot - 2) == id)
+            {
+                mSlots[pos] = kTomb;
+                return;
+            }
+        }
+    }
+
+    void clear()
+    {
+        mSlots.clear();
+        mMask = mUsed = 0;
+    }
+
+  private:
+    static constexpr uint32_t kEmpty = 0, kTomb = 1;
+    size_t home(const EntityId& id) const
+    {
+        return static_cast<size_t>((static_cast<uint64_t>(std::hash<EntityId>{}(id)) * 0x9E3779B97F4A7C15ull) >> mShift);
+    }
+    std::vector<uint32_t> mSlots;
+    size_t mMask = 0, mUsed = 0; // mUsed counts live + tombstone slots
+    int mShift = 60;
+};
+
+} // namespace detail
+
+template <typename EntityId, PartitioningMethod Method = PartitioningMethod::None>
+class Registry
+{
+  public:
+    struct EntityCollision
+    {
+        EntityId entityA;
+        EntityId entityB;
+        ShapeId shapeA;
+        ShapeId shapeB;
+        Manifold manifold;
+    };
+
+    using RayHit = RaycastHit<std::pair<EntityId, ShapeId>>;
+
+    Registry() { init(0); }
+    Registry(uint32_t cellSize) requires(Method == PartitioningMethod::Grid) { init(cellSize); }
+    ~Registry() { c2d_gpu_destroy(mCtx); }
+
+    Registry(const Registry&) = delete;
+    Registry& operator=(const Registry&) = delete;
+    Registry(Registry&& o) noexcept { *this = std::move(o); }
+    Registry& operator=(Registry&& o) noexcept
+    {
+        if (this != &o)
+        {
+            c2d_gpu_destroy(mCtx);
+            mCtx = std::exchange(o.mCtx, nullptr);
+            mIndex = std::move(o.mIndex);
+            mEntities = std::move(o.mEntities);
+            mFreeEntitySlots = std::move(o.mFreeEntitySlots);
+            mLiveEntities = std::exchange(o.mLiveEntities, 0);
+            mShapes = std::move(o.mShapes);
+            mFreeShapeIds = std::move(o.mFreeShapeIds);
+            mStats = o.mStats;
+        }
+        return *this;
+    }
+
+    void createEntity(EntityId id, BodyType type, const Transform& transform = Transform{});
+    void removeEntity(EntityId id);
+
+    template <IsShape Shape>
+    ShapeId addShape(EntityId entityId, const Shape& shape, uint64_t categoryBits = 1, uint64_t maskBits = ~0ull);
+    void removeShape(ShapeId shapeId);
+    void setShapeActive(ShapeId shapeId, bool isActive = true);
+
+    void teleportEntity(EntityId id, const Transform& transform);
+    void teleportEntity(EntityId id, Translation translation);
+    void moveEntity(EntityId id, const Transform& delta);
+    void moveEntity(EntityId id, Translation deltaTranslation);
+    Transform getEntityTransform(EntityId id) const;
+
+    std::vector<EntityCollision> getCollidingPairs();
+
+    std::set<RayHit> rayCast(Ray ray, BitMaskType maskBits = ~0ull) const;
+    std::set<RayHit> rayCast(InfiniteRay ray, BitMaskType maskBits = ~0ull) const;
+
+    size_t size() const { return mLiveEntities; }
+    void clear();
+
+    // ---- extensions (not in the reference) ------------------------------------------------------------
+    // moveEntity(ids[i], deltas[i]) for every i, in order.
+    void moveEntities(std::span<const EntityId> ids, std::span<const Translation> deltas);
+    // rayCast for a batch of rays; hits of ray i are result[i] in std::set order.
+    std::vector<std::vector<RayHit>> rayCastBatch(std::span<const Ray> rays, std::span<const InfiniteRay> infiniteRays,
+                                                  BitMaskType maskBits = ~0ull) const;
+    // Counters and CUDA-event timings of the last getCollidingPairs() / rayCast().
+    const c2d_gpu_stats& lastQueryStats() const { return mStats; }
+    // Runs the pipeline but leaves the records on the device; returns the number of colliding pairs.
+    uint64_t countCollidingPairsOnDevice();
+    c2d_gpu_ctx* nativeContext() const { return mCtx; }
+
+  private:
+    static constexpr uint32_t kNone = 0xffffffffu;
+    // EntityIds that are 4 trivially-copyable bytes travel through the GPU as their own bit pattern, so the
+    // 84-byte records come back already in EntityCollision layout; any other id type uses the dense index.
+    static constexpr bool kDirectTag = sizeof(EntityId) == 4 && std::is_trivially_copyable_v<EntityId> &&
+                                       std::has_unique_object_representations_v<EntityId>;
+
+    struct EntityInfo
+    {
+        EntityId id{};
+        Transform transform{};
+        Transform previous{}; // bullets only (reference mBulletPreviousTransforms)
+        uint32_t firstShape = kNone;
+        uint32_t lastShape = kNone;
+        BodyType type = BodyType::Static;
+        bool alive = false;
+    };
+    struct ShapeLink
+    {
+        uint32_t entity = kNone; // dense index
+        uint32_t prev = kNone, next = kNone;
+    };
+    struct KeyOf
+    {
+        const std::vector<EntityInfo>* entities;
+        const EntityId& operator()(uint32_t index) const { return (*entities)[index].id; }
+    };
+
+    void init(uint32_t cellSize)
+    {
+        if (c2d_gpu_create(-1, &mCtx) != 0)
+            throw std::runtime_error(std::string("colli2de-b200: ") + c2d_gpu_last_error(nullptr));
+        if constexpr (Method == PartitioningMethod::Grid)
+            check(c2d_gpu_set_broadphase(mCtx, C2D_BROADPHASE_GRID, cellSize));
+    }
+    void check(int rc) const
+    {
+        if (rc != 0)
+            throw std::runtime_error(std::string("colli2de-b200: ") + c2d_gpu_last_error(mCtx));
+    }
+    uint32_t indexOf(const EntityId& id) const { return mIndex.find(id, KeyOf{&mEntities}); }
+    EntityInfo& entityAt(const EntityId& id)
+    {
+        const uint32_t idx = indexOf(id);
+        C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
+        return mEntities[idx];
+    }
+    uint32_t tagOf(uint32_t denseIndex) const
+    {
+        if constexpr (kDirectTag)
+            return std::bit_cast<uint32_t>(mEntities[denseIndex].id);
+        else
+            return denseIndex;
+    }
+    static c2d_xf pack(const Transform& t, bool withLibmTrig)
+    {
+        c2d_xf x;
+        x.tx = t.translation.x;
+        x.ty = t.translation.y;
+        x.angle = t.rotation.angleRadians;
+        x.sin = t.rotation.sin;
+        x.cos = t.rotation.cos;
+        // what Transform(translation, angle) would hold: used by sweeps, which rebuild sin/cos from the angle
+        x.csin = withLibmTrig ? std::sin(t.rotation.angleRadians) : t.rotation.sin;
+        x.ccos = withLibmTrig ? std::cos(t.rotation.angleRadians) : t.rotation.cos;
+        x._pad = 0.0f;
+        return x;
+    }
+    static void packGeometry(const Circle& s, float* g, uint32_t& count)
+    {
+        g[0] = s.center.x, g[1] = s.center.y, g[2] = s.radius;
+        count = 0;
+    }
+    static void packGeometry(const Capsule& s, float* g, uint32_t& count)
+    {
+        g[0] = s.center1.x, g[1] = s.center1.y, g[2] = s.center2.x, g[3] = s.center2.y, g[4] = s.radius;
+        count = 0;
+    }
+    static void packGeometry(const Segment& s, float* g, uint32_t& count)
+    {
+        g[0] = s.start.x, g[1] = s.start.y, g[2] = s.end.x, g[3] = s.end.y;
+        count = 0;
+    }
+    static void packGeometry(const Polygon& s, float* g, uint32_t& count)
+    {
+        count = s.count;
+        for (uint32_t i = 0; i < s.count && i < MAX_POLYGON_VERTICES; ++i)
+        {
+            g[2 * i] = s.vertices[i].x, g[2 * i + 1] = s.vertices[i].y;
+            g[16 + 2 * i] = s.normals[i].x, g[16 + 2 * i + 1] = s.normals[i].y;
+        }
+    }
+    void pushShapeTransforms(EntityInfo& entity)
+    {
+        const c2d_xf x = pack(entity.transform, entity.type == BodyType::Bullet);
+        for (uint32_t s = entity.firstShape; s != kNone; s = mShapes[s].next)
+            check(c2d_gpu_shape_move(mCtx, s, &x));
+    }
+    template <typename RayT>
+    std::set<RayHit> rayCastOne(RayT ray, BitMaskType maskBits, bool infinite) const;
+
+    c2d_gpu_ctx* mCtx = nullptr;
+    detail::IndexMap<EntityId, KeyOf> mIndex;
+    std::vector<EntityInfo> mEntities;
+    std::vector<uint32_t> mFreeEntitySlots;
+    size_t mLiveEntities = 0;
+    std::vector<ShapeLink> mShapes;
+    std::vector<ShapeId> mFreeShapeIds;
+    mutable c2d_gpu_stats mStats{};
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// mutators
+// ---------------------------------------------------------------------------------------------------------
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::createEntity(EntityId id, BodyType type, const Transform& transform)
+{
+    C2D_DEBUG_ASSERT(indexOf(id) == kNone, "Entity with this ID already exists");
+    uint32_t idx;
+    if (!mFreeEntitySlots.empty())
+    {
+        idx = mFreeEntitySlots.back();
+        mFreeEntitySlots.pop_back();
+    }
+    else
+    {
+        idx = static_cast<uint32_t>(mEntities.size());
+        mEntities.emplace_back();
+    }
+    EntityInfo& e = mEntities[idx];
+    e = EntityInfo{};
+    e.id = id;
+    e.transform = transform;
+    e.previous = transform; // mBulletPreviousTransforms.emplace(id, transform) (reference Registry.hpp:268-269)
+    e.type = type;
+    e.alive = true;
+    ++mLiveEntities;
+    if (mIndex.needsRehash())
+    {
+        std::vector<uint32_t> live;
+        live.reserve(mLiveEntities);
+        for (uint32_t i = 0; i < mEntities.size(); ++i)
+            if (mEntities[i].alive && i != idx)
+                live.push_back(i);
+        mIndex.rehash(KeyOf{&mEntities}, live);
+    }
+    mIndex.insert(id, idx);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+template <IsShape Shape>
+ShapeId Registry<EntityId, Method>::addShape(EntityId entityId, const Shape& shape, uint64_t categoryBits,
+                                             uint64_t maskBits)
+{
+    const uint32_t idx = indexOf(entityId);
+    C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
+    EntityInfo& entity = mEntities[idx];
+
+    ShapeId shapeId;
+    if (!mFreeShapeIds.empty())
+    {
+        shapeId = mFreeShapeIds.back(); // LIFO reuse (reference Registry.hpp:283-289)
+        mFreeShapeIds.pop_back();
+    }
+    else
+    {
+        shapeId = static_cast<ShapeId>(mShapes.size());
+        mShapes.emplace_back();
+    }
+
+    float geom[C2D_GEOM_FLOATS] = {};
+    uint32_t count = 0;
+    packGeometry(shape, geom, count);
+    const bool bullet = entity.type == BodyType::Bullet;
+    const c2d_xf cur = pack(entity.transform, bullet);
+    const c2d_xf prev = pack(entity.previous, bullet);
+    check(c2d_gpu_shape_add(mCtx, shapeId, tagOf(idx), static_cast<uint32_t>(shape.getType()),
+                            static_cast<uint32_t>(entity.type), count, categoryBits, maskBits, geom, &cur, &prev));
+
+    ShapeLink& link = mShapes[shapeId];
+    link.entity = idx;
+    link.prev = entity.lastShape;
+    link.next = kNone;
+    if (entity.lastShape != kNone)
+        mShapes[entity.lastShape].next = shapeId;
+    else
+        entity.firstShape = shapeId;
+    entity.lastShape = shapeId;
+    return shapeId;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::removeShape(ShapeId shapeId)
+{
+    C2D_DEBUG_ASSERT(shapeId < mShapes.size(), "Shape ID out of bounds");
+    ShapeLink& link = mShapes[shapeId];
+    C2D_DEBUG_ASSERT(link.entity != kNone, "Shape with this ID does not exist in the entity");
+    EntityInfo& entity = mEntities[link.entity];
+    check(c2d_gpu_shape_remove(mCtx, shapeId));
+    if (link.prev != kNone)
+        mShapes[link.prev].next = link.next;
+    else
+        entity.firstShape = link.next;
+    if (link.next != kNone)
+        mShapes[link.next].prev = link.prev;
+    else
+        entity.lastShape = link.prev;
+    link = ShapeLink{};
+    mFreeShapeIds.push_back(shapeId);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::setShapeActive(ShapeId shapeId, bool isActive)
+{
+    C2D_DEBUG_ASSERT(shapeId < mShapes.size(), "Shape ID out of bounds");
+    check(c2d_gpu_shape_set_active(mCtx, shapeId, isActive ? 1 : 0));
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::removeEntity(EntityId id)
+{
+    const uint32_t idx = indexOf(id);
+    C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
+    EntityInfo& entity = mEntities[idx];
+    for (uint32_t s = entity.firstShape; s != kNone;)
+    {
+        const uint32_t next = mShapes[s].next;
+        check(c2d_gpu_shape_remove(mCtx, s));
+        mShapes[s] = ShapeLink{};
+        mFreeShapeIds.push_back(s); // in insertion order, like the reference (Registry.hpp:367-373)
+        s = next;
+    }
+    mIndex.erase(id, KeyOf{&mEntities});
+    entity = EntityInfo{};
+    mFreeEntitySlots.push_back(idx);
+    --mLiveEntities;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::teleportEntity(EntityId id, const Transform& transform)
+{
+    EntityInfo& entity = entityAt(id);
+    // reference Registry.hpp:382-401: shapes are refit at `transform`, then previous <- current <- transform
+    if (entity.type == BodyType::Bullet)
+        entity.previous = entity.transform;
+    entity.transform = transform;
+    pushShapeTransforms(entity);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::teleportEntity(EntityId id, Translation translation)
+{
+    const EntityInfo& entity = entityAt(id);
+    moveEntity(id, translation - entity.transform.translation); // reference Registry.hpp:403-411
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::moveEntity(EntityId id, const Transform& delta)
+{
+    EntityInfo& entity = entityAt(id);
+    if (entity.type == BodyType::Bullet)
+        entity.previous = entity.transform;
+    entity.transform += delta; // Rotation::operator+= quirk included
+    pushShapeTransforms(entity);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::moveEntity(EntityId id, Translation d)
+{
+    EntityInfo& entity = entityAt(id);
+    for (uint32_t s = entity.firstShape; s != kNone; s = mShapes[s].next)
+        check(c2d_gpu_shape_translate(mCtx, s, d.x, d.y));
+    if (entity.type == BodyType::Bullet)
+        entity.previous = entity.transform;
+    entity.transform.translation += d;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::moveEntities(std::span<const EntityId> ids, std::span<const Translation> deltas)
+{
+    C2D_DEBUG_ASSERT(ids.size() == deltas.size());
+    for (size_t i = 0; i < ids.size(); ++i)
+        moveEntity(ids[i], deltas[i]);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+Transform Registry<EntityId, Method>::getEntityTransform(EntityId id) const
+{
+    const uint32_t idx = indexOf(id);
+    C2D_DEBUG_ASSERT(idx != kNone);
+    return mEntities[idx].transform;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::clear()
+{
+    check(c2d_gpu_clear(mCtx));
+    mIndex.clear();
+    mEntities.clear();
+    mFreeEntitySlots.clear();
+    mLiveEntities = 0;
+    mShapes.clear();
+    mFreeShapeIds.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// queries
+// ---------------------------------------------------------------------------------------------------------
+template <typename EntityId, PartitioningMethod Method>
+std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<EntityId, Method>::getCollidingPairs()
+{
+    const c2d_pair_record* records = nullptr;
+    uint64_t count = 0;
+    check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
+    if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
+                  std::is_trivially_copyable_v<EntityCollision>)
+    {
+        // the device wrote EntityCollision records: one block copy out of the pinned buffer
+        const auto* first = reinterpret_cast<const EntityCollision*>(records);
+        return std::vector<EntityCollision>(first, first + count);
+    }
+    else
+    {
+        std::vector<EntityCollision> out;
+        out.reserve(count);
+        for (uint64_t i = 0; i < count; ++i)
+        {
+            const c2d_pair_record& r = records[i];
+            EntityCollision c{mEntities[r.entityA].id, mEntities[r.entityB].id, r.shapeA, r.shapeB, Manifold{}};
+            static_assert(sizeof(Manifold) == sizeof(c2d_manifold));
+            std::memcpy(static_cast<void*>(&c.manifold), &r.manifold, sizeof(Manifold));
+            out.push_back(std::move(c));
+        }
+        return out;
+    }
+}
+
+template <typename EntityId, PartitioningMethod Method>
+uint64_t Registry<EntityId, Method>::countCollidingPairsOnDevice()
+{
+    uint64_t count = 0;
+    check(c2d_gpu_collide_device(mCtx, &count, &mStats));
+    return count;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+template <typename RayT>
+std::set<typename Registry<EntityId, Method>::RayHit> Registry<EntityId, Method>::rayCastOne(RayT ray,
+                                                                                             BitMaskType maskBits,
+                                                                                             bool infinite) const
+{
+    c2d_ray r{};
+    r.sx = ray.start.x;
+    r.sy = ray.start.y;
+    if constexpr (std::is_same_v<RayT, Ray>)
+        r.ex = ray.end.x, r.ey = ray.end.y;
+    else
+        r.ex = ray.direction.x, r.ey = ray.direction.y;
+    r.mask = maskBits;
+    r.infinite = infinite ? 1u : 0u;
+    const c2d_hit_record* hits = nullptr;
+    const uint64_t* offsets = nullptr;
+    check(c2d_gpu_raycast(mCtx, 1, &r, &hits, &offsets, &mStats));
+    std::set<RayHit> out;
+    for (uint64_t i = offsets[0]; i < offsets[1]; ++i)
+    {
+        const c2d_hit_record& h = hits[i];
+        EntityId id;
+        if constexpr (kDirectTag)
+            id = std::bit_cast<EntityId>(h.entity);
+        else
+            id = mEntities[h.entity].id;
+        out.insert(out.end(), RayHit{{id, h.shape}, Vec2{h.entry[0], h.entry[1]}, Vec2{h.exit[0], h.exit[1]},
+                                     h.entryTime, h.exitTime});
+    }
+    return out;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+std::set<typename Registry<EntityId, Method>::RayHit> Registry<EntityId, Method>::rayCast(Ray ray,
+                                                                                          BitMaskType maskBits) const
+{
+    return rayCastOne(ray, maskBits, false);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+std::set<typename Registry<EntityId, Method>::RayHit> Registry<EntityId, Method>::rayCast(InfiniteRay ray,
+                                                                                          BitMaskType maskBits) const
+{
+    return rayCastOne(ray, maskBits, true);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+std::vector<std::vector<typename Registry<EntityId, Method>::RayHit>> Registry<EntityId, Method>::rayCastBatch(
+    std::span<const Ray> rays, std::span<const InfiniteRay> infiniteRays, BitMaskType maskBits) const
+{
+    std::vector<c2d_ray> packed;
+    packed.reserve(rays.size() + infiniteRays.size());
+    for (const Ray& ray : rays)
+        packed.push_back(c2d_ray{ray.start.x, ray.start.y, ray.end.x, ray.end.y, maskBits, 0u, 0u});
+    for (const InfiniteRay& ray : infiniteRays)
+        packed.push_back(c2d_ray{ray.start.x, ray.start.y, ray.direction.x, ray.direction.y, maskBits, 1u, 0u});
+    const c2d_hit_record* hits = nullptr;
+    const uint64_t* offsets = nullptr;
+    check(c2d_gpu_raycast(mCtx, static_cast<uint32_t>(packed.size()), packed.data(), &hits, &offsets, &mStats));
+    std::vector<std::vector<RayHit>> out(packed.size());
+    for (size_t i = 0; i < packed.size(); ++i)
+    {
+        out[i].reserve(offsets[i + 1] - offsets[i]);
+        for (uint64_t k = offsets[i]; k < offsets[i + 1]; ++k)
+        {
+            const c2d_hit_record& h = hits[k];
+            EntityId id;
+            if constexpr (kDirectTag)
+                id = std::bit_cast<EntityId>(h.entity);
+            else
+                id = mEntities[h.entity].id;
+            out[i].push_back(RayHit{{id, h.shape}, Vec2{h.entry[0], h.entry[1]}, Vec2{h.exit[0], h.exit[1]},
+                                    h.entryTime, h.exitTime});
+        }
+    }
+    return out;
+}
+
+} // namespace c2d

@@ -21,7 +21,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB_PATHS = {
     "oracle": os.path.join(REPO, "oracle", "libc2d_oracle.so"),
     "reference": os.path.join(REPO, "oracle", "_ref", "libc2d_ref_runner.so"),
-    "b200": os.path.join(REPO, "colli2de_b200", "libc2d_b200_runner.so"),
+    "b200": os.environ.get("C2D_B200_RUNNER", os.path.join(REPO, "colli2de_b200", "libc2d_b200_runner.so")),
 }
 
 PAIR_DTYPE = np.dtype(
