@@ -21,8 +21,10 @@ RUNNER_LIB = os.path.join(HERE, "libc2d_b200_runner.so")
 CU_SOURCES = ["c2d_sort.cu", "c2d_gpu.cu", "c2d_batch.cu", "c2d_rays.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-    "-fmad=false", "-Xcompiler", "-fPIC", "-DC2D_HAVE_RAYS",
+    "-fmad=false", "-Xcompiler", "-fPIC",
 ]
+if os.path.exists(os.path.join(CSRC, "c2d_rays.cu")):
+    NVCC_FLAGS.append("-DC2D_HAVE_RAYS")
 
 
 def _newer(target: str, deps: list[str]) -> bool:
@@ -67,12 +69,13 @@ def build_runner(force: bool = False) -> str:
     if force or not _newer(RUNNER_LIB, deps):
         _run(["g++", "-std=c++23", "-O2", "-fPIC", "-shared", "-DRN_BACKEND_B200", "-I" + inc,
               "-I" + os.path.join(REPO, "tests", "cpp"), src, "-o", RUNNER_LIB,
-              "-L" + HERE, "-lc2d_gpu", "-Wl,-rpath,$ORIGIN"])
+              "-L" + HERE, "-lc2d_gpu", "-Wl,-rpath,$ORIGIN", "-Wl,-Bsymbolic"])
     return RUNNER_LIB
 
 
 def build_oracles():
-    _run(["make", "-C", os.path.join(REPO, "oracle"), "all"])
+    targets = ["ref"] + (["oracle"] if os.path.exists(os.path.join(REPO, "oracle", "c2d_oracle.c")) else [])
+    _run(["make", "-C", os.path.join(REPO, "oracle"), *targets])
 
 
 def build_all(force: bool = False):

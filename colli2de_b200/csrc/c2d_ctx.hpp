@@ -1,0 +1,180 @@
+// c2d_ctx.hpp — the context object behind the C ABI (shared by c2d_gpu.cu and c2d_rays.cu).
+#pragma once
+
+#include "c2d_internal.hpp"
+
+#include "../../include/c2d_gpu.h"
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace c2d_host
+{
+using namespace c2d_dev;
+
+// ---- small RAII helpers ---------------------------------------------------------------------------
+template <typename T>
+struct PinnedVec
+{
+    T* data = nullptr;
+    size_t size = 0;
+    size_t capacity = 0;
+
+    ~PinnedVec()
+    {
+        if (data)
+            cudaFreeHost(data);
+    }
+    bool reserve(size_t want)
+    {
+        if (want <= capacity)
+            return true;
+        size_t cap = capacity ? capacity : 1024;
+        while (cap < want)
+            cap *= 2;
+        T* fresh = nullptr;
+        if (cudaHostAlloc(reinterpret_cast<void**>(&fresh), cap * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
+            return false;
+        if (size)
+            std::memcpy(fresh, data, size * sizeof(T));
+        if (data)
+            cudaFreeHost(data);
+        data = fresh;
+        capacity = cap;
+        return true;
+    }
+    T* push()
+    {
+        if (size == capacity && !reserve(size + 1))
+            return nullptr;
+        return &data[size++];
+    }
+};
+
+template <typename T>
+struct DevBuf
+{
+    T* ptr = nullptr;
+    size_t capacity = 0;
+    ~DevBuf()
+    {
+        if (ptr)
+            cudaFree(ptr);
+    }
+    // contents are NOT preserved
+    cudaError_t reserve(size_t want)
+    {
+        if (want <= capacity)
+            return cudaSuccess;
+        size_t cap = capacity ? capacity : 1024;
+        while (cap < want)
+            cap *= 2;
+        if (ptr)
+            cudaFree(ptr);
+        ptr = nullptr;
+        capacity = 0;
+        const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), cap * sizeof(T));
+        if (e == cudaSuccess)
+            capacity = cap;
+        return e;
+    }
+};
+
+enum Phase : uint32_t
+{
+    PH_FLAG = 0,
+    PH_ADD = 1,
+    PH_TRANS = 2,
+    PH_MOVE = 3
+};
+
+struct Round
+{
+    size_t f0, a0, t0, m0; // begin offsets in the four logs; the end is the next round's begin (or the log size)
+};
+
+struct TreeBuf
+{
+    DevBuf<uint32_t> members; // shape ids, host order
+    DevBuf<uint32_t> keys, vals, keysTmp, valsTmp;
+    DevBuf<BvhNode> nodes;
+    DevBuf<int> nodeParent, leafParent;
+    DevBuf<uint32_t> arrival;
+    DevBuf<unsigned char> sortWs;
+    uint32_t n = 0; // leaves in the built tree
+};
+
+} // namespace c2d_host
+
+using namespace c2d_dev;  // internal header: only included by the library's own translation units
+using namespace c2d_host;
+
+struct c2d_gpu_ctx
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[6] = {};
+    std::string error;
+
+    // shapes
+    uint32_t capacity = 0;
+    uint32_t shapeSlots = 0; // 1 + highest shape id ever added
+    ShapeArrays d{};
+    std::vector<uint32_t> hostMeta; // body / alive per shape
+    std::vector<uint32_t> stamp;    // (round << 2) | phase of the last logged op
+    std::vector<uint32_t> memberPos;
+    std::vector<uint32_t> members[3];
+    bool membersDirty[3] = {false, false, false};
+    bool treeDirty[3] = {false, false, false};
+
+    // mutation log
+    uint32_t round = 1;
+    PinnedVec<FlagRec> flagLog;
+    PinnedVec<AddRec> addLog;
+    PinnedVec<TransRec> transLog;
+    PinnedVec<MoveRec> moveLog;
+    std::vector<Round> rounds;
+    DevBuf<FlagRec> dFlagLog;
+    DevBuf<AddRec> dAddLog;
+    DevBuf<TransRec> dTransLog;
+    DevBuf<MoveRec> dMoveLog;
+
+    // trees
+    TreeBuf tree[3];
+    int broadphase = C2D_BROADPHASE_LBVH;
+    uint32_t cellSize = 120;
+    uint32_t shardRank = 0, shardWorld = 1;
+
+    // frame
+    c2d_dev::FrameScratch* dScratch = nullptr;
+    c2d_dev::FrameScratch* hScratch = nullptr; // pinned
+    c2d_host::DevBuf<uint2> cand, binned;
+    c2d_host::DevBuf<c2d_dev::PairOut> out;
+    c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
+    uint64_t lastCandidates = 0;
+    uint32_t launches = 0;
+    uint64_t h2dBytes = 0;
+};
+
+
+namespace c2d_host
+{
+// c2d_gpu.cu
+int fail(c2d_gpu_ctx* ctx, const std::string& msg);
+int flush(c2d_gpu_ctx* ctx);        // replays the mutation log
+int ensure_trees(c2d_gpu_ctx* ctx); // flush + rebuild of the dirty trees (launches k_frame_init first)
+
+#define C2D_CUDA(ctx, call)                                                                                            \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        const cudaError_t _e = (call);                                                                                 \
+        if (_e != cudaSuccess)                                                                                         \
+            return ::c2d_host::fail(ctx, std::string(#call) + ": " + cudaGetErrorString(_e));                          \
+    } while (0)
+
+inline uint32_t blocks_for(size_t n, uint32_t threads)
+{
+    return static_cast<uint32_t>((n + threads - 1) / threads);
+}
+} // namespace c2d_host

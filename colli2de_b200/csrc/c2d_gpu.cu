@@ -8,9 +8,8 @@
 //     phases run flags -> adds -> translates -> moves and a shape appears at most once per phase with
 //     strictly increasing phase, so per-shape program order is preserved without one launch per call;
 //   * a query = flush + (re)build of the dirty trees + 5 traversals + binning + narrowphase on one stream.
+#include "c2d_ctx.hpp"
 #include "c2d_kernels.cuh"
-
-#include "../../include/c2d_gpu.h"
 
 #include <algorithm>
 #include <chrono>
@@ -27,150 +26,10 @@ namespace
 
 thread_local std::string g_lastError;
 
-// ---- small RAII helpers ---------------------------------------------------------------------------
-template <typename T>
-struct PinnedVec
-{
-    T* data = nullptr;
-    size_t size = 0;
-    size_t capacity = 0;
-
-    ~PinnedVec()
-    {
-        if (data)
-            cudaFreeHost(data);
-    }
-    bool reserve(size_t want)
-    {
-        if (want <= capacity)
-            return true;
-        size_t cap = capacity ? capacity : 1024;
-        while (cap < want)
-            cap *= 2;
-        T* fresh = nullptr;
-        if (cudaHostAlloc(reinterpret_cast<void**>(&fresh), cap * sizeof(T), cudaHostAllocDefault) != cudaSuccess)
-            return false;
-        if (size)
-            std::memcpy(fresh, data, size * sizeof(T));
-        if (data)
-            cudaFreeHost(data);
-        data = fresh;
-        capacity = cap;
-        return true;
-    }
-    T* push()
-    {
-        if (size == capacity && !reserve(size + 1))
-            return nullptr;
-        return &data[size++];
-    }
-};
-
-template <typename T>
-struct DevBuf
-{
-    T* ptr = nullptr;
-    size_t capacity = 0;
-    ~DevBuf()
-    {
-        if (ptr)
-            cudaFree(ptr);
-    }
-    // contents are NOT preserved
-    cudaError_t reserve(size_t want)
-    {
-        if (want <= capacity)
-            return cudaSuccess;
-        size_t cap = capacity ? capacity : 1024;
-        while (cap < want)
-            cap *= 2;
-        if (ptr)
-            cudaFree(ptr);
-        ptr = nullptr;
-        capacity = 0;
-        const cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&ptr), cap * sizeof(T));
-        if (e == cudaSuccess)
-            capacity = cap;
-        return e;
-    }
-};
-
-enum Phase : uint32_t
-{
-    PH_FLAG = 0,
-    PH_ADD = 1,
-    PH_TRANS = 2,
-    PH_MOVE = 3
-};
-
-struct Round
-{
-    size_t f0, a0, t0, m0; // begin offsets in the four logs; the end is the next round's begin (or the log size)
-};
-
-struct TreeBuf
-{
-    DevBuf<uint32_t> members; // shape ids, host order
-    DevBuf<uint32_t> keys, vals, keysTmp, valsTmp;
-    DevBuf<BvhNode> nodes;
-    DevBuf<int> nodeParent, leafParent;
-    DevBuf<uint32_t> arrival;
-    DevBuf<unsigned char> sortWs;
-    uint32_t n = 0; // leaves in the built tree
-};
-
 } // namespace
 
-struct c2d_gpu_ctx
+namespace c2d_host
 {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[6] = {};
-    std::string error;
-
-    // shapes
-    uint32_t capacity = 0;
-    uint32_t shapeSlots = 0; // 1 + highest shape id ever added
-    ShapeArrays d{};
-    std::vector<uint32_t> hostMeta; // body / alive per shape
-    std::vector<uint32_t> stamp;    // (round << 2) | phase of the last logged op
-    std::vector<uint32_t> memberPos;
-    std::vector<uint32_t> members[3];
-    bool membersDirty[3] = {false, false, false};
-    bool treeDirty[3] = {false, false, false};
-
-    // mutation log
-    uint32_t round = 1;
-    PinnedVec<FlagRec> flagLog;
-    PinnedVec<AddRec> addLog;
-    PinnedVec<TransRec> transLog;
-    PinnedVec<MoveRec> moveLog;
-    std::vector<Round> rounds;
-    DevBuf<FlagRec> dFlagLog;
-    DevBuf<AddRec> dAddLog;
-    DevBuf<TransRec> dTransLog;
-    DevBuf<MoveRec> dMoveLog;
-
-    // trees
-    TreeBuf tree[3];
-    int broadphase = C2D_BROADPHASE_LBVH;
-    uint32_t cellSize = 120;
-    uint32_t shardRank = 0, shardWorld = 1;
-
-    // frame
-    FrameScratch* dScratch = nullptr;
-    FrameScratch* hScratch = nullptr; // pinned
-    DevBuf<uint2> cand, binned;
-    DevBuf<PairOut> out;
-    PinnedVec<PairOut> hostOut;
-    uint64_t lastCandidates = 0;
-    uint32_t launches = 0;
-    uint64_t h2dBytes = 0;
-};
-
-namespace
-{
-
 int fail(c2d_gpu_ctx* ctx, const std::string& msg)
 {
     if (ctx)
@@ -178,19 +37,10 @@ int fail(c2d_gpu_ctx* ctx, const std::string& msg)
     g_lastError = msg;
     return 1;
 }
+} // namespace c2d_host
 
-#define C2D_CUDA(ctx, call)                                                                                            \
-    do                                                                                                                 \
-    {                                                                                                                  \
-        const cudaError_t _e = (call);                                                                                 \
-        if (_e != cudaSuccess)                                                                                         \
-            return fail(ctx, std::string(#call) + ": " + cudaGetErrorString(_e));                                      \
-    } while (0)
-
-inline uint32_t blocks_for(size_t n, uint32_t threads)
+namespace
 {
-    return static_cast<uint32_t>((n + threads - 1) / threads);
-}
 
 template <typename T>
 cudaError_t grow_array(T*& ptr, uint32_t oldCap, uint32_t newCap, size_t perShape, cudaStream_t stream)
@@ -284,7 +134,9 @@ void member_remove(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
     ctx->membersDirty[body] = ctx->treeDirty[body] = true;
 }
 
-int flush(c2d_gpu_ctx* ctx)
+} // namespace
+
+int c2d_host::flush(c2d_gpu_ctx* ctx)
 {
     if (ctx->rounds.empty())
         return 0;
@@ -355,6 +207,9 @@ int flush(c2d_gpu_ctx* ctx)
     return 0;
 }
 
+namespace
+{
+
 // ---- tree build --------------------------------------------------------------------------------------
 int build_tree(c2d_gpu_ctx* ctx, int body)
 {
@@ -408,6 +263,29 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     C2D_CUDA(ctx, cudaGetLastError());
     return 0;
 }
+
+} // namespace
+
+int c2d_host::ensure_trees(c2d_gpu_ctx* ctx)
+{
+    if (int rc = flush(ctx))
+        return rc;
+    bool any = false;
+    for (int body = 0; body < 3; ++body)
+        any = any || ctx->treeDirty[body];
+    if (!any)
+        return 0;
+    k_frame_init<<<1, 32, 0, ctx->stream>>>(ctx->dScratch);
+    ++ctx->launches;
+    for (int body = 0; body < 3; ++body)
+        if (ctx->treeDirty[body])
+            if (int rc = build_tree(ctx, body))
+                return rc;
+    return 0;
+}
+
+namespace
+{
 
 template <bool SELF>
 void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)

@@ -86,6 +86,26 @@ struct Tree
     BvhNode* nodes;      // n - 1 internal nodes, root = 0
 };
 
+// frame scratch: [0..3] bounds tree 0 (minx, miny, maxx, maxy as ordered uints), [4..7] tree 1, [8..11] tree 2,
+// then counters.
+struct FrameScratch
+{
+    uint32_t bounds[3][4];
+    uint32_t candCount;
+    uint32_t outCount;
+    uint32_t clipOverflow;
+    uint32_t _pad;
+    uint32_t binCount[16];
+    uint32_t binOffset[16];
+    uint32_t binCursor[16];
+};
+
+struct PairOut // 84 bytes, = Registry<uint32_t>::EntityCollision
+{
+    uint32_t entityA, entityB, shapeA, shapeB;
+    float manifold[17];
+};
+
 // radix sort (c2d_sort.cu)
 size_t sort_workspace_bytes(uint32_t n, int passes);
 int radix_sort_pairs(cudaStream_t stream, uint32_t* keys, uint32_t* vals, uint32_t* keysTmp, uint32_t* valsTmp,

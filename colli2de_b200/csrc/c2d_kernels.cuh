@@ -169,20 +169,6 @@ __device__ __forceinline__ float ordered_to_float(uint32_t u)
     return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-// frame scratch: [0..3] bounds tree 0 (minx, miny, maxx, maxy as ordered uints), [4..7] tree 1, [8..11] tree 2,
-// then counters.
-struct FrameScratch
-{
-    uint32_t bounds[3][4];
-    uint32_t candCount;
-    uint32_t outCount;
-    uint32_t clipOverflow;
-    uint32_t _pad;
-    uint32_t binCount[16];
-    uint32_t binOffset[16];
-    uint32_t binCursor[16];
-};
-
 __global__ void k_frame_init(FrameScratch* fs)
 {
     const int t = threadIdx.x;
@@ -555,12 +541,6 @@ __device__ __forceinline__ XF xf_from(float4 f)
     t.c = f.w;
     return t;
 }
-
-struct PairOut // 84 bytes, = Registry<uint32_t>::EntityCollision
-{
-    uint32_t entityA, entityB, shapeA, shapeB;
-    float manifold[17];
-};
 
 __global__ void __launch_bounds__(128) k_narrow(const uint2* __restrict__ binned, uint32_t capacity, ShapeArrays s,
                                                 FrameScratch* fs, PairOut* __restrict__ out, uint32_t outCapacity)

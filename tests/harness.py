@@ -97,10 +97,9 @@ def load(name: str) -> C.CDLL:
     if name in _LIBS:
         return _LIBS[name]
     path = LIB_PATHS[name]
-    if name == "b200":
-        # the runner links libc2d_gpu.so by rpath ($ORIGIN)
-        pass
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    # RTLD_LOCAL: the reference runner and the B200 runner both instantiate c2d::Registry<uint32_t> (same mangled
+    # names, different code) and must never see each other's symbols; both are also linked -Bsymbolic.
+    lib = C.CDLL(path, mode=C.RTLD_LOCAL)
     vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
     pf, pu8, pu32, pu64 = C.POINTER(C.c_float), C.POINTER(C.c_uint8), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
     pd = C.POINTER(C.c_double)
