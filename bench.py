@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — Colli2De per-frame collision query path on B200: getCollidingPairs ms/frame and pairs/s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3-clustered|cfg3-uniform|cfg2]
+
+Own arm (default): the BASELINE.json workload quoted by the metric — cfg 3, 1 M dynamic mixed shapes
+(circle / capsule / segment / convex polygon) + 100 k static polygons, clustered density — driven through the
+drop-in c2d::Registry<uint32_t> (tests/cpp/runner.cpp compiled against include/colli2de/Registry.hpp)
+-> C ABI (include/c2d_gpu.h) -> hand-written sm_100a kernels.  One "step" = one frame: every dynamic entity
+is moved by a jitter in U(-0.5, 0.5)^2, then getCollidingPairs runs.
+  * `value` / `ms_per_step`: device-resident path — the K frames' move batches are staged in HBM before the
+    timed region (Registry::stageMoves), each step = applyStagedMoves + the whole pipeline (refit, Morton,
+    radix sort, LBVH build + fit, traversal, binning, narrowphase); results stay on the device.
+  * `e2e`: the reference-facing call with HOST buffers — Registry::getCollidingPairs() after per-entity
+    moveEntity calls: the pinned move log is uploaded (H2D) and the 84-byte EntityCollision records are
+    downloaded (D2H) and returned as std::vector inside the timed call.  Like the reference's metric
+     the per-entity moveEntity host calls are outside the timed call; their cost is
+    reported as e2e.moves_host_ms.
+  * `roofline`: the dominant kernel by live CUDA-event time (c2d_gpu_set_profiling), algorithmic bytes per
+    launch as defined in DESIGN.md section "Roofline", against MEASURED_PEAKS.json hbm_gbs.
+  * `cpu_baseline`: the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by oracle/Makefile)
+    timed on this host on a bounded sample (same scene, a few frames).
+Reference arm (--impl reference): the reference's own CPU getCollidingPairs on the same scene, K steps.
+
+Multi-GPU (torchrun, one rank per GPU): every rank mirrors the scene and owns one Morton-rank slab of the query
+leaves (c2d_gpu_set_shard) — traversal and narrowphase are sharded, the pair count is all-reduced over NCCL;
+`scaling` is "strong" (the scene is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from colli2de_b200 import scenes  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_dynamic, n_static, box, clustered)
+    "cfg3-clustered": (1_000_000, 100_000, 5000.0, True),
+    "cfg3-uniform": (1_000_000, 100_000, 5000.0, False),
+    "cfg2": (100_000, 10_000, 1600.0, False),
+}
+METRIC = "getCollidingPairs pairs/sec at 1M shapes (ms/frame = ms_per_step)"
+UNIT = "pairs/s"
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, flag in zip(names, r[3:7]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_scene(name: str):
+    n_dyn, n_sta, box, clustered = WORKLOADS[name]
+    return scenes.mixed_scene(n_dyn, n_sta, box, clustered=clustered), n_dyn, n_sta
+
+
+def measured_peak_gbs():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def geometry_bytes(scene, mask) -> float:
+    """mean geometry bytes per shape as in SURVEY.md section 8(d): circle 12, capsule 20, segment 16, polygon 4 + 8*count"""
+    t, c = scene["shp_type"][mask], scene["shp_count"][mask].astype(np.float64)
+    return float(np.where(t == 0, 12, np.where(t == 1, 20, np.where(t == 2, 16, 4 + 8 * c))).mean())
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_reference(args, scene, n_dyn, as_baseline: bool):
+    """The reference's own CPU getCollidingPairs (oracle/_ref).  as_baseline: bounded sample for cpu_baseline."""
+    from tests import harness as H
+
+    which = "reference" if H.available("reference") else "oracle"
+    kind = "reference" if which == "reference" else "port"
+    b = H.Backend(which)
+    scenes.populate(b, scene)
+    rng = scenes.LCG(2024)
+    dyn = np.arange(n_dyn, dtype=np.uint32)
+    steps, warm = (3, 1) if as_baseline else (args.steps, args.warmup)
+    # bound the arm: probe one frame, shrink the step count if K frames would take more than ~3 minutes
+    times, pairs = [], 0
+    budget_s = 25.0 if as_baseline else 170.0
+    t_start = time.perf_counter()
+    for f in range(warm + steps):
+        b.move_translate(dyn, scenes.jitter(rng, n_dyn, 0.5))
+        sec = C.c_double(0.0)
+        n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
+        b._check()
+        if f >= warm:
+            times.append(sec.value)
+            pairs += n
+        if time.perf_counter() - t_start > budget_s and len(times) >= 1:
+            break
+    done = len(times)
+    total = float(np.sum(times))
+    threads = 5 if len(scene["shp_entity"]) > 9000 else 1  # Registry.hpp:469,536-539: 5 std::threads, narrowphase serial
+    return dict(value=pairs / total, unit=UNIT, cores=threads, kind=kind, steps=done, ms_per_step=1e3 * total / done,
+                pairs_per_frame=pairs / done, host_cores=os.cpu_count(),
+                sample=(f"full workload scene, {done} timed frames after {warm} warm-up; reference Release flags "
+                        f"(-O3 -DNDEBUG -ffp-contract=off), broadphase on <= {threads} std::threads, narrowphase serial; "
+                        f"steady_clock around getCollidingPairs() only"))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    from colli2de_b200 import capi
+    from tests import harness as H
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (own arm) needs a CUDA device: colli2de_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    capi.lib()  # fail loudly if libc2d_gpu.so is missing
+    b = H.Backend("b200")
+    scenes.populate(b, scene)
+    ctx = b.native_context()
+    capi.set_shard(ctx, rank, world)
+    dyn = np.arange(n_dyn, dtype=np.uint32)
+    K, W = args.steps, args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- device-resident arm: move batches staged in HBM before the timed region -------------------------------
+    rng = scenes.LCG(2024)
+    handles = [b.stage_translations(dyn, scenes.jitter(rng, n_dyn, 0.5)) for _ in range(W + K)]
+    for h in handles[:W]:
+        b.apply_staged(h)
+        b.count_pairs_device()
+    capi.set_profiling(ctx, True)
+    capi.kernel_profile(ctx, reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches = 0
+    pairs_total = 0
+    stage_ms = dict(ms_refit=0.0, ms_build=0.0, ms_broad=0.0, ms_narrow=0.0, ms_device=0.0)
+    cand_total = 0
+    barrier()
+    t0 = time.perf_counter()
+    for h in handles[W:]:
+        b.apply_staged(h)
+        n, _ = b.count_pairs_device()
+        st = b.stats()
+        pairs_total += n
+        cand_total += st["candidates"]
+        launches += int(st["kernel_launches"])
+        for k in stage_ms:
+            stage_ms[k] += st[k]
+    barrier()
+    elapsed = allmax(time.perf_counter() - t0)
+    clocks = sampler.stop() if sampler else None
+    profile = capi.kernel_profile(ctx, reset=True)
+    capi.set_profiling(ctx, False)
+    for h in handles:
+        b.release_staged(h)
+    pairs_all = allsum(float(pairs_total))
+    cand_all = allsum(float(cand_total))
+    ms_per_step = 1e3 * elapsed / K
+    value = pairs_all / elapsed
+
+    # ---- end-to-end arm: host buffers through the drop-in API ----------------------------------------------------
+    e2e_times, move_times, e2e_pairs, h2d, d2h = [], [], 0, 0.0, 0.0
+    for f in range(2 + K):
+        d = scenes.jitter(rng, n_dyn, 0.5)
+        if f == 2:
+            barrier()
+            te0 = time.perf_counter()
+        tm = time.perf_counter()
+        b.move_translate(dyn, d)
+        tm = time.perf_counter() - tm
+        sec = C.c_double(0.0)
+        n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
+        b._check()
+        if f >= 2:
+            st = b.stats()
+            e2e_times.append(sec.value)
+            move_times.append(tm)
+            e2e_pairs += n
+            h2d += st["h2d_bytes"]
+            d2h += st["d2h_bytes"]
+    barrier()
+    e2e_elapsed = allmax(float(np.sum(e2e_times)))
+    e2e_pairs_all = allsum(float(e2e_pairs))
+
+    if rank != 0:
+        return None
+
+    # ---- roofline of the dominant kernel (live CUDA-event times) ----------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    dom_name, (dom_count, dom_ms) = max(profile.items(), key=lambda kv: kv[1][1])
+    n_shapes = n_dyn + n_sta
+    cand_per_frame = cand_all / K / world
+    pairs_per_frame = pairs_all / K
+    g_all = geometry_bytes(scene, np.ones(n_shapes, bool))
+    g_np = float(np.where(scene["shp_type"] == 3, 4 + 16 * scene["shp_count"].astype(np.float64),
+                          np.where(scene["shp_type"] == 0, 12, np.where(scene["shp_type"] == 1, 20, 16))).mean())
+    alg = {
+        # per-launch algorithmic bytes of each kernel (DESIGN.md "Roofline")
+        "k_apply_translates": n_dyn * (16 + 4 + 16 + 16 + 16 + 16 + 16 + 16),
+        "k_traverse<self>": n_dyn * (4 + 16 + 8) + (n_dyn - 1) * 64 + 0.8 * cand_per_frame * 8,
+        "k_traverse<cross>": n_dyn * (4 + 16 + 8) + (n_sta - 1) * 64 + 0.2 * cand_per_frame * 8,
+        "k_narrow": cand_per_frame * (8 + 2 * (4 + 4 + 16 + g_np)) + pairs_per_frame / world * 84,
+        "radix_sort(1 memset + 5 kernels)": n_dyn * (4 + 4 * 16),
+        "k_fit": n_dyn * (4 + 16 + 8 + 4) + (n_dyn - 1) * (64 + 4 + 4),
+        "k_karras_build": n_dyn * 4 + (n_dyn - 1) * (16 + 8),
+        "k_morton": n_dyn * (4 + 16 + 8),
+        "k_bounds": n_dyn * (4 + 16),
+        "k_bin_count": cand_per_frame * (8 + 8),
+        "k_bin_scatter": cand_per_frame * (8 + 8 + 8),
+    }
+    frame_alg = n_shapes * (20 + g_all + 16 + 16 + 8) + cand_per_frame * world * (16 + 2 * (20 + g_np)) + pairs_per_frame * 84
+    dom_avg_ms = dom_ms / max(dom_count, 1)
+    dom_bytes = float(alg.get(dom_name, 0.0))
+    achieved = dom_bytes / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
+    kernels = {k: {"launches": c, "avg_ms": ms / max(c, 1), "share": ms / max(sum(v[1] for v in profile.values()), 1e-9),
+                   "alg_gbs": (alg.get(k, 0.0) / (ms / max(c, 1) * 1e-3) / 1e9) if ms > 0 else 0.0}
+               for k, (c, ms) in sorted(profile.items(), key=lambda kv: -kv[1][1])}
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_avg_ms,
+                "frame": {"alg_bytes": frame_alg, "achieved": frame_alg / (ms_per_step * 1e-3) / 1e9,
+                          "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak},
+                "note": "latency/divergence-bound path (SURVEY.md 8(d)): whole-frame algorithmic traffic is ~0.2 GB",
+                "kernels": kernels}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {n_dyn} dynamic mixed circle/capsule/segment/polygon + {n_sta} static "
+                               f"polygons, per-frame jitter U(-0.5,0.5)^2, LCG seed 4242 (SURVEY.md 8(d) cfg 3)",
+                   "parallelism": f"morton-slab x{world}" if world > 1 else "single GPU",
+                   "l2": "inputs larger than L2 (fresh 16 MB move batch per frame; ~255 MB shape state + ~100 MB "
+                         "sort/tree buffers rewritten every frame vs 126 MB L2), no explicit flush",
+                   "pairs_per_frame": pairs_per_frame, "candidates_per_frame": cand_per_frame * world,
+                   "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()}},
+        "e2e": {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
+                "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
+                "moves_host_ms": 1e3 * float(np.mean(move_times)),
+                "call": "c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+    }
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank, world, local = dist_env()
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        scene, n_dyn, n_sta = build_scene(args.workload)
+        r = run_reference(args, scene, n_dyn, as_baseline=False)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {n_dyn} dynamic + {n_sta} static (same scene and seed as the own arm)",
+                           "pairs_per_frame": r["pairs_per_frame"]},
+                "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return 0
+
+    scene, n_dyn, n_sta = build_scene(args.workload)
+    out = run_b200(args, scene, n_dyn, n_sta, rank, world, local)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            r = run_reference(args, scene, n_dyn, as_baseline=True)
+            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")}
+            out["cpu_baseline"]["ms_per_step"] = r["ms_per_step"]
+        print(json.dumps(out))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,85 @@
+"""ctypes access to the C ABI of libc2d_gpu.so (include/c2d_gpu.h) for bench.py / tests.
+
+Fails loudly when the library is missing: there is no CPU fallback anywhere in this package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GPU_LIB = os.path.join(HERE, "libc2d_gpu.so")
+
+EXPORTS = [
+    "c2d_gpu_create", "c2d_gpu_destroy", "c2d_gpu_last_error", "c2d_gpu_clear", "c2d_gpu_set_broadphase",
+    "c2d_gpu_set_shard", "c2d_gpu_set_profiling", "c2d_gpu_kernel_profile", "c2d_gpu_shape_add",
+    "c2d_gpu_shape_remove", "c2d_gpu_shape_set_active", "c2d_gpu_shape_translate", "c2d_gpu_shapes_translate",
+    "c2d_gpu_shape_move", "c2d_gpu_stage_translations", "c2d_gpu_apply_staged", "c2d_gpu_release_staged",
+    "c2d_gpu_flush", "c2d_gpu_collide", "c2d_gpu_collide_device", "c2d_gpu_raycast", "c2d_gpu_read_boxes",
+    "c2d_gpu_read_candidates", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
+    "c2d_gpu_compute_aabb_batch",
+]
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(GPU_LIB):
+            raise RuntimeError(f"{GPU_LIB} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(colli2de_b200 has no CPU fallback)")
+        _lib = C.CDLL(GPU_LIB)
+        _lib.c2d_gpu_last_error.restype = C.c_char_p
+        _lib.c2d_gpu_last_error.argtypes = [C.c_void_p]
+        _lib.c2d_gpu_set_profiling.argtypes = [C.c_void_p, C.c_int]
+        _lib.c2d_gpu_kernel_profile.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.c_int]
+        _lib.c2d_gpu_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        _lib.c2d_gpu_read_boxes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
+        _lib.c2d_gpu_read_candidates.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
+    return _lib
+
+
+def _check(ctx, rc: int):
+    if rc != 0:
+        raise RuntimeError(lib().c2d_gpu_last_error(ctx).decode())
+
+
+def set_profiling(ctx, on: bool):
+    _check(ctx, lib().c2d_gpu_set_profiling(ctx, 1 if on else 0))
+
+
+def set_shard(ctx, rank: int, world: int):
+    _check(ctx, lib().c2d_gpu_set_shard(ctx, rank, world))
+
+
+def kernel_profile(ctx, reset: bool = True) -> dict:
+    """{kernel name: (launches, total_ms)} accumulated since the last reset."""
+    buf = C.create_string_buffer(1 << 16)
+    _check(ctx, lib().c2d_gpu_kernel_profile(ctx, buf, len(buf), 1 if reset else 0))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, count, ms = line.split("\t")
+        out[name] = (int(count), float(ms))
+    return out
+
+
+def read_boxes(ctx, first: int, count: int):
+    import numpy as np
+
+    tight = np.zeros((count, 4), np.float32)
+    fat = np.zeros((count, 4), np.float32)
+    _check(ctx, lib().c2d_gpu_read_boxes(ctx, first, count, tight.ctypes.data_as(C.c_void_p),
+                                         fat.ctypes.data_as(C.c_void_p)))
+    return tight, fat
+
+
+def read_candidates(ctx):
+    import numpy as np
+
+    n = C.c_uint64(0)
+    _check(ctx, lib().c2d_gpu_read_candidates(ctx, 0, None, C.byref(n)))
+    out = np.zeros((n.value, 2), np.uint32)
+    if n.value:
+        _check(ctx, lib().c2d_gpu_read_candidates(ctx, n.value, out.ctypes.data_as(C.c_void_p), C.byref(n)))
+    return out

@@ -6,6 +6,7 @@
 #include "../../include/c2d_gpu.h"
 
 #include <cstring>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -92,6 +93,22 @@ enum Phase : uint32_t
 struct Round
 {
     size_t f0, a0, t0, m0; // begin offsets in the four logs; the end is the next round's begin (or the log size)
+    int staged = -1;       // >= 0: this round replays a device-resident translation batch instead of log ranges
+};
+
+struct ProfSpan
+{
+    const char* name;
+    cudaEvent_t start, stop;
+};
+
+// A batch of per-shape translations already resident in HBM (c2d_gpu_stage_translations).
+struct StagedBatch
+{
+    DevBuf<TransRec> records;
+    uint32_t n = 0;
+    bool touches[3] = {false, false, false};
+    bool live = false;
 };
 
 struct TreeBuf
@@ -139,6 +156,7 @@ struct c2d_gpu_ctx
     DevBuf<AddRec> dAddLog;
     DevBuf<TransRec> dTransLog;
     DevBuf<MoveRec> dMoveLog;
+    std::vector<StagedBatch*> staged;
 
     // trees
     TreeBuf tree[3];
@@ -153,6 +171,12 @@ struct c2d_gpu_ctx
     c2d_host::DevBuf<c2d_dev::PairOut> out;
     c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
     uint64_t lastCandidates = 0;
+
+    // optional per-kernel timing
+    bool profiling = false;
+    std::vector<c2d_host::ProfSpan> spans;
+    std::vector<cudaEvent_t> eventPool;
+    std::map<std::string, std::pair<double, uint32_t>> kernelTotals;
     uint32_t launches = 0;
     uint64_t h2dBytes = 0;
 };

@@ -42,6 +42,63 @@ int fail(c2d_gpu_ctx* ctx, const std::string& msg)
 namespace
 {
 
+// Optional per-kernel CUDA-event timing (c2d_gpu_set_profiling): one event pair around each launch, read back
+// after the frame's final synchronize.  Events on the launching stream add no synchronisation.
+struct ProfScope
+{
+    c2d_gpu_ctx* ctx;
+    cudaEvent_t stop = nullptr;
+    ProfScope(c2d_gpu_ctx* c, const char* name) : ctx(c)
+    {
+        if (!ctx->profiling)
+            return;
+        cudaEvent_t a = nullptr;
+        if (ctx->eventPool.size() >= 2)
+        {
+            a = ctx->eventPool.back();
+            ctx->eventPool.pop_back();
+            stop = ctx->eventPool.back();
+            ctx->eventPool.pop_back();
+        }
+        else
+        {
+            cudaEventCreate(&a);
+            cudaEventCreate(&stop);
+        }
+        cudaEventRecord(a, ctx->stream);
+        ctx->spans.push_back(ProfSpan{name, a, stop});
+    }
+    ~ProfScope()
+    {
+        if (stop)
+            cudaEventRecord(stop, ctx->stream);
+    }
+};
+#define C2D_TIMED(ctx, name, ...)                                                                                      \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        ProfScope _ps(ctx, name);                                                                                      \
+        __VA_ARGS__;                                                                                                   \
+    } while (0)
+
+// call after a stream synchronize
+void collect_profile(c2d_gpu_ctx* ctx)
+{
+    for (const ProfSpan& sp : ctx->spans)
+    {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, sp.start, sp.stop) == cudaSuccess)
+        {
+            auto& slot = ctx->kernelTotals[sp.name];
+            slot.first += ms;
+            slot.second += 1;
+        }
+        ctx->eventPool.push_back(sp.start);
+        ctx->eventPool.push_back(sp.stop);
+    }
+    ctx->spans.clear();
+}
+
 template <typename T>
 cudaError_t grow_array(T*& ptr, uint32_t oldCap, uint32_t newCap, size_t perShape, cudaStream_t stream)
 {
@@ -96,7 +153,7 @@ int ensure_shape_capacity(c2d_gpu_ctx* ctx, uint32_t want)
 void begin_round(c2d_gpu_ctx* ctx)
 {
     ++ctx->round;
-    ctx->rounds.push_back(Round{ctx->flagLog.size, ctx->addLog.size, ctx->transLog.size, ctx->moveLog.size});
+    ctx->rounds.push_back(Round{ctx->flagLog.size, ctx->addLog.size, ctx->transLog.size, ctx->moveLog.size, -1});
 }
 
 // Makes sure an op of `phase` on `shape` can join the current round (strictly increasing phase per shape).
@@ -169,6 +226,16 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
     for (size_t r = 0; r < ctx->rounds.size(); ++r)
     {
         const Round& cur = ctx->rounds[r];
+        if (cur.staged >= 0)
+        {
+            const StagedBatch* sb = ctx->staged[cur.staged];
+            if (sb->n)
+            {
+                C2D_TIMED(ctx, "k_apply_translates", k_apply_translates<<<blocks_for(sb->n, 256), 256, 0, s>>>(sb->records.ptr, sb->n, ctx->d));
+                ++ctx->launches;
+            }
+            continue;
+        }
         const bool lastRound = r + 1 == ctx->rounds.size();
         const size_t f1 = lastRound ? nf : ctx->rounds[r + 1].f0;
         const size_t a1 = lastRound ? na : ctx->rounds[r + 1].a0;
@@ -177,25 +244,25 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
         if (f1 > cur.f0)
         {
             const uint32_t n = static_cast<uint32_t>(f1 - cur.f0);
-            k_apply_flags<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dFlagLog.ptr + cur.f0, n, ctx->d);
+            C2D_TIMED(ctx, "k_apply_flags", k_apply_flags<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dFlagLog.ptr + cur.f0, n, ctx->d));
             ++ctx->launches;
         }
         if (a1 > cur.a0)
         {
             const uint32_t n = static_cast<uint32_t>(a1 - cur.a0);
-            k_apply_adds<<<blocks_for(static_cast<size_t>(n) * 32, 128), 128, 0, s>>>(ctx->dAddLog.ptr + cur.a0, n, ctx->d);
+            C2D_TIMED(ctx, "k_apply_adds", k_apply_adds<<<blocks_for(static_cast<size_t>(n) * 32, 128), 128, 0, s>>>(ctx->dAddLog.ptr + cur.a0, n, ctx->d));
             ++ctx->launches;
         }
         if (t1 > cur.t0)
         {
             const uint32_t n = static_cast<uint32_t>(t1 - cur.t0);
-            k_apply_translates<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dTransLog.ptr + cur.t0, n, ctx->d);
+            C2D_TIMED(ctx, "k_apply_translates", k_apply_translates<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dTransLog.ptr + cur.t0, n, ctx->d));
             ++ctx->launches;
         }
         if (m1 > cur.m0)
         {
             const uint32_t n = static_cast<uint32_t>(m1 - cur.m0);
-            k_apply_moves<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dMoveLog.ptr + cur.m0, n, ctx->d);
+            C2D_TIMED(ctx, "k_apply_moves", k_apply_moves<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dMoveLog.ptr + cur.m0, n, ctx->d));
             ++ctx->launches;
         }
     }
@@ -247,17 +314,20 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     uint32_t rb = blocks_for(n, 256);
     if (rb > 148 * 8)
         rb = 148 * 8;
-    k_bounds<<<rb, 256, 0, s>>>(t.members.ptr, n, ctx->d.fat, bounds);
-    k_morton<<<blocks_for(n, 256), 256, 0, s>>>(t.members.ptr, n, ctx->d.fat, bounds, t.keys.ptr, t.vals.ptr);
+    C2D_TIMED(ctx, "k_bounds", k_bounds<<<rb, 256, 0, s>>>(t.members.ptr, n, ctx->d.fat, bounds));
+    C2D_TIMED(ctx, "k_morton", k_morton<<<blocks_for(n, 256), 256, 0, s>>>(t.members.ptr, n, ctx->d.fat, bounds, t.keys.ptr, t.vals.ptr));
     ctx->launches += 2;
-    ctx->launches += radix_sort_pairs(s, t.keys.ptr, t.vals.ptr, t.keysTmp.ptr, t.valsTmp.ptr, n, 4, t.sortWs.ptr);
+    {
+        ProfScope ps(ctx, "radix_sort(1 memset + 5 kernels)");
+        ctx->launches += radix_sort_pairs(s, t.keys.ptr, t.vals.ptr, t.keysTmp.ptr, t.valsTmp.ptr, n, 4, t.sortWs.ptr);
+    }
     if (n > 1)
     {
         C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
-        k_karras_build<<<blocks_for(n - 1, 256), 256, 0, s>>>(t.keys.ptr, static_cast<int>(n), t.nodes.ptr,
-                                                             t.nodeParent.ptr, t.leafParent.ptr);
-        k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
-                                                 t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr);
+        C2D_TIMED(ctx, "k_karras_build", k_karras_build<<<blocks_for(n - 1, 256), 256, 0, s>>>(t.keys.ptr, static_cast<int>(n), t.nodes.ptr,
+                                                             t.nodeParent.ptr, t.leafParent.ptr));
+        C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
+                                                 t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
         ctx->launches += 2;
     }
     C2D_CUDA(ctx, cudaGetLastError());
@@ -275,7 +345,7 @@ int c2d_host::ensure_trees(c2d_gpu_ctx* ctx)
         any = any || ctx->treeDirty[body];
     if (!any)
         return 0;
-    k_frame_init<<<1, 32, 0, ctx->stream>>>(ctx->dScratch);
+    C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, ctx->stream>>>(ctx->dScratch));
     ++ctx->launches;
     for (int body = 0; body < 3; ++body)
         if (ctx->treeDirty[body])
@@ -299,9 +369,9 @@ void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)
     const uint32_t hi = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * (ctx->shardRank + 1) / ctx->shardWorld);
     if (hi <= lo)
         return;
-    k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+    C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
         q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
-        static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount);
+        static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount));
     ++ctx->launches;
 }
 
@@ -320,7 +390,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         return rc;
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
 
-    k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch);
+    C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
     ++ctx->launches;
     for (int body = 0; body < 3; ++body)
         if (ctx->treeDirty[body])
@@ -349,11 +419,11 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
 
         const uint32_t cap = static_cast<uint32_t>(ctx->cand.capacity);
         const uint32_t grid = 148 * 4;
-        k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch);
-        k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch);
-        k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr);
-        k_narrow<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->out.ptr,
-                                         static_cast<uint32_t>(ctx->out.capacity));
+        C2D_TIMED(ctx, "k_bin_count", k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch));
+        C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
+        C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
+        C2D_TIMED(ctx, "k_narrow", k_narrow<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                         static_cast<uint32_t>(ctx->out.capacity)));
         ctx->launches += 4;
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
@@ -377,7 +447,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         }
         if (outOverflow)
             C2D_CUDA(ctx, ctx->out.reserve(static_cast<size_t>(pairCount) + pairCount / 4));
-        k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch);
+        C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
         ++ctx->launches;
     }
     ctx->lastCandidates = candCount;
@@ -391,6 +461,8 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         C2D_CUDA(ctx, cudaStreamSynchronize(s));
         d2h += static_cast<uint64_t>(pairCount) * sizeof(PairOut);
     }
+    if (ctx->profiling)
+        collect_profile(ctx);
     if (outRecords)
         *outRecords = reinterpret_cast<const c2d_pair_record*>(ctx->hostOut.data);
     if (outCount)
@@ -481,9 +553,13 @@ void c2d_gpu_destroy(c2d_gpu_ctx* ctx)
     cudaFree(ctx->d.geom);
     cudaFree(ctx->dScratch);
     cudaFreeHost(ctx->hScratch);
+    for (StagedBatch* sb : ctx->staged)
+        delete sb;
     for (auto& ev : ctx->ev)
         if (ev)
             cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->eventPool)
+        cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -499,6 +575,9 @@ int c2d_gpu_clear(c2d_gpu_ctx* ctx)
     C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->flagLog.size = ctx->addLog.size = ctx->transLog.size = ctx->moveLog.size = 0;
     ctx->rounds.clear();
+    for (StagedBatch* sb : ctx->staged)
+        delete sb;
+    ctx->staged.clear();
     std::fill(ctx->hostMeta.begin(), ctx->hostMeta.end(), 0u);
     std::fill(ctx->stamp.begin(), ctx->stamp.end(), 0u);
     ctx->shapeSlots = 0;
@@ -520,6 +599,28 @@ int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size)
         return fail(ctx, "c2d_gpu_set_broadphase: unknown mode");
     ctx->broadphase = mode;
     ctx->cellSize = cell_size ? cell_size : 120;
+    return 0;
+}
+
+int c2d_gpu_set_profiling(c2d_gpu_ctx* ctx, int on)
+{
+    ctx->profiling = on != 0;
+    return 0;
+}
+
+int c2d_gpu_kernel_profile(c2d_gpu_ctx* ctx, char* buffer, uint64_t capacity, int reset)
+{
+    std::string text;
+    for (const auto& kv : ctx->kernelTotals)
+        text += kv.first + "\t" + std::to_string(kv.second.second) + "\t" + std::to_string(kv.second.first) + "\n";
+    if (buffer && capacity)
+    {
+        const size_t n = std::min<size_t>(text.size(), capacity - 1);
+        std::memcpy(buffer, text.data(), n);
+        buffer[n] = 0;
+    }
+    if (reset)
+        ctx->kernelTotals.clear();
     return 0;
 }
 
@@ -633,6 +734,76 @@ int c2d_gpu_shape_move(c2d_gpu_ctx* ctx, uint32_t shape, const c2d_xf* xf)
     r->csin = xf->csin;
     r->ccos = xf->ccos;
     ctx->treeDirty[meta_body(ctx->hostMeta[shape])] = true;
+    return 0;
+}
+
+int c2d_gpu_stage_translations(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy,
+                               uint32_t* out_handle)
+{
+    cudaSetDevice(ctx->device);
+    if (!out_handle || (n && (!shapes || !dxy)))
+        return fail(ctx, "c2d_gpu_stage_translations: bad argument");
+    StagedBatch* sb = new StagedBatch();
+    std::vector<TransRec> host(n);
+    std::vector<uint8_t> seen(ctx->hostMeta.size(), 0);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t s = shapes[i];
+        if (s >= ctx->hostMeta.size() || !(ctx->hostMeta[s] & META_ALIVE) || seen[s])
+        {
+            delete sb;
+            return fail(ctx, "c2d_gpu_stage_translations: unknown or repeated shape in batch");
+        }
+        seen[s] = 1;
+        sb->touches[meta_body(ctx->hostMeta[s])] = true;
+        host[i] = TransRec{s, dxy[2 * i], dxy[2 * i + 1], 0u};
+    }
+    sb->n = n;
+    sb->live = true;
+    if (n)
+    {
+        if (sb->records.reserve(n) != cudaSuccess ||
+            cudaMemcpy(sb->records.ptr, host.data(), n * sizeof(TransRec), cudaMemcpyHostToDevice) != cudaSuccess)
+        {
+            delete sb;
+            return fail(ctx, "c2d_gpu_stage_translations: device allocation / copy failed");
+        }
+    }
+    size_t slot = 0;
+    while (slot < ctx->staged.size() && ctx->staged[slot])
+        ++slot;
+    if (slot == ctx->staged.size())
+        ctx->staged.push_back(nullptr);
+    ctx->staged[slot] = sb;
+    *out_handle = static_cast<uint32_t>(slot);
+    return 0;
+}
+
+int c2d_gpu_apply_staged(c2d_gpu_ctx* ctx, uint32_t handle)
+{
+    if (handle >= ctx->staged.size() || !ctx->staged[handle])
+        return fail(ctx, "c2d_gpu_apply_staged: unknown handle");
+    const StagedBatch* sb = ctx->staged[handle];
+    // the batch is its own round (a barrier between everything logged before and after it), so no per-shape
+    // hazard stamps are needed: O(1) host work per frame.  Shapes removed since staging must not be in it.
+    begin_round(ctx);
+    ctx->rounds.back().staged = static_cast<int>(handle);
+    begin_round(ctx);
+    for (int b = 0; b < 3; ++b)
+        if (sb->touches[b])
+            ctx->treeDirty[b] = true;
+    return 0;
+}
+
+int c2d_gpu_release_staged(c2d_gpu_ctx* ctx, uint32_t handle)
+{
+    cudaSetDevice(ctx->device);
+    if (handle >= ctx->staged.size() || !ctx->staged[handle])
+        return fail(ctx, "c2d_gpu_release_staged: unknown handle");
+    if (int rc = flush(ctx)) // a logged round may still reference the batch
+        return rc;
+    delete ctx->staged[handle];
+    ctx->staged[handle] = nullptr;
     return 0;
 }
 

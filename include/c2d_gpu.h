@@ -125,6 +125,11 @@ int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size);
  * query leaf lies in Morton-rank slab `rank` of `world`.  Default 0 of 1. */
 int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world);
 
+/* Per-kernel CUDA-event timing of the queries (off by default).  c2d_gpu_kernel_profile writes one line per
+ * kernel name, "name<TAB>launches<TAB>total_ms", accumulated since the last reset. */
+int c2d_gpu_set_profiling(c2d_gpu_ctx* ctx, int on);
+int c2d_gpu_kernel_profile(c2d_gpu_ctx* ctx, char* buffer, uint64_t capacity, int reset);
+
 /* ---- mutation log ----------------------------------------------------------------------------- */
 /* Registry::addShape (Registry.hpp:272-330): tight AABB = computeAABB(shape, xf) (ShapesUtils.hpp:13-60),
  * leaf AABB = tight.fattened(0) (DynamicBVH.hpp:352-365).  `prev` is the bullet's previous transform
@@ -145,6 +150,14 @@ int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shape
  * moveDynamicShape / moveBulletShape 191-212): tight = computeAABB at the new transform `xf`
  * (the host has already applied Transform += delta), same leaf rule. */
 int c2d_gpu_shape_move(c2d_gpu_ctx* ctx, uint32_t shape, const c2d_xf* xf);
+/* Device-resident move batches (extension; the reference has only the per-entity call): the per-shape
+ * translations are uploaded ONCE, then each c2d_gpu_apply_staged logs "translate all of them" in O(1) host
+ * work and no PCIe traffic - the moveEntity(Translation) semantics above, n shapes at a time.  A batch must
+ * name each shape at most once and only live shapes (also at apply time). */
+int c2d_gpu_stage_translations(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy,
+                               uint32_t* out_handle);
+int c2d_gpu_apply_staged(c2d_gpu_ctx* ctx, uint32_t handle);
+int c2d_gpu_release_staged(c2d_gpu_ctx* ctx, uint32_t handle);
 /* Replays the log on the device now (otherwise done by the next query). */
 int c2d_gpu_flush(c2d_gpu_ctx* ctx);
 

@@ -182,6 +182,9 @@ class Registry
             mLiveEntities = std::exchange(o.mLiveEntities, 0);
             mShapes = std::move(o.mShapes);
             mFreeShapeIds = std::move(o.mFreeShapeIds);
+            mStaged = std::move(o.mStaged);
+            mPendingApplies = std::move(o.mPendingApplies);
+            mStructureEpoch = o.mStructureEpoch;
             mStats = o.mStats;
         }
         return *this;
@@ -215,6 +218,14 @@ class Registry
     // rayCast for a batch of rays; hits of ray i are result[i] in std::set order.
     std::vector<std::vector<RayHit>> rayCastBatch(std::span<const Ray> rays, std::span<const InfiniteRay> infiniteRays,
                                                   BitMaskType maskBits = ~0ull) const;
+    // Device-resident move batches: stageMoves() uploads moveEntity(ids[i], deltas[i]) for all i ONCE and returns
+    // a handle; every applyStagedMoves(handle) then performs those moves with O(1) host work and no PCIe
+    // traffic (the host-side transforms are brought up to date lazily, on the next call that reads them).
+    // A batch names each entity at most once and is invalidated by removeShape / removeEntity / clear.
+    using MoveBatch = uint32_t;
+    MoveBatch stageMoves(std::span<const EntityId> ids, std::span<const Translation> deltas);
+    void applyStagedMoves(MoveBatch batch);
+    void releaseStagedMoves(MoveBatch batch);
     // Counters and CUDA-event timings of the last getCollidingPairs() / rayCast().
     const c2d_gpu_stats& lastQueryStats() const { return mStats; }
     // Runs the pipeline but leaves the records on the device; returns the number of colliding pairs.
@@ -322,9 +333,37 @@ class Registry
     template <typename RayT>
     std::set<RayHit> rayCastOne(RayT ray, BitMaskType maskBits, bool infinite) const;
 
+    struct StagedMoves
+    {
+        uint32_t handle = 0;
+        uint64_t epoch = 0;
+        bool live = false;
+        std::vector<uint32_t> entityIndex;
+        std::vector<Translation> deltas;
+    };
+    // applies the staged batches that were replayed on the device but not yet on the host-side transforms
+    void syncHost() const
+    {
+        for (const MoveBatch b : mPendingApplies)
+        {
+            const StagedMoves& batch = mStaged[b];
+            for (size_t i = 0; i < batch.entityIndex.size(); ++i)
+            {
+                EntityInfo& e = mEntities[batch.entityIndex[i]];
+                if (e.type == BodyType::Bullet)
+                    e.previous = e.transform;
+                e.transform.translation += batch.deltas[i];
+            }
+        }
+        mPendingApplies.clear();
+    }
+
     c2d_gpu_ctx* mCtx = nullptr;
     detail::IndexMap<EntityId, KeyOf> mIndex;
-    std::vector<EntityInfo> mEntities;
+    mutable std::vector<EntityInfo> mEntities;
+    std::vector<StagedMoves> mStaged;
+    mutable std::vector<MoveBatch> mPendingApplies;
+    uint64_t mStructureEpoch = 0;
     std::vector<uint32_t> mFreeEntitySlots;
     size_t mLiveEntities = 0;
     std::vector<ShapeLink> mShapes;
@@ -375,6 +414,7 @@ template <IsShape Shape>
 ShapeId Registry<EntityId, Method>::addShape(EntityId entityId, const Shape& shape, uint64_t categoryBits,
                                              uint64_t maskBits)
 {
+    syncHost();
     const uint32_t idx = indexOf(entityId);
     C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
     EntityInfo& entity = mEntities[idx];
@@ -416,6 +456,8 @@ template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::removeShape(ShapeId shapeId)
 {
     C2D_DEBUG_ASSERT(shapeId < mShapes.size(), "Shape ID out of bounds");
+    syncHost();
+    ++mStructureEpoch;
     ShapeLink& link = mShapes[shapeId];
     C2D_DEBUG_ASSERT(link.entity != kNone, "Shape with this ID does not exist in the entity");
     EntityInfo& entity = mEntities[link.entity];
@@ -442,6 +484,8 @@ void Registry<EntityId, Method>::setShapeActive(ShapeId shapeId, bool isActive)
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::removeEntity(EntityId id)
 {
+    syncHost();
+    ++mStructureEpoch;
     const uint32_t idx = indexOf(id);
     C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
     EntityInfo& entity = mEntities[idx];
@@ -462,6 +506,7 @@ void Registry<EntityId, Method>::removeEntity(EntityId id)
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::teleportEntity(EntityId id, const Transform& transform)
 {
+    syncHost();
     EntityInfo& entity = entityAt(id);
     // reference Registry.hpp:382-401: shapes are refit at `transform`, then previous <- current <- transform
     if (entity.type == BodyType::Bullet)
@@ -473,6 +518,7 @@ void Registry<EntityId, Method>::teleportEntity(EntityId id, const Transform& tr
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::teleportEntity(EntityId id, Translation translation)
 {
+    syncHost();
     const EntityInfo& entity = entityAt(id);
     moveEntity(id, translation - entity.transform.translation); // reference Registry.hpp:403-411
 }
@@ -480,6 +526,7 @@ void Registry<EntityId, Method>::teleportEntity(EntityId id, Translation transla
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::moveEntity(EntityId id, const Transform& delta)
 {
+    syncHost();
     EntityInfo& entity = entityAt(id);
     if (entity.type == BodyType::Bullet)
         entity.previous = entity.transform;
@@ -490,6 +537,8 @@ void Registry<EntityId, Method>::moveEntity(EntityId id, const Transform& delta)
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::moveEntity(EntityId id, Translation d)
 {
+    if (!mPendingApplies.empty())
+        syncHost();
     EntityInfo& entity = entityAt(id);
     for (uint32_t s = entity.firstShape; s != kNone; s = mShapes[s].next)
         check(c2d_gpu_shape_translate(mCtx, s, d.x, d.y));
@@ -507,8 +556,69 @@ void Registry<EntityId, Method>::moveEntities(std::span<const EntityId> ids, std
 }
 
 template <typename EntityId, PartitioningMethod Method>
+typename Registry<EntityId, Method>::MoveBatch Registry<EntityId, Method>::stageMoves(
+    std::span<const EntityId> ids, std::span<const Translation> deltas)
+{
+    C2D_DEBUG_ASSERT(ids.size() == deltas.size());
+    syncHost();
+    StagedMoves batch;
+    batch.epoch = mStructureEpoch;
+    batch.live = true;
+    batch.entityIndex.reserve(ids.size());
+    batch.deltas.assign(deltas.begin(), deltas.end());
+    std::vector<uint32_t> shapes;
+    std::vector<float> dxy;
+    shapes.reserve(ids.size());
+    dxy.reserve(ids.size() * 2);
+    for (size_t i = 0; i < ids.size(); ++i)
+    {
+        const uint32_t idx = indexOf(ids[i]);
+        C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
+        batch.entityIndex.push_back(idx);
+        for (uint32_t s = mEntities[idx].firstShape; s != kNone; s = mShapes[s].next)
+        {
+            shapes.push_back(s);
+            dxy.push_back(deltas[i].x);
+            dxy.push_back(deltas[i].y);
+        }
+    }
+    check(c2d_gpu_stage_translations(mCtx, static_cast<uint32_t>(shapes.size()), shapes.data(), dxy.data(),
+                                     &batch.handle));
+    MoveBatch slot = 0;
+    while (slot < mStaged.size() && mStaged[slot].live)
+        ++slot;
+    if (slot == mStaged.size())
+        mStaged.emplace_back();
+    mStaged[slot] = std::move(batch);
+    return slot;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::applyStagedMoves(MoveBatch batch)
+{
+    if (batch >= mStaged.size() || !mStaged[batch].live)
+        throw std::runtime_error("colli2de-b200: applyStagedMoves: unknown batch");
+    if (mStaged[batch].epoch != mStructureEpoch)
+        throw std::runtime_error("colli2de-b200: applyStagedMoves: shapes were removed since the batch was staged");
+    check(c2d_gpu_apply_staged(mCtx, mStaged[batch].handle));
+    mPendingApplies.push_back(batch);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::releaseStagedMoves(MoveBatch batch)
+{
+    if (batch >= mStaged.size() || !mStaged[batch].live)
+        return;
+    syncHost();
+    if (mStaged[batch].epoch == mStructureEpoch || true)
+        c2d_gpu_release_staged(mCtx, mStaged[batch].handle);
+    mStaged[batch] = StagedMoves{};
+}
+
+template <typename EntityId, PartitioningMethod Method>
 Transform Registry<EntityId, Method>::getEntityTransform(EntityId id) const
 {
+    syncHost();
     const uint32_t idx = indexOf(id);
     C2D_DEBUG_ASSERT(idx != kNone);
     return mEntities[idx].transform;
@@ -518,6 +628,9 @@ template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::clear()
 {
     check(c2d_gpu_clear(mCtx));
+    ++mStructureEpoch;
+    mStaged.clear();
+    mPendingApplies.clear();
     mIndex.clear();
     mEntities.clear();
     mFreeEntitySlots.clear();

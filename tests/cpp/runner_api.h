@@ -60,6 +60,22 @@ void rn_clear(rn_ctx*);
 uint64_t rn_get_colliding_pairs(rn_ctx*, double* seconds);
 void rn_copy_pairs(rn_ctx*, void* out84);
 
+/* getCollidingPairs() whose records stay on the device (B200: Registry::countCollidingPairsOnDevice; the
+ * reference simply runs getCollidingPairs()).  Used for the device-resident timing of bench.py. */
+uint64_t rn_count_colliding_pairs_device(rn_ctx*, double* seconds);
+/* c2d_gpu_stats of the last query as 16 doubles (B200 only, zeros elsewhere):
+ * shapes_alive, candidates, pairs, h2d_bytes, d2h_bytes, kernel_launches, retries,
+ * ms_refit, ms_build, ms_broad, ms_narrow, ms_device, ms_total, 0, 0, 0 */
+void rn_query_stats(rn_ctx*, double* out16);
+/* Move batches: stage n (entity, translation) moves, then apply them any number of times.  B200: the batch
+ * lives in HBM (Registry::stageMoves / applyStagedMoves); reference: a loop of moveEntity(id, Translation). */
+int rn_stage_translations(rn_ctx*, uint32_t n, const uint32_t* ids, const float* dxy);
+void rn_apply_staged(rn_ctx*, int handle);
+void rn_release_staged(rn_ctx*, int handle);
+
+/* B200 only: the c2d_gpu_ctx* behind the Registry (Registry::nativeContext); NULL elsewhere. */
+void* rn_native_context(rn_ctx*);
+
 /* rayCast() looped over n rays; offsets has n+1 entries; hits are concatenated in std::set order. */
 uint64_t rn_raycast(rn_ctx*, uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
                     uint64_t* offsets, double* seconds);

@@ -124,6 +124,12 @@ def load(name: str) -> C.CDLL:
         "rn_clear": (None, [vp]),
         "rn_get_colliding_pairs": (u64, [vp, pd]),
         "rn_copy_pairs": (None, [vp, vp]),
+        "rn_count_colliding_pairs_device": (u64, [vp, pd]),
+        "rn_query_stats": (None, [vp, pd]),
+        "rn_native_context": (vp, [vp]),
+        "rn_stage_translations": (i32, [vp, u32, pu32, pf]),
+        "rn_apply_staged": (None, [vp, i32]),
+        "rn_release_staged": (None, [vp, i32]),
         "rn_raycast": (u64, [vp, u32, pf, pu8, pu64, pu64, pd]),
         "rn_copy_hits": (None, [vp, vp]),
         "rn_collide": (None, [u32, pu8, pf, pu8, pf, pu8, pf, pu8, pf, vp, pu8]),
@@ -272,6 +278,37 @@ class Backend:
         if n:
             self.lib.rn_copy_pairs(self.ctx, out.ctypes.data_as(C.c_void_p))
         return (out, sec.value) if with_time else out
+
+    STAT_FIELDS = ("shapes_alive", "candidates", "pairs", "h2d_bytes", "d2h_bytes", "kernel_launches", "retries",
+                   "ms_refit", "ms_build", "ms_broad", "ms_narrow", "ms_device", "ms_total")
+
+    def count_pairs_device(self):
+        sec = C.c_double(0.0)
+        n = int(self.lib.rn_count_colliding_pairs_device(self.ctx, C.byref(sec)))
+        self._check()
+        return n, sec.value
+
+    def native_context(self):
+        return self.lib.rn_native_context(self.ctx)
+
+    def stats(self) -> dict:
+        out = np.zeros(16, np.float64)
+        self.lib.rn_query_stats(self.ctx, _p(out, C.c_double))
+        return dict(zip(self.STAT_FIELDS, out.tolist()))
+
+    def stage_translations(self, ids, dxy) -> int:
+        ids, dxy = _u32(ids), _f32(dxy)
+        h = int(self.lib.rn_stage_translations(self.ctx, len(ids), _p(ids, C.c_uint32), _p(dxy, C.c_float)))
+        self._check()
+        return h
+
+    def apply_staged(self, handle: int):
+        self.lib.rn_apply_staged(self.ctx, handle)
+        self._check()
+
+    def release_staged(self, handle: int):
+        self.lib.rn_release_staged(self.ctx, handle)
+        self._check()
 
     def raycast(self, ray4, infinite=None, masks=None, with_time=False):
         ray4 = _f32(ray4).reshape(-1, 4)
