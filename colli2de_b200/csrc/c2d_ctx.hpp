@@ -168,6 +168,7 @@ struct c2d_gpu_ctx
     c2d_dev::FrameScratch* dScratch = nullptr;
     c2d_dev::FrameScratch* hScratch = nullptr; // pinned
     c2d_host::DevBuf<uint2> cand, binned;
+    c2d_host::DevBuf<uint4> hits;
     c2d_host::DevBuf<c2d_dev::PairOut> out;
     c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
     uint64_t lastCandidates = 0;

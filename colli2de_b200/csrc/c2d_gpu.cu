@@ -402,6 +402,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
     {
         C2D_CUDA(ctx, ctx->cand.reserve(1u << 16));
         C2D_CUDA(ctx, ctx->binned.reserve(1u << 16));
+        C2D_CUDA(ctx, ctx->hits.reserve(1u << 16));
     }
     if (ctx->out.capacity == 0)
         C2D_CUDA(ctx, ctx->out.reserve(1u << 15));
@@ -422,9 +423,11 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         C2D_TIMED(ctx, "k_bin_count", k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch));
         C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
         C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
-        C2D_TIMED(ctx, "k_narrow", k_narrow<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->out.ptr,
+        C2D_TIMED(ctx, "k_narrow_filter", k_narrow_filter<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+        C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
+        C2D_TIMED(ctx, "k_narrow_manifold", k_narrow_manifold<<<148 * 8, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                          static_cast<uint32_t>(ctx->out.capacity)));
-        ctx->launches += 4;
+        ctx->launches += 6;
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
         C2D_CUDA(ctx, cudaStreamSynchronize(s));
@@ -444,6 +447,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         {
             C2D_CUDA(ctx, ctx->cand.reserve(static_cast<size_t>(candCount) + candCount / 4));
             C2D_CUDA(ctx, ctx->binned.reserve(ctx->cand.capacity));
+            C2D_CUDA(ctx, ctx->hits.reserve(ctx->cand.capacity));
         }
         if (outOverflow)
             C2D_CUDA(ctx, ctx->out.reserve(static_cast<size_t>(pairCount) + pairCount / 4));

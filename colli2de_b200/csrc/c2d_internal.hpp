@@ -98,6 +98,9 @@ struct FrameScratch
     uint32_t binCount[16];
     uint32_t binOffset[16];
     uint32_t binCursor[16];
+    uint32_t hitCount[16]; // narrowphase hits per bin (phase 1)
+    uint32_t hitBase[17];  // exclusive scan of hitCount; [16] = total
+    uint32_t _pad2[3];
 };
 
 struct PairOut // 84 bytes, = Registry<uint32_t>::EntityCollision

@@ -185,7 +185,11 @@ __global__ void k_frame_init(FrameScratch* fs)
         fs->binCount[t - 16] = 0;
         fs->binOffset[t - 16] = 0;
         fs->binCursor[t - 16] = 0;
+        fs->hitCount[t - 16] = 0;
+        fs->hitBase[t - 16] = 0;
     }
+    if (t == 15)
+        fs->hitBase[16] = 0;
 }
 
 __global__ void __launch_bounds__(256) k_bounds(const uint32_t* __restrict__ members, uint32_t n,
@@ -542,66 +546,143 @@ __device__ __forceinline__ XF xf_from(float4 f)
     return t;
 }
 
-__global__ void __launch_bounds__(128) k_narrow(const uint2* __restrict__ binned, uint32_t capacity, ShapeArrays s,
-                                                FrameScratch* fs, PairOut* __restrict__ out, uint32_t outCapacity)
+// Per-pair inputs shared by the two narrowphase phases.
+struct PairCtx
+{
+    ShapeRef A, B;
+    XF xa, xb;
+    uint32_t ea, eb;
+    bool bulletA, bulletB;
+};
+
+__device__ __forceinline__ bool load_pair(const ShapeArrays& s, uint2 p, PairCtx& c)
+{
+    const uint32_t ma = s.meta[p.x], mb = s.meta[p.y];
+    c.ea = s.entity[p.x];
+    c.eb = s.entity[p.y];
+    // self-collision and inactive shapes are rejected here, not in the broadphase (Registry.hpp:619-624)
+    if (c.ea == c.eb || !(ma & META_ACTIVE) || !(mb & META_ACTIVE))
+        return false;
+    c.A.type = static_cast<int>(meta_type(ma));
+    c.A.count = static_cast<int>(meta_count(ma));
+    c.A.g = s.geom + static_cast<size_t>(p.x) * 32;
+    c.B.type = static_cast<int>(meta_type(mb));
+    c.B.count = static_cast<int>(meta_count(mb));
+    c.B.g = s.geom + static_cast<size_t>(p.y) * 32;
+    c.xa = xf_from(s.xf[p.x]);
+    c.xb = xf_from(s.xf[p.y]);
+    c.bulletA = meta_body(ma) == 2u;
+    c.bulletB = meta_body(mb) == 2u;
+    return true;
+}
+
+// A is the bullet whenever exactly one side is (cross-tree pairs are emitted bullet-first)
+__device__ __forceinline__ void load_motions(const ShapeArrays& s, uint2 p, const PairCtx& c, Motion& moA, Motion& moB)
+{
+    const float4 pa = s.pxf[p.x], paa = s.pxa[p.x], ca = s.xa[p.x];
+    moA = motion_between(xf_from(pa), paa.x, paa.y, paa.z, c.xa, ca.x);
+    if (c.bulletB)
+    {
+        const float4 pb = s.pxf[p.y], pba = s.pxa[p.y], cb = s.xa[p.y];
+        moB = motion_between(xf_from(pb), pba.x, pba.y, pba.z, c.xb, cb.x);
+    }
+    else
+        moB = motion_fixed(c.xb);
+}
+
+// Phase 1: boolean test (areColliding / sweepHelper) of every binned candidate; hits are compacted per bin
+// into hits[binOffset[bin] + k] = (shapeA, shapeB, fraction bits, 0).  Most candidates are rejected here by
+// the cheap early-out paths, so the expensive manifold code of phase 2 runs on full warps of real hits.
+__global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__ binned, uint32_t capacity,
+                                                       ShapeArrays s, FrameScratch* fs, uint4* __restrict__ hits)
 {
     const uint32_t n = min(fs->candCount, capacity);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
     {
         const uint2 p = binned[i];
-        const uint32_t ma = s.meta[p.x], mb = s.meta[p.y];
-        const uint32_t ea = s.entity[p.x], eb = s.entity[p.y];
-        // self-collision and inactive shapes are rejected here, not in the broadphase (Registry.hpp:619-624)
-        if (ea == eb || !(ma & META_ACTIVE) || !(mb & META_ACTIVE))
+        PairCtx c;
+        if (!load_pair(s, p, c))
             continue;
-        ShapeRef A, B;
-        A.type = static_cast<int>(meta_type(ma));
-        A.count = static_cast<int>(meta_count(ma));
-        A.g = s.geom + static_cast<size_t>(p.x) * 32;
-        B.type = static_cast<int>(meta_type(mb));
-        B.count = static_cast<int>(meta_count(mb));
-        B.g = s.geom + static_cast<size_t>(p.y) * 32;
-        const XF xa = xf_from(s.xf[p.x]);
-        const XF xb = xf_from(s.xf[p.y]);
-        const bool ba = meta_body(ma) == 2u, bb = meta_body(mb) == 2u;
-
-        Manifold m;
+        float fraction = 0.0f;
         bool hit;
-        if (!ba && !bb)
+        if (!c.bulletA && !c.bulletB)
         {
-            hit = narrow_test<true>(A, xa, B, xb, m);
+            Manifold unused;
+            hit = narrow_test<false>(c.A, c.xa, c.B, c.xb, unused);
         }
         else
         {
-            // A is the bullet whenever exactly one side is (cross-tree pairs are emitted bullet-first)
-            const float4 pa = s.pxf[p.x], paa = s.pxa[p.x], ca = s.xa[p.x];
-            const Motion moA = motion_between(xf_from(pa), paa.x, paa.y, paa.z, xa, ca.x);
-            Motion moB;
-            if (bb)
-            {
-                const float4 pb = s.pxf[p.y], pba = s.pxa[p.y], cb = s.xa[p.y];
-                moB = motion_between(xf_from(pb), pba.x, pba.y, pba.z, xb, cb.x);
-            }
-            else
-                moB = motion_fixed(xb);
-            float fraction;
-            // a sweep hit is reported even if the final collide() yields no point (Registry.hpp:644,709:
-            // the optional holds the manifold as soon as sweep() returned a value)
-            hit = narrow_sweep(A, moA, B, moB, fraction, m);
+            Motion moA, moB;
+            load_motions(s, p, c, moA, moB);
+            hit = sweep_search(c.A, moA, c.B, moB, fraction);
         }
         if (!hit)
             continue;
+        // the bin of entry i: the binned array is the concatenation of the bins
+        int bin = 0;
+#pragma unroll
+        for (int b = 1; b < 15; ++b)
+            bin += (i >= fs->binOffset[b]) ? 1 : 0;
         cg::coalesced_group g = cg::coalesced_threads();
+        const cg::coalesced_group sameBin = cg::labeled_partition(g, bin);
         uint32_t base = 0;
-        if (g.thread_rank() == 0)
-            base = atomicAdd(&fs->outCount, g.size());
-        base = g.shfl(base, 0);
-        const uint32_t idx = base + g.thread_rank();
-        if (idx < outCapacity)
+        if (sameBin.thread_rank() == 0)
+            base = atomicAdd(&fs->hitCount[bin], sameBin.size());
+        base = sameBin.shfl(base, 0);
+        hits[fs->binOffset[bin] + base + sameBin.thread_rank()] = make_uint4(p.x, p.y, __float_as_uint(fraction), 0u);
+    }
+}
+
+__global__ void k_hit_scan(FrameScratch* fs)
+{
+    if (threadIdx.x == 0)
+    {
+        uint32_t run = 0;
+        for (int b = 0; b < 16; ++b)
         {
-            PairOut* o = out + idx;
-            o->entityA = ea;
-            o->entityB = eb;
+            fs->hitBase[b] = run;
+            run += fs->hitCount[b];
+        }
+        fs->hitBase[16] = run;
+        fs->outCount = run;
+    }
+}
+
+// Phase 2: the manifold of every hit (collide(), or collide() at the sweep fraction), written as an 84-byte
+// EntityCollision record at out[hitBase[bin] + k]: no atomics, output grouped by bin.
+__global__ void __launch_bounds__(128) k_narrow_manifold(const uint4* __restrict__ hits, ShapeArrays s,
+                                                         const FrameScratch* __restrict__ fs,
+                                                         PairOut* __restrict__ out, uint32_t outCapacity)
+{
+    const uint32_t total = fs->hitBase[16];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x)
+    {
+        int bin = 0;
+#pragma unroll
+        for (int b = 1; b < 15; ++b)
+            bin += (j >= fs->hitBase[b]) ? 1 : 0;
+        const uint4 h = hits[fs->binOffset[bin] + (j - fs->hitBase[bin])];
+        const uint2 p = make_uint2(h.x, h.y);
+        PairCtx c;
+        load_pair(s, p, c);
+        Manifold m;
+        if (!c.bulletA && !c.bulletB)
+        {
+            narrow_test<true>(c.A, c.xa, c.B, c.xb, m);
+        }
+        else
+        {
+            // a sweep hit is reported even if the final collide() yields no point (Registry.hpp:644,709:
+            // the optional holds the manifold as soon as sweep() returned a value)
+            Motion moA, moB;
+            load_motions(s, p, c, moA, moB);
+            sweep_manifold(c.A, moA, c.B, moB, __uint_as_float(h.z), m);
+        }
+        if (j < outCapacity)
+        {
+            PairOut* o = out + j;
+            o->entityA = c.ea;
+            o->entityB = c.eb;
             o->shapeA = p.x;
             o->shapeB = p.y;
             manifold_store(m, o->manifold);

@@ -564,68 +564,58 @@ __device__ __forceinline__ void shape_poly(const ShapeRef& s, const XF& t, PolyW
 }
 
 // collide(A, xa, B, xb) / areColliding(A, xa, B, xb).  kManifold=false never touches `m`.
+//
+// The 16 overloads reduce to five cores.  Overloads that the reference implements as "swap the arguments and
+// Manifold::reverse()" are brought into the core's argument order FIRST and reversed at the end, so each core
+// is instantiated once and a warp of one bin never splits over two copies of the same code:
+//   circle-X            -> core(X, xb, circle, xa).reverse()              (Collision.cpp:102-107,218-224,475-480)
+//   polygon-capsule|seg -> core(capsule, xb, polygon, xa).reverse()       (Collision.cpp:498-510)
+//   segment-capsule     -> core(capsule, xb, segCap, xa).reverse()        (Collision.cpp:240-246)
+//   segment-polygon     -> reverse(reverse(core(segCap, xa, polygon, xb))) = core(...)  (Collision.cpp:512-517)
 template <bool kManifold>
-__device__ bool narrow_test(const ShapeRef& A, const XF& xa, const ShapeRef& B, const XF& xb, Manifold& m)
+__device__ inline bool narrow_test(const ShapeRef& A, const XF& xa, const ShapeRef& B, const XF& xb, Manifold& m)
 {
     if (kManifold)
         manifold_clear(m);
-    const int ta = A.type, tb = B.type;
-    bool hit;
-    if (ta == T_CIRCLE && tb == T_CIRCLE)
-        return circle_circle<kManifold>(g2(A.g, 0), A.g[2], xa, g2(B.g, 0), B.g[2], xb, m);
+    const bool rev = (A.type == T_CIRCLE && B.type != T_CIRCLE) ||
+                     (A.type == T_POLYGON && (B.type == T_CAPSULE || B.type == T_SEGMENT)) ||
+                     (A.type == T_SEGMENT && B.type == T_CAPSULE);
+    const ShapeRef& S1 = rev ? B : A;
+    const ShapeRef& S2 = rev ? A : B;
+    const XF& x1 = rev ? xb : xa;
+    const XF& x2 = rev ? xa : xb;
 
-    if (ta == T_POLYGON || tb == T_POLYGON)
+    bool hit;
+    if (S1.type == T_CIRCLE)
     {
-        if (tb == T_CIRCLE) // Polygon, Circle
-            {
-                PolyW p;
-                poly_world(A.g, A.count, xa, p);
-                return poly_circle<kManifold>(p, xa, g2(B.g, 0), B.g[2], xb, m);
-            }
-        if (ta == T_CIRCLE) // Circle, Polygon -> collide(polygon, xb, circle, xa).reverse()  (Collision.cpp:475-480)
+        hit = circle_circle<kManifold>(g2(S1.g, 0), S1.g[2], x1, g2(S2.g, 0), S2.g[2], x2, m);
+    }
+    else if (S2.type == T_CIRCLE)
+    {
+        if (S1.type == T_POLYGON)
         {
             PolyW p;
-            poly_world(B.g, B.count, xb, p);
-            hit = poly_circle<kManifold>(p, xb, g2(A.g, 0), A.g[2], xa, m);
-            if (kManifold && hit)
-                manifold_reverse(m);
-            return hit;
+            poly_world(S1.g, S1.count, x1, p);
+            hit = poly_circle<kManifold>(p, x1, g2(S2.g, 0), S2.g[2], x2, m);
         }
-        PolyW pa, pb;
-        if (ta == T_POLYGON && tb != T_POLYGON)
-        {
-            // Polygon vs Capsule|Segment -> collide(capsule, xb, polygon, xa).reverse() (Collision.cpp:498-510)
-            shape_poly(B, xb, pa);
-            shape_poly(A, xa, pb);
-            hit = poly_poly<kManifold>(pa, xb, pb, xa, m);
-            if (kManifold && hit)
-                manifold_reverse(m);
-            return hit;
-        }
-        // Polygon-Polygon, Capsule-Polygon, Segment-Polygon (double reverse = identity, Collision.cpp:512-517)
-        shape_poly(A, xa, pa);
-        shape_poly(B, xb, pb);
-        return poly_poly<kManifold>(pa, xa, pb, xb, m);
+        else
+            hit = capsule_circle<kManifold>(g2(S1.g, 0), g2(S1.g, 1), cap_radius(S1), x1, g2(S2.g, 0), S2.g[2], x2, m);
     }
-
-    if (tb == T_CIRCLE) // Capsule|Segment, Circle
-        return capsule_circle<kManifold>(g2(A.g, 0), g2(A.g, 1), cap_radius(A), xa, g2(B.g, 0), B.g[2], xb, m);
-    if (ta == T_CIRCLE) // Circle, Capsule|Segment -> reversed (Collision.cpp:102-107,218-224)
+    else if (S2.type == T_POLYGON)
     {
-        hit = capsule_circle<kManifold>(g2(B.g, 0), g2(B.g, 1), cap_radius(B), xb, g2(A.g, 0), A.g[2], xa, m);
-        if (kManifold && hit)
-            manifold_reverse(m);
-        return hit;
+        PolyW p1, p2;
+        shape_poly(S1, x1, p1);
+        poly_world(S2.g, S2.count, x2, p2);
+        hit = poly_poly<kManifold>(p1, x1, p2, x2, m);
     }
-    if (ta == T_SEGMENT && tb == T_CAPSULE) // collide(capsule, xb, segCap, xa).reverse() (Collision.cpp:240-246)
+    else
     {
-        hit = capsule_capsule<kManifold>(g2(B.g, 0), g2(B.g, 1), B.g[4], xb, g2(A.g, 0), g2(A.g, 1), 0.0f, xa, m);
-        if (kManifold && hit)
-            manifold_reverse(m);
-        return hit;
+        hit = capsule_capsule<kManifold>(g2(S1.g, 0), g2(S1.g, 1), cap_radius(S1), x1, g2(S2.g, 0), g2(S2.g, 1),
+                                         cap_radius(S2), x2, m);
     }
-    return capsule_capsule<kManifold>(g2(A.g, 0), g2(A.g, 1), cap_radius(A), xa, g2(B.g, 0), g2(B.g, 1),
-                                      cap_radius(B), xb, m);
+    if (kManifold && rev && hit)
+        manifold_reverse(m);
+    return hit;
 }
 
 // computeAABB(shape, transform) (reference internal/geometry/ShapesUtils.hpp:13-60)
@@ -744,45 +734,59 @@ __device__ __forceinline__ XF motion_at(const Motion& mo, float f)
     return t;
 }
 
-// sweepHelper + final collide.  Returns true on hit; `fraction` = fractionUpper.
-// The t=0 test uses the start transforms AS STORED (Collision.hpp:75-76); every later sample, including
-// the final manifold at fraction 0, rebuilds sin/cos from the interpolated angle (Collision.hpp:85-99,260-264).
-__device__ inline bool narrow_sweep(const ShapeRef& A, const Motion& ma, const ShapeRef& B, const Motion& mb,
-                             float& fraction, Manifold& m)
+// sweepHelper (Collision.hpp:71-124 / 151-213).  Returns true on hit with `fraction` = fractionUpper.
+// The t=0 test uses the start transforms AS STORED (Collision.hpp:75-76); every later sample rebuilds sin/cos
+// from the interpolated angle (Collision.hpp:85-99).
+__device__ inline bool sweep_search(const ShapeRef& A, const Motion& ma, const ShapeRef& B, const Motion& mb,
+                                    float& fraction)
 {
     Manifold dummy;
-    float hitFraction;
     if (narrow_test<false>(A, ma.start, B, mb.start, dummy))
-        hitFraction = 0.0f;
-    else
     {
-        float lower = 0.0f, upper = 1.0f;
-        for (int step = 1; step <= 8; ++step)
-        {
-            const float f = static_cast<float>(step) / 8.0f;
-            if (narrow_test<false>(A, motion_at(ma, f), B, motion_at(mb, f), dummy))
-            {
-                lower = static_cast<float>(step - 1) / 8.0f;
-                upper = f;
-                break;
-            }
-        }
-        if (lower == 0.0f && upper == 1.0f)
-            return false;
-        for (int it = 0; it < 10; ++it)
-        {
-            const float mid = 0.5f * (lower + upper);
-            if (narrow_test<false>(A, motion_at(ma, mid), B, motion_at(mb, mid), dummy))
-                upper = mid;
-            else
-                lower = mid;
-            if (upper - lower < 1e-6f)
-                break;
-        }
-        hitFraction = upper;
+        fraction = 0.0f;
+        return true;
     }
-    fraction = hitFraction;
-    narrow_test<true>(A, motion_at(ma, hitFraction), B, motion_at(mb, hitFraction), m);
+    float lower = 0.0f, upper = 1.0f;
+    for (int step = 1; step <= 8; ++step)
+    {
+        const float f = static_cast<float>(step) / 8.0f;
+        if (narrow_test<false>(A, motion_at(ma, f), B, motion_at(mb, f), dummy))
+        {
+            lower = static_cast<float>(step - 1) / 8.0f;
+            upper = f;
+            break;
+        }
+    }
+    if (lower == 0.0f && upper == 1.0f)
+        return false;
+    for (int it = 0; it < 10; ++it)
+    {
+        const float mid = 0.5f * (lower + upper);
+        if (narrow_test<false>(A, motion_at(ma, mid), B, motion_at(mb, mid), dummy))
+            upper = mid;
+        else
+            lower = mid;
+        if (upper - lower < 1e-6f)
+            break;
+    }
+    fraction = upper;
+    return true;
+}
+
+// The manifold of a sweep hit: collide() at the transforms rebuilt from the hit fraction — also for fraction 0
+// (Collision.hpp:260-264, 296-306).
+__device__ inline void sweep_manifold(const ShapeRef& A, const Motion& ma, const ShapeRef& B, const Motion& mb,
+                                      float fraction, Manifold& m)
+{
+    narrow_test<true>(A, motion_at(ma, fraction), B, motion_at(mb, fraction), m);
+}
+
+__device__ inline bool narrow_sweep(const ShapeRef& A, const Motion& ma, const ShapeRef& B, const Motion& mb,
+                                    float& fraction, Manifold& m)
+{
+    if (!sweep_search(A, ma, B, mb, fraction))
+        return false;
+    sweep_manifold(A, ma, B, mb, fraction, m);
     return true;
 }
 
