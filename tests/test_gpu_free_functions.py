@@ -10,6 +10,7 @@ from tests import gen, harness as H, parity as P
 pytestmark = pytest.mark.gpu
 
 ORACLE = "reference" if H.available("reference") else "oracle"
+SUBJECT = "b200"
 
 
 def _assert_manifolds(exp, got, what):
@@ -26,7 +27,7 @@ def test_collide_all_type_pairs():
     A, B = gen.random_shapes(rng, n, ta), gen.random_shapes(rng, n, tb)
     xa, xb = H.xf5_from_xf3(gen.random_xf3(rng, n, 1.2)), H.xf5_from_xf3(gen.random_xf3(rng, n, 1.2))
     em, ef = H.collide(ORACLE, A, xa, B, xb)
-    gm, gf = H.collide("b200", A, xa, B, xb)
+    gm, gf = H.collide(SUBJECT, A, xa, B, xb)
     assert np.array_equal(ef, gf)
     assert 0.15 < ef.mean() < 0.9
     nb = _assert_manifolds(em, gm, "collide")
@@ -43,7 +44,7 @@ def test_collide_drifted_rotation():
     xa[:, 4] *= np.float32(0.9)
     xb[:, 3] *= np.float32(1.1)
     em, ef = H.collide(ORACLE, A, xa, B, xb)
-    gm, gf = H.collide("b200", A, xa, B, xb)
+    gm, gf = H.collide(SUBJECT, A, xa, B, xb)
     assert np.array_equal(ef, gf)
     assert _assert_manifolds(em, gm, "collide drifted") == 0
 
@@ -62,7 +63,7 @@ def test_sweep_translation_only(mode):
     b1[:, :2] += rng.uniform(-3, 3, (n, 2)).astype(np.float32)
     xa0, xa1, xb0, xb1 = (H.xf5_from_xf3(v) for v in (a0, a1, b0, b1))
     ef, em, eh = H.sweep(ORACLE, mode, A, xa0, xa1, B, xb0, xb1)
-    gf, gm, gh = H.sweep("b200", mode, A, xa0, xa1, B, xb0, xb1)
+    gf, gm, gh = H.sweep(SUBJECT, mode, A, xa0, xa1, B, xb0, xb1)
     assert np.array_equal(eh, gh)
     assert 0.05 < eh.mean() < 0.95
     assert np.array_equal(ef[eh > 0].view(np.uint32), gf[gh > 0].view(np.uint32)), "sweep fractions differ"
@@ -80,7 +81,7 @@ def test_sweep_rotating_within_tolerance():
     a1 = a0 + np.concatenate([rng.uniform(-5, 5, (n, 2)), rng.uniform(-1.5, 1.5, (n, 1))], 1).astype(np.float32)
     xa0, xa1, xb0 = (H.xf5_from_xf3(v) for v in (a0, a1, b0))
     ef, em, eh = H.sweep(ORACLE, 1, A, xa0, xa1, B, xb0)
-    gf, gm, gh = H.sweep("b200", 1, A, xa0, xa1, B, xb0)
+    gf, gm, gh = H.sweep(SUBJECT, 1, A, xa0, xa1, B, xb0)
     agree = eh == gh
     assert agree.mean() >= 0.999
     both = agree & (eh > 0) & (np.abs(ef - gf) < 1e-6)
@@ -102,7 +103,7 @@ def test_raycast_shapes_and_ray_sweep():
     # a few degenerate rays
     ray[:50, 2:] = np.where(inf[:50, None] == 1, 0.0, ray[:50, :2])
     et, eh = H.raycast_shape(ORACLE, S, xf, ray, inf)
-    gt, gh = H.raycast_shape("b200", S, xf, ray, inf)
+    gt, gh = H.raycast_shape(SUBJECT, S, xf, ray, inf)
     assert np.array_equal(eh, gh)
     assert 0.2 < eh.mean() < 0.95
     assert np.array_equal(et.view(np.uint32), gt.view(np.uint32)), "ray times not bit-identical"
@@ -110,7 +111,7 @@ def test_raycast_shapes_and_ray_sweep():
     xf1 = xf.copy()
     xf1[:, :2] += rng.uniform(-3, 3, (n, 2)).astype(np.float32)
     et, eh = H.sweep_ray(ORACLE, S, xf, xf1, ray, inf)
-    gt, gh = H.sweep_ray("b200", S, xf, xf1, ray, inf)
+    gt, gh = H.sweep_ray(SUBJECT, S, xf, xf1, ray, inf)
     assert np.array_equal(eh, gh)
     assert np.array_equal(et.view(np.uint32), gt.view(np.uint32))
 
@@ -121,5 +122,5 @@ def test_compute_aabb():
     S = gen.random_shapes(rng, n)
     xf = H.xf5_from_xf3(gen.random_xf3(rng, n, 100.0))
     e = H.compute_aabb(ORACLE, S, xf)
-    g = H.compute_aabb("b200", S, xf)
+    g = H.compute_aabb(SUBJECT, S, xf)
     assert np.array_equal(e.view(np.uint32), g.view(np.uint32))

@@ -11,10 +11,11 @@ from tests import harness as H, parity as P
 pytestmark = pytest.mark.gpu
 
 ORACLE = "reference" if H.available("reference") else "oracle"
+SUBJECT = "b200"
 
 
 def _both(scene, method=0, cell=120):
-    ref, gpu = H.Backend(ORACLE, method, cell), H.Backend("b200", method, cell)
+    ref, gpu = H.Backend(ORACLE, method, cell), H.Backend(SUBJECT, method, cell)
     ids_r = scenes.populate(ref, scene)
     ids_g = scenes.populate(gpu, scene)
     assert np.array_equal(ids_r, ids_g)
@@ -121,7 +122,7 @@ def test_transform_moves_teleports_removal_activation():
 def test_category_filter_and_same_entity():
     """(catA & catB) != 0 decides, the mask is ignored on this path; shapes of one entity
     never collide with each other (Registry.hpp:619-621)."""
-    for name in (ORACLE, "b200"):
+    for name in (ORACLE, SUBJECT):
         b = H.Backend(name)
         b.create_entities([1, 2, 3], [H.DYNAMIC, H.DYNAMIC, H.STATIC], np.zeros((3, 3), np.float32))
         g = np.zeros((4, 16), np.float32)
