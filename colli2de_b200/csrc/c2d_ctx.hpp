@@ -96,6 +96,18 @@ struct Round
     int staged = -1;       // >= 0: this round replays a device-resident translation batch instead of log ranges
 };
 
+// buffers of the batched rayCast (c2d_rays.cu)
+struct RayBuffers
+{
+    DevBuf<c2d_ray> dRays;
+    DevBuf<uint32_t> counts, finalCounts, sums, totals;
+    DevBuf<unsigned char> segs;
+    DevBuf<c2d_hit_record> out;
+    PinnedVec<c2d_hit_record> hostHits;
+    PinnedVec<uint64_t> hostOffsets;
+    PinnedVec<uint32_t> hostOffsets32;
+};
+
 struct ProfSpan
 {
     const char* name;
@@ -172,6 +184,7 @@ struct c2d_gpu_ctx
     c2d_host::DevBuf<c2d_dev::PairOut> out;
     c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
     uint64_t lastCandidates = 0;
+    c2d_host::RayBuffers rays;
 
     // optional per-kernel timing
     bool profiling = false;
