@@ -13,6 +13,7 @@
 #include <array>
 #include <chrono>
 #include <cstring>
+#include <malloc.h>
 #include <memory>
 #include <span>
 #include <string>
@@ -330,6 +331,16 @@ const char* rn_backend_name(void)
 
 rn_ctx* rn_create(int method, uint32_t cell_size)
 {
+    // Application-level allocator policy, applied to BOTH backends: getCollidingPairs() returns a fresh
+    // std::vector every frame (tens of MB at 1 M shapes); keeping freed blocks in the heap instead of
+    // mmap/munmap-ing them avoids a page-fault storm per frame.
+    static const bool mallocTuned = []
+    {
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);
+        return true;
+    }();
+    (void)mallocTuned;
     auto* ctx = new rn_ctx();
     try
     {

@@ -1,0 +1,59 @@
+"""CPU, world_size 2 over gloo: the multi-GPU plumbing around the path — Morton-rank slab bounds
+(c2d_gpu_set_shard uses the same arithmetic), the owner rule (a pair belongs to the rank that owns its query
+leaf) and the variable-size gather of 84-byte pair records to rank 0.  Each rank runs the C oracle on the full
+scene, keeps the pairs its slab owns, and rank 0 must end up with exactly the full set, no duplicates."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from colli2de_b200 import scenes, sharding
+from tests import harness as H, parity as P
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out_path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = scenes.mixed_scene(3000, 300, 260.0, seed=5)
+    b = H.Backend("oracle")
+    scenes.populate(b, sc)
+    pairs = b.get_colliding_pairs()
+    # query-leaf order stand-in: shapes sorted by id (the GPU uses Morton rank; the rule is the same)
+    n_query = 3300
+    lo, hi = sharding.slab_bounds(n_query, rank, world)
+    mine = pairs[(pairs["shapeA"] >= lo) & (pairs["shapeA"] < hi)]
+    gathered = sharding.gather_records(mine, dst=0)
+    total = sharding.allreduce_sum(len(mine))
+    if rank == 0:
+        np.save(out_path, gathered)
+        assert total == len(pairs)
+        assert len(gathered) == len(pairs)
+        assert P.sort_pairs(gathered).tobytes() == P.sort_pairs(pairs).tobytes()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not H.available("oracle"), reason="needs oracle/libc2d_oracle.so")
+def test_slab_sharding_and_gather_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path / "gathered.npy")), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "gathered.npy")
+
+
+def test_slab_bounds_partition():
+    for n in (0, 1, 7, 1000, 1_000_003):
+        for world in (1, 2, 3, 8):
+            edges = [sharding.slab_bounds(n, r, world) for r in range(world)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in edges]
+            assert max(sizes) - min(sizes) <= 1
