@@ -60,6 +60,24 @@ __device__ __forceinline__ RayQ make_ray(const RayIn& r, V2& second)
     return q;
 }
 
+// PartitioningMethod::Grid casts an infinite ray as the FINITE ray
+// Ray{start, start + direction.normalize() * cellSize * 50} through its cells (reference BroadPhaseTree.hpp:22,
+// 531-537): only leaves whose box that segment meets are found, and the leaf-box times are fractions of it.  The
+// narrowphase still receives the original infinite ray (Registry.hpp:1150-1153).  gridCell == 0: no truncation.
+__device__ __forceinline__ RayQ box_ray_of(const RayQ& q, float gridCell)
+{
+    if (!q.infinite || gridCell <= 0.0f)
+        return q;
+    const V2 unit = normalize(q.d);
+    const V2 span = (unit * gridCell) * 50.0f;
+    const V2 end = q.start + span;
+    RayQ b;
+    b.start = q.start;
+    b.d = end - q.start;
+    b.infinite = false;
+    return b;
+}
+
 // Visits every leaf of `tree` whose (fat) box the ray hits and whose category matches the mask
 // (node.matchesMask(maskBits), DynamicBVH.hpp:789).  FILL = false only counts.
 template <bool FILL>
@@ -129,14 +147,15 @@ __device__ uint32_t ray_tree(const RayQ& ray, unsigned long long mask, const Tre
 
 __global__ void __launch_bounds__(128) k_ray_count(const RayIn* __restrict__ rays, uint32_t n, TreeView t0, TreeView t1,
                                                    TreeView t2, const float4* __restrict__ fat,
-                                                   const uint64_t* __restrict__ category, uint32_t* __restrict__ counts)
+                                                   const uint64_t* __restrict__ category, uint32_t* __restrict__ counts,
+                                                   float gridCell)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
     V2 second;
     const RayIn r = rays[i];
-    const RayQ q = make_ray(r, second);
+    const RayQ q = box_ray_of(make_ray(r, second), gridCell);
     uint32_t c = ray_tree<false>(q, r.mask, t0, fat, category, 0, nullptr);
     c += ray_tree<false>(q, r.mask, t1, fat, category, 1, nullptr);
     c += ray_tree<false>(q, r.mask, t2, fat, category, 2, nullptr);
@@ -297,7 +316,8 @@ __device__ void heapsort(LeafHit* a, int n, Less less)
 
 __global__ void __launch_bounds__(128)
     k_ray_fill(const RayIn* __restrict__ rays, uint32_t n, TreeView t0, TreeView t1, TreeView t2, ShapeArrays s,
-               const uint32_t* __restrict__ offsets, LeafHit* __restrict__ segs, uint32_t* __restrict__ finalCounts)
+               const uint32_t* __restrict__ offsets, LeafHit* __restrict__ segs, uint32_t* __restrict__ finalCounts,
+               float gridCell)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -305,10 +325,11 @@ __global__ void __launch_bounds__(128)
     V2 second;
     const RayIn r = rays[i];
     const RayQ q = make_ray(r, second);
+    const RayQ bq = box_ray_of(q, gridCell);
     LeafHit* seg = segs + offsets[i];
-    uint32_t c = ray_tree<true>(q, r.mask, t0, s.fat, s.category, 0, seg);
-    c += ray_tree<true>(q, r.mask, t1, s.fat, s.category, 1, seg + c);
-    c += ray_tree<true>(q, r.mask, t2, s.fat, s.category, 2, seg + c);
+    uint32_t c = ray_tree<true>(bq, r.mask, t0, s.fat, s.category, 0, seg);
+    c += ray_tree<true>(bq, r.mask, t1, s.fat, s.category, 1, seg + c);
+    c += ray_tree<true>(bq, r.mask, t2, s.fat, s.category, 2, seg + c);
     if (c == 0)
     {
         finalCounts[i] = 0;
@@ -450,6 +471,7 @@ extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays
     uint64_t totalHits = 0, d2h = 0, leafHits = 0;
 
     const TreeView t0 = view_of(ctx, 0), t1 = view_of(ctx, 1), t2 = view_of(ctx, 2);
+    const float gridCell = ctx->broadphase == C2D_BROADPHASE_GRID ? static_cast<float>(static_cast<int32_t>(ctx->cellSize)) : 0.0f;
     const uint32_t kChunk = 1u << 20;
     for (uint32_t first = 0; first < n; first += kChunk)
     {
@@ -462,7 +484,7 @@ extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays
                                       cudaMemcpyHostToDevice, s));
         ctx->h2dBytes += static_cast<uint64_t>(m) * sizeof(c2d_ray);
         const RayIn* dr = reinterpret_cast<const RayIn*>(rb.dRays.ptr);
-        k_ray_count<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d.fat, ctx->d.category, rb.counts.ptr);
+        k_ray_count<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d.fat, ctx->d.category, rb.counts.ptr, gridCell);
         ++ctx->launches;
         if (int rc = exclusive_scan(ctx, rb.counts.ptr, m, rb.sums, rb.totals.ptr))
             return rc;
@@ -472,7 +494,7 @@ extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays
         leafHits += segTotal;
         C2D_CUDA(ctx, rb.segs.reserve(std::max<size_t>(segTotal, 1) * sizeof(LeafHit)));
         LeafHit* segs = reinterpret_cast<LeafHit*>(rb.segs.ptr);
-        k_ray_fill<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d, rb.counts.ptr, segs, rb.finalCounts.ptr);
+        k_ray_fill<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d, rb.counts.ptr, segs, rb.finalCounts.ptr, gridCell);
         ++ctx->launches;
         if (int rc = exclusive_scan(ctx, rb.finalCounts.ptr, m, rb.sums, rb.totals.ptr + 1))
             return rc;
