@@ -31,19 +31,36 @@ def test_grid_registry_pairs_and_rays():
         res = P.compare_pairs("reference", ref, idx, rp, gp, max_ambiguous=8)
         assert res["expected"] > 2000 and res["not_bit_identical"] == 0, res
         assert len(rp) >= res["expected"]  # the reference's list has the duplicates
-    # rays: finite rays as with None; infinite rays only reach 50 cells = 2000 units... use a small cell so the
-    # truncation actually cuts: cell 40 -> 2000 > scene; so also test a registry with cell 4 (reach 200)
+    # Rays.  The reference's grid walk (BroadPhaseTree.hpp:473-528) steps to `currentCell + direction` also for
+    # NEGATIVE directions, where the next grid line is the current cell's own lower edge: it then skips cells and
+    # MISSES hits (probe: 133 of 600 rays of this scene lose hits w.r.t. Registry<None>).  That bug is not
+    # reproduced; what is: the 50-cell truncation of infinite rays.  Hence:
+    #   (1) rays with both direction components > 0 (correct walk): hit-for-hit equal to the reference grid;
+    #   (2) every ray: the reference grid's hits are a subset of ours;
+    #   (3) reach >= scene (cell 40): ours == the reference with PartitioningMethod::None, hit-for-hit.
+    def keyset(h):
+        return set(zip(h["shape"].tolist(), h["entryTime"].tolist(), h["exitTime"].tolist()))
+
     for c in (cell, 4):
-        ref, gpu = H.Backend("reference", 1, c), H.Backend(SUBJECT, 1, c)
+        ref, gpu, none = H.Backend("reference", 1, c), H.Backend(SUBJECT, 1, c), H.Backend("reference", 0, c)
         small = scenes.mixed_scene(3000, 300, 520.0, seed=22)
-        scenes.populate(ref, small)
-        scenes.populate(gpu, small)
+        for b in (ref, gpu, none):
+            scenes.populate(b, small)
         ray4, inf = scenes.rays(600, 520.0, seed=9)
         eo, eh = ref.raycast(ray4, inf)
         go, gh = gpu.raycast(ray4, inf)
-        bad = 0
+        no, nh = none.raycast(ray4, inf)
+        d = np.where(inf[:, None] == 1, ray4[:, 2:], ray4[:, 2:] - ray4[:, :2])
+        positive = (d[:, 0] > 0) & (d[:, 1] > 0)
+        assert positive.sum() > 100
         for i in range(600):
-            a, b = eh[int(eo[i]):int(eo[i + 1])], gh[int(go[i]):int(go[i + 1])]
-            bad += not (len(a) == len(b) and a.tobytes() == b.tobytes())
-        assert bad <= 6, f"cell {c}: {bad} of 600 rays differ"
-        assert len(eh) > 600
+            e, g, n = (h[int(o[i]):int(o[i + 1])] for o, h in ((eo, eh), (go, gh), (no, nh)))
+            if positive[i]:
+                assert e.tobytes() == g.tobytes(), f"cell {c} ray {i}: differs from the reference grid"
+            assert keyset(e) <= keyset(g), f"cell {c} ray {i}: misses a hit the reference grid has"
+            assert keyset(g) <= keyset(n), f"cell {c} ray {i}: reports a hit Registry<None> does not have"
+            if c == cell:
+                assert g.tobytes() == n.tobytes(), f"ray {i}: differs from Registry<None> although within reach"
+        assert len(gh) > 600
+        if c == 4:
+            assert len(gh) < len(nh), "the 50-cell truncation must cut some infinite-ray hits"
