@@ -108,6 +108,15 @@ struct RayBuffers
     PinnedVec<uint32_t> hostOffsets32;
 };
 
+// buffers of the uniform-grid broadphase (c2d_grid.cu)
+struct GridBuffers
+{
+    DevBuf<uint32_t> ext, counts, sums, totals, keys, vals, keysTmp, valsTmp, sbody;
+    DevBuf<unsigned char> params, sortWs;
+    DevBuf<float4> sbox;
+    DevBuf<uint64_t> scat;
+};
+
 struct ProfSpan
 {
     const char* name;
@@ -185,6 +194,7 @@ struct c2d_gpu_ctx
     c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
     uint64_t lastCandidates = 0;
     c2d_host::RayBuffers rays;
+    c2d_host::GridBuffers grid;
 
     // optional per-kernel timing
     bool profiling = false;
@@ -202,6 +212,11 @@ namespace c2d_host
 int fail(c2d_gpu_ctx* ctx, const std::string& msg);
 int flush(c2d_gpu_ctx* ctx);        // replays the mutation log
 int ensure_trees(c2d_gpu_ctx* ctx); // flush + rebuild of the dirty trees (launches k_frame_init first)
+int upload_members(c2d_gpu_ctx* ctx, int body); // host member list of one tree -> device, if it changed
+// c2d_rays.cu
+int exclusive_scan_u32(c2d_gpu_ctx* ctx, uint32_t* data, uint32_t n, DevBuf<uint32_t>& sums, uint32_t* dTotal);
+// c2d_grid.cu
+int grid_broadphase(c2d_gpu_ctx* ctx);
 
 #define C2D_CUDA(ctx, call)                                                                                            \
     do                                                                                                                 \

@@ -274,6 +274,25 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
     return 0;
 }
 
+int c2d_host::upload_members(c2d_gpu_ctx* ctx, int body)
+{
+    if (!ctx->membersDirty[body])
+        return 0;
+    TreeBuf& t = ctx->tree[body];
+    const uint32_t n = static_cast<uint32_t>(ctx->members[body].size());
+    if (n)
+    {
+        C2D_CUDA(ctx, t.members.reserve(n));
+        C2D_CUDA(ctx, cudaMemcpyAsync(t.members.ptr, ctx->members[body].data(), n * sizeof(uint32_t),
+                                      cudaMemcpyHostToDevice, ctx->stream));
+        // the host vector may be modified right after this call returns
+        C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->h2dBytes += n * sizeof(uint32_t);
+    }
+    ctx->membersDirty[body] = false;
+    return 0;
+}
+
 namespace
 {
 
@@ -283,19 +302,8 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     TreeBuf& t = ctx->tree[body];
     cudaStream_t s = ctx->stream;
     const uint32_t n = static_cast<uint32_t>(ctx->members[body].size());
-    if (ctx->membersDirty[body])
-    {
-        if (n)
-        {
-            C2D_CUDA(ctx, t.members.reserve(n));
-            C2D_CUDA(ctx, cudaMemcpyAsync(t.members.ptr, ctx->members[body].data(), n * sizeof(uint32_t),
-                                          cudaMemcpyHostToDevice, s));
-            // the host vector may be modified right after this call returns
-            C2D_CUDA(ctx, cudaStreamSynchronize(s));
-            ctx->h2dBytes += n * sizeof(uint32_t);
-        }
-        ctx->membersDirty[body] = false;
-    }
+    if (int rc = upload_members(ctx, body))
+        return rc;
     t.n = n;
     ctx->treeDirty[body] = false;
     if (n == 0)
@@ -392,10 +400,12 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
 
     C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
     ++ctx->launches;
-    for (int body = 0; body < 3; ++body)
-        if (ctx->treeDirty[body])
-            if (int rc = build_tree(ctx, body))
-                return rc;
+    const bool useGrid = ctx->broadphase == C2D_BROADPHASE_GRID;
+    if (!useGrid) // the grid broadphase needs no tree; rays build them on demand (ensure_trees)
+        for (int body = 0; body < 3; ++body)
+            if (ctx->treeDirty[body])
+                if (int rc = build_tree(ctx, body))
+                    return rc;
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
 
     if (ctx->cand.capacity == 0)
@@ -410,12 +420,21 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
     uint32_t candCount = 0, pairCount = 0;
     while (true)
     {
+        if (useGrid)
+        {
+            ProfScope ps(ctx, "grid_broadphase(extent+count+scan+fill+sort+gather+pairs)");
+            if (int rc = grid_broadphase(ctx))
+                return rc;
+        }
+        else
+        {
         // groups in the reference's order (Registry.hpp:487-545)
         launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC);
         launch_traverse<true>(ctx, C2D_DYNAMIC, C2D_DYNAMIC);
         launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
         launch_traverse<false>(ctx, C2D_BULLET, C2D_DYNAMIC);
         launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
+        }
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
 
         const uint32_t cap = static_cast<uint32_t>(ctx->cand.capacity);
@@ -424,10 +443,13 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
         C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
         C2D_TIMED(ctx, "k_narrow_filter", k_narrow_filter<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+        C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
         C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
+        C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 8, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                         static_cast<uint32_t>(ctx->out.capacity)));
         C2D_TIMED(ctx, "k_narrow_manifold", k_narrow_manifold<<<148 * 8, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                          static_cast<uint32_t>(ctx->out.capacity)));
-        ctx->launches += 6;
+        ctx->launches += 8;
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
         C2D_CUDA(ctx, cudaStreamSynchronize(s));

@@ -12,6 +12,7 @@
 
 #include "c2d_internal.hpp"
 #include "c2d_narrow.cuh"
+#include "c2d_narrow_pp.cuh"
 
 #include <cooperative_groups.h>
 
@@ -597,8 +598,11 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
                                                        ShapeArrays s, FrameScratch* fs, uint4* __restrict__ hits)
 {
     const uint32_t n = min(fs->candCount, capacity);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    // the polygon bin of mode 0 is handled by k_narrow_filter_pp (8 lanes per pair)
+    const uint32_t ppOff = fs->binOffset[CORE_PP], ppCnt = fs->binCount[CORE_PP];
+    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n - ppCnt; i0 += gridDim.x * blockDim.x)
     {
+        const uint32_t i = i0 < ppOff ? i0 : i0 + ppCnt;
         const uint2 p = binned[i];
         PairCtx c;
         if (!load_pair(s, p, c))
@@ -655,8 +659,11 @@ __global__ void __launch_bounds__(128) k_narrow_manifold(const uint4* __restrict
                                                          PairOut* __restrict__ out, uint32_t outCapacity)
 {
     const uint32_t total = fs->hitBase[16];
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < total; j += gridDim.x * blockDim.x)
+    // the polygon bin of mode 0 is handled by k_narrow_manifold_pp
+    const uint32_t ppBase = fs->hitBase[CORE_PP], ppHits = fs->hitCount[CORE_PP];
+    for (uint32_t j0 = blockIdx.x * blockDim.x + threadIdx.x; j0 < total - ppHits; j0 += gridDim.x * blockDim.x)
     {
+        const uint32_t j = j0 < ppBase ? j0 : j0 + ppHits;
         int bin = 0;
 #pragma unroll
         for (int b = 1; b < 15; ++b)
@@ -688,6 +695,92 @@ __global__ void __launch_bounds__(128) k_narrow_manifold(const uint4* __restrict
             manifold_store(m, o->manifold);
         }
     }
+}
+
+// ---- polygon bin of mode 0 (polygon vs polygon | capsule | segment, no bullet): 8 lanes per pair --------------
+__device__ __forceinline__ bool pp_setup(const ShapeArrays& s, uint2 p, bool valid, PairCtx& c, bool& rev)
+{
+    rev = false;
+    if (!valid)
+        return false;
+    const bool ok = load_pair(s, p, c);
+    // collide(polygon, capsule|segment) = collide(capsule, tB, polygon, tA).reverse() (Collision.cpp:498-510)
+    rev = c.A.type == T_POLYGON && c.B.type != T_POLYGON;
+    return ok;
+}
+
+__global__ void __launch_bounds__(128) k_narrow_filter_pp(const uint2* __restrict__ binned, ShapeArrays s,
+                                                          FrameScratch* fs, uint4* __restrict__ hits)
+{
+    __shared__ OctetShared sh[16];
+    const uint32_t off = fs->binOffset[CORE_PP], cnt = fs->binCount[CORE_PP];
+    const int sub = threadIdx.x & 7, octetInWarp = (threadIdx.x & 31) >> 3, octetInBlock = threadIdx.x >> 3;
+    const uint32_t octetsPerGrid = gridDim.x * 16;
+    bool overflow = false;
+    for (uint32_t first = blockIdx.x * 16 + (octetInBlock & ~3u); first < cnt; first += octetsPerGrid)
+    {
+        const uint32_t idx = first + octetInWarp;
+        const bool valid = idx < cnt;
+        const uint2 p = valid ? binned[off + idx] : make_uint2(0, 0);
+        PairCtx c;
+        bool rev;
+        const bool alive = pp_setup(s, p, valid, c, rev);
+        Manifold unused;
+        const bool hit = octet_poly_poly<false>(alive, sub, octetInWarp, rev ? c.B : c.A, rev ? c.xb : c.xa,
+                                                rev ? c.A : c.B, rev ? c.xa : c.xb, sh[octetInBlock], unused, overflow);
+        __syncwarp();
+        if (hit && sub == 0)
+        {
+            cg::coalesced_group g = cg::coalesced_threads();
+            uint32_t base = 0;
+            if (g.thread_rank() == 0)
+                base = atomicAdd(&fs->hitCount[CORE_PP], g.size());
+            base = g.shfl(base, 0);
+            hits[off + base + g.thread_rank()] = make_uint4(p.x, p.y, 0u, 0u);
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128) k_narrow_manifold_pp(const uint4* __restrict__ hits, ShapeArrays s,
+                                                            FrameScratch* fs, PairOut* __restrict__ out,
+                                                            uint32_t outCapacity)
+{
+    __shared__ OctetShared sh[16];
+    const uint32_t off = fs->binOffset[CORE_PP], cnt = fs->hitCount[CORE_PP], outBase = fs->hitBase[CORE_PP];
+    const int sub = threadIdx.x & 7, octetInWarp = (threadIdx.x & 31) >> 3, octetInBlock = threadIdx.x >> 3;
+    const uint32_t octetsPerGrid = gridDim.x * 16;
+    bool overflow = false;
+    for (uint32_t first = blockIdx.x * 16 + (octetInBlock & ~3u); first < cnt; first += octetsPerGrid)
+    {
+        const uint32_t idx = first + octetInWarp;
+        const bool valid = idx < cnt;
+        const uint4 h = valid ? hits[off + idx] : make_uint4(0, 0, 0, 0);
+        const uint2 p = make_uint2(h.x, h.y);
+        PairCtx c;
+        bool rev;
+        const bool alive = pp_setup(s, p, valid, c, rev);
+        Manifold m;
+        const bool hit = octet_poly_poly<true>(alive, sub, octetInWarp, rev ? c.B : c.A, rev ? c.xb : c.xa,
+                                               rev ? c.A : c.B, rev ? c.xa : c.xb, sh[octetInBlock], m, overflow);
+        __syncwarp();
+        if (valid && sub == 0 && outBase + idx < outCapacity)
+        {
+            if (!hit)
+                manifold_clear(m); // cannot happen: phase 1 accepted the pair with the same arithmetic
+            else if (rev)
+                manifold_reverse(m);
+            PairOut* o = out + outBase + idx;
+            o->entityA = c.ea;
+            o->entityB = c.eb;
+            o->shapeA = p.x;
+            o->shapeB = p.y;
+            manifold_store(m, o->manifold);
+        }
+        __syncwarp();
+    }
+    if (overflow)
+        fs->clipOverflow = 1;
 }
 
 } // namespace c2d_dev

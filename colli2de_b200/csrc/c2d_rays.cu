@@ -427,17 +427,6 @@ __global__ void __launch_bounds__(128)
     }
 }
 
-int exclusive_scan(c2d_gpu_ctx* ctx, uint32_t* data, uint32_t n, DevBuf<uint32_t>& sums, uint32_t* dTotal)
-{
-    const uint32_t nblocks = (n + 1023) / 1024;
-    C2D_CUDA(ctx, sums.reserve(nblocks + 1));
-    k_scan_local<<<nblocks, 1024, 0, ctx->stream>>>(data, n, sums.ptr);
-    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(sums.ptr, nblocks, dTotal);
-    k_scan_add<<<nblocks, 1024, 0, ctx->stream>>>(data, n, sums.ptr);
-    ctx->launches += 3;
-    return 0;
-}
-
 TreeView view_of(const c2d_gpu_ctx* ctx, int body)
 {
     TreeView v;
@@ -448,6 +437,17 @@ TreeView view_of(const c2d_gpu_ctx* ctx, int body)
 }
 
 } // namespace
+
+int c2d_host::exclusive_scan_u32(c2d_gpu_ctx* ctx, uint32_t* data, uint32_t n, DevBuf<uint32_t>& sums, uint32_t* dTotal)
+{
+    const uint32_t nblocks = (n + 1023) / 1024;
+    C2D_CUDA(ctx, sums.reserve(nblocks + 1));
+    k_scan_local<<<nblocks, 1024, 0, ctx->stream>>>(data, n, sums.ptr);
+    k_scan_sums<<<1, 1024, 0, ctx->stream>>>(sums.ptr, nblocks, dTotal);
+    k_scan_add<<<nblocks, 1024, 0, ctx->stream>>>(data, n, sums.ptr);
+    ctx->launches += 3;
+    return 0;
+}
 
 extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, const c2d_hit_record** out_hits,
                                const uint64_t** out_offsets, c2d_gpu_stats* stats)
@@ -486,7 +486,7 @@ extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays
         const RayIn* dr = reinterpret_cast<const RayIn*>(rb.dRays.ptr);
         k_ray_count<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d.fat, ctx->d.category, rb.counts.ptr, gridCell);
         ++ctx->launches;
-        if (int rc = exclusive_scan(ctx, rb.counts.ptr, m, rb.sums, rb.totals.ptr))
+        if (int rc = exclusive_scan_u32(ctx, rb.counts.ptr, m, rb.sums, rb.totals.ptr))
             return rc;
         uint32_t segTotal = 0;
         C2D_CUDA(ctx, cudaMemcpyAsync(&segTotal, rb.totals.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -496,7 +496,7 @@ extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays
         LeafHit* segs = reinterpret_cast<LeafHit*>(rb.segs.ptr);
         k_ray_fill<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d, rb.counts.ptr, segs, rb.finalCounts.ptr, gridCell);
         ++ctx->launches;
-        if (int rc = exclusive_scan(ctx, rb.finalCounts.ptr, m, rb.sums, rb.totals.ptr + 1))
+        if (int rc = exclusive_scan_u32(ctx, rb.finalCounts.ptr, m, rb.sums, rb.totals.ptr + 1))
             return rc;
         uint32_t outTotal = 0;
         C2D_CUDA(ctx, cudaMemcpyAsync(&outTotal, rb.totals.ptr + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));

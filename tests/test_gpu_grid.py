@@ -64,3 +64,50 @@ def test_grid_registry_pairs_and_rays():
         assert len(gh) > 600
         if c == 4:
             assert len(gh) < len(nh), "the 50-cell truncation must cut some infinite-ray hits"
+
+
+def test_grid_and_lbvh_candidate_sets_are_identical():
+    """Secondary oracle: the uniform-grid sort-and-sweep and the LBVH traversal must produce
+    the same candidate SET (leaf boxes intersect & categories match), each pair exactly once."""
+    from colli2de_b200 import capi
+
+    sc = scenes.mixed_scene(40000, 4000, 900.0, seed=3, clustered=True)
+    sc["ent_body"][::50] = 2
+    sc["shp_cat"][::9] = 2
+    a, b = H.Backend(SUBJECT, 0), H.Backend(SUBJECT, 1, 25)
+    scenes.populate(a, sc)
+    scenes.populate(b, sc)
+    rng = scenes.LCG(12)
+    mov = np.nonzero(sc["ent_body"] != 0)[0].astype(np.uint32)
+    for frame in range(3):
+        d = scenes.jitter(rng, len(mov), 1.5)
+        a.move_translate(mov, d)
+        b.move_translate(mov, d)
+        pa, pb = a.get_colliding_pairs(), b.get_colliding_pairs()
+        ca = capi.read_candidates(a.native_context())
+        cb = capi.read_candidates(b.native_context())
+        ka = np.sort(ca[:, 0].astype(np.uint64) << np.uint64(32) | ca[:, 1].astype(np.uint64))
+        kb = np.sort(cb[:, 0].astype(np.uint64) << np.uint64(32) | cb[:, 1].astype(np.uint64))
+        assert len(np.unique(ka)) == len(ka) and len(np.unique(kb)) == len(kb), "duplicate candidates"
+        assert len(ka) > 20000 and np.array_equal(ka, kb)
+        assert P.sort_pairs(pa).tobytes() == P.sort_pairs(pb).tobytes()
+
+
+@pytest.mark.parametrize("n,expected_unique", [(1000, 22), (10000, 2386), (100000, 242098)])
+def test_repo_perf_scene_counts(n, expected_unique):
+    """cfg 1a — the reference's own benchmark scene (tests/registry/test_registry_performance.cpp:114-162) with
+    None and Grid(120): SURVEY.md [probe] unique pair counts 22 / 2 386 / 242 098, and exact parity with the
+    reference at 1 k and 10 k."""
+    sc = scenes.repo_perf_scene(n)
+    for method in (0, 1):
+        gpu = H.Backend(SUBJECT, method, 120)
+        scenes.populate(gpu, sc)
+        gpu.move_translate(sc["ent_id"], sc["first_move"])
+        gp = gpu.get_colliding_pairs()
+        assert len(gp) == expected_unique, (method, len(gp))
+        if n <= 10000 and H.available("reference"):
+            ref = H.Backend("reference", method, 120)
+            scenes.populate(ref, sc)
+            ref.move_translate(sc["ent_id"], sc["first_move"])
+            res = P.compare_pairs("reference", ref, P.SceneIndex(sc), ref.get_colliding_pairs(), gp, max_ambiguous=0)
+            assert res["not_bit_identical"] == 0, res
