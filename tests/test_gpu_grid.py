@@ -93,21 +93,24 @@ def test_grid_and_lbvh_candidate_sets_are_identical():
         assert P.sort_pairs(pa).tobytes() == P.sort_pairs(pb).tobytes()
 
 
-@pytest.mark.parametrize("n,expected_unique", [(1000, 22), (10000, 2386), (100000, 242098)])
-def test_repo_perf_scene_counts(n, expected_unique):
-    """cfg 1a — the reference's own benchmark scene (tests/registry/test_registry_performance.cpp:114-162) with
-    None and Grid(120): SURVEY.md [probe] unique pair counts 22 / 2 386 / 242 098, and exact parity with the
-    reference at 1 k and 10 k."""
+@pytest.mark.parametrize("n", [1000, 10000, 100000])
+def test_repo_perf_scene(n):
+    """cfg 1a - the reference's own benchmark scene (tests/registry/test_registry_performance.cpp:114-162: circles
+    r=12, Static/Dynamic/Bullet mix, every entity moved by (3,3)) with PartitioningMethod None and Grid(120): exact
+    parity with the reference (its Grid list de-duplicated) and None == Grid."""
     sc = scenes.repo_perf_scene(n)
+    idx = P.SceneIndex(sc)
+    results = []
     for method in (0, 1):
         gpu = H.Backend(SUBJECT, method, 120)
         scenes.populate(gpu, sc)
         gpu.move_translate(sc["ent_id"], sc["first_move"])
         gp = gpu.get_colliding_pairs()
-        assert len(gp) == expected_unique, (method, len(gp))
-        if n <= 10000 and H.available("reference"):
+        results.append(P.sort_pairs(gp).tobytes())
+        if H.available("reference"):
             ref = H.Backend("reference", method, 120)
             scenes.populate(ref, sc)
             ref.move_translate(sc["ent_id"], sc["first_move"])
-            res = P.compare_pairs("reference", ref, P.SceneIndex(sc), ref.get_colliding_pairs(), gp, max_ambiguous=0)
-            assert res["not_bit_identical"] == 0, res
+            res = P.compare_pairs("reference", ref, idx, ref.get_colliding_pairs(), gp, max_ambiguous=0)
+            assert res["not_bit_identical"] == 0 and res["expected"] > n // 60, res
+    assert results[0] == results[1]
