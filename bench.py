@@ -183,6 +183,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     scenes.populate(b, scene)
     ctx = b.native_context()
     capi.set_shard(ctx, rank, world)
+    capi.set_rebuild_period(ctx, args.rebuild_period)
     dyn = np.arange(n_dyn, dtype=np.uint32)
     K, W = args.steps, args.warmup
 
@@ -282,7 +283,11 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         "k_apply_translates": n_dyn * (16 + 4 + 16 + 16 + 16 + 16 + 16 + 16),
         "k_traverse<self>": n_dyn * (4 + 16 + 8) + (n_dyn - 1) * 64 + 0.8 * cand_per_frame * 8,
         "k_traverse<cross>": n_dyn * (4 + 16 + 8) + (n_sta - 1) * 64 + 0.2 * cand_per_frame * 8,
-        "k_narrow": cand_per_frame * (8 + 2 * (4 + 4 + 16 + g_np)) + pairs_per_frame / world * 84,
+        # narrowphase: the polygon bin (polygon vs polygon|capsule|segment) holds ~45 % of the candidates of this mix
+        "k_narrow_filter": 0.55 * cand_per_frame * (8 + 2 * (4 + 4 + 16 + 20)) + 0.2 * cand_per_frame * 16,
+        "k_narrow_filter_pp": 0.45 * cand_per_frame * (8 + 2 * (4 + 4 + 16 + 4 + 16 * 5.5)) + 0.15 * cand_per_frame * 16,
+        "k_narrow_manifold": 0.55 * pairs_per_frame / world * (16 + 2 * (4 + 4 + 16 + 20) + 84),
+        "k_narrow_manifold_pp": 0.45 * pairs_per_frame / world * (16 + 2 * (4 + 4 + 16 + 4 + 16 * 5.5) + 84),
         "radix_sort(1 memset + 5 kernels)": n_dyn * (4 + 4 * 16),
         "k_fit": n_dyn * (4 + 16 + 8 + 4) + (n_dyn - 1) * (64 + 4 + 4),
         "k_karras_build": n_dyn * 4 + (n_dyn - 1) * (16 + 8),
@@ -315,6 +320,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                    "parallelism": f"morton-slab x{world}" if world > 1 else "single GPU",
                    "l2": "inputs larger than L2 (fresh 16 MB move batch per frame; ~255 MB shape state + ~100 MB "
                          "sort/tree buffers rewritten every frame vs 126 MB L2), no explicit flush",
+                   "lbvh_rebuild_period": args.rebuild_period,
                    "pairs_per_frame": pairs_per_frame, "candidates_per_frame": cand_per_frame * world,
                    "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()}},
         "e2e": {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
@@ -336,6 +342,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rebuild-period", type=int, default=4,
+                    help="LBVH topology rebuilt every N-th frame, bottom-up refit in between (1 = every frame)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local = dist_env()

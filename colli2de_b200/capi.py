@@ -12,7 +12,7 @@ GPU_LIB = os.path.join(HERE, "libc2d_gpu.so")
 
 EXPORTS = [
     "c2d_gpu_create", "c2d_gpu_destroy", "c2d_gpu_last_error", "c2d_gpu_clear", "c2d_gpu_set_broadphase",
-    "c2d_gpu_set_shard", "c2d_gpu_set_profiling", "c2d_gpu_kernel_profile", "c2d_gpu_shape_add",
+    "c2d_gpu_set_shard", "c2d_gpu_set_rebuild_period", "c2d_gpu_set_profiling", "c2d_gpu_kernel_profile", "c2d_gpu_shape_add",
     "c2d_gpu_shape_remove", "c2d_gpu_shape_set_active", "c2d_gpu_shape_translate", "c2d_gpu_shapes_translate",
     "c2d_gpu_shape_move", "c2d_gpu_stage_translations", "c2d_gpu_apply_staged", "c2d_gpu_release_staged",
     "c2d_gpu_flush", "c2d_gpu_collide", "c2d_gpu_collide_device", "c2d_gpu_raycast", "c2d_gpu_read_boxes",
@@ -47,6 +47,11 @@ def _check(ctx, rc: int):
 
 def set_profiling(ctx, on: bool):
     _check(ctx, lib().c2d_gpu_set_profiling(ctx, 1 if on else 0))
+
+
+def set_rebuild_period(ctx, frames: int):
+    lib().c2d_gpu_set_rebuild_period.argtypes = [C.c_void_p, C.c_uint32]
+    _check(ctx, lib().c2d_gpu_set_rebuild_period(ctx, frames))
 
 
 def set_shard(ctx, rank: int, world: int):

@@ -141,6 +141,8 @@ struct TreeBuf
     DevBuf<uint32_t> arrival;
     DevBuf<unsigned char> sortWs;
     uint32_t n = 0; // leaves in the built tree
+    uint32_t age = 0; // frames since the topology (sort + Karras) was last rebuilt
+    bool membershipChanged = true;
 };
 
 } // namespace c2d_host
@@ -184,6 +186,7 @@ struct c2d_gpu_ctx
     int broadphase = C2D_BROADPHASE_LBVH;
     uint32_t cellSize = 120;
     uint32_t shardRank = 0, shardWorld = 1;
+    uint32_t rebuildPeriod = 4; // LBVH topology rebuilt every N-th dirty frame, refit in between
 
     // frame
     c2d_dev::FrameScratch* dScratch = nullptr;

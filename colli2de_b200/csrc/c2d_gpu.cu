@@ -15,6 +15,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -279,6 +280,7 @@ int c2d_host::upload_members(c2d_gpu_ctx* ctx, int body)
     if (!ctx->membersDirty[body])
         return 0;
     TreeBuf& t = ctx->tree[body];
+    t.membershipChanged = true;
     const uint32_t n = static_cast<uint32_t>(ctx->members[body].size());
     if (n)
     {
@@ -304,10 +306,25 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     const uint32_t n = static_cast<uint32_t>(ctx->members[body].size());
     if (int rc = upload_members(ctx, body))
         return rc;
+    // Topology (Morton order + Karras links) is reused for up to rebuildPeriod - 1 frames when only boxes moved:
+    // a bottom-up refit keeps every node box exact, so the candidate set is unchanged; only traversal efficiency
+    // decays slowly as shapes drift away from their Morton slots (the reference's DynamicBVH never rebuilds at all).
+    const bool topologyValid = t.n == n && n > 1 && !t.membershipChanged && t.age + 1 < ctx->rebuildPeriod;
+    t.membershipChanged = false;
     t.n = n;
     ctx->treeDirty[body] = false;
     if (n == 0)
         return 0;
+    if (topologyValid)
+    {
+        ++t.age;
+        C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
+        C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
+                                                 t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
+        ++ctx->launches;
+        return 0;
+    }
+    t.age = 0;
     C2D_CUDA(ctx, t.keys.reserve(n));
     C2D_CUDA(ctx, t.vals.reserve(n));
     C2D_CUDA(ctx, t.keysTmp.reserve(n));
@@ -647,6 +664,12 @@ int c2d_gpu_kernel_profile(c2d_gpu_ctx* ctx, char* buffer, uint64_t capacity, in
     }
     if (reset)
         ctx->kernelTotals.clear();
+    return 0;
+}
+
+int c2d_gpu_set_rebuild_period(c2d_gpu_ctx* ctx, uint32_t frames)
+{
+    ctx->rebuildPeriod = frames ? frames : 1;
     return 0;
 }
 

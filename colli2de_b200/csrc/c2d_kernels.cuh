@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(256) k_fit(int n, const uint32_t* __restrict__
         const uint32_t old = atomicAdd(&arrival[q], 1u);
         if (old == 0)
             return; // the sibling subtree is not finished: its last thread continues upward
-        __threadfence();
+        // the sibling's box was published before its own fence + atomic; ld.cg reads it from L2 (coherence point)
         const float4 sib = __ldcg(right ? &node->boxL : &node->boxR);
         const uint64_t sibCat = __ldcg(reinterpret_cast<const unsigned long long*>(right ? &node->catL : &node->catR));
         box.x = fminf(box.x, sib.x);

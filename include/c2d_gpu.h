@@ -121,6 +121,10 @@ const char* c2d_gpu_last_error(c2d_gpu_ctx* ctx);
 int c2d_gpu_clear(c2d_gpu_ctx* ctx);
 /* PartitioningMethod::None -> LBVH; PartitioningMethod::Grid(cellSize) -> uniform grid (BroadPhaseTree.hpp:96). */
 int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size);
+/* LBVH maintenance policy: the topology (Morton sort + Karras links) of a tree whose membership did not change is
+ * rebuilt every `frames`-th dirty frame and only refit (exact boxes, bottom-up) in between.  1 = rebuild every
+ * frame.  Default 4.  Results do not depend on it. */
+int c2d_gpu_set_rebuild_period(c2d_gpu_ctx* ctx, uint32_t frames);
 /* Multi-GPU sharding of the query leaves: this context emits only the pairs whose
  * query leaf lies in Morton-rank slab `rank` of `world`.  Default 0 of 1. */
 int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world);
