@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 GPU_LIB = os.path.join(HERE, "libc2d_gpu.so")
 RUNNER_LIB = os.path.join(HERE, "libc2d_b200_runner.so")
 
-CU_SOURCES = ["c2d_sort.cu", "c2d_gpu.cu", "c2d_batch.cu", "c2d_rays.cu", "c2d_grid.cu"]
+CU_SOURCES = ["c2d_sort.cu", "c2d_gpu.cu", "c2d_batch.cu", "c2d_rays.cu", "c2d_grid.cu", "c2d_query.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "-Xcompiler", "-fPIC",

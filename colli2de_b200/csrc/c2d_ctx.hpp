@@ -117,6 +117,15 @@ struct GridBuffers
     DevBuf<uint64_t> scat;
 };
 
+// buffers of the per-entity queries (c2d_query.cu)
+struct QueryBuffers
+{
+    DevBuf<uint32_t> shapes, counter;
+    DevBuf<uint8_t> flags;
+    DevBuf<c2d_dev::PairOut> out;
+    PinnedVec<c2d_dev::PairOut> hostOut;
+};
+
 struct ProfSpan
 {
     const char* name;
@@ -198,6 +207,7 @@ struct c2d_gpu_ctx
     uint64_t lastCandidates = 0;
     c2d_host::RayBuffers rays;
     c2d_host::GridBuffers grid;
+    c2d_host::QueryBuffers query;
 
     // optional per-kernel timing
     bool profiling = false;

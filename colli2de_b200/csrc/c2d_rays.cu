@@ -317,7 +317,7 @@ __device__ void heapsort(LeafHit* a, int n, Less less)
 __global__ void __launch_bounds__(128)
     k_ray_fill(const RayIn* __restrict__ rays, uint32_t n, TreeView t0, TreeView t1, TreeView t2, ShapeArrays s,
                const uint32_t* __restrict__ offsets, LeafHit* __restrict__ segs, uint32_t* __restrict__ finalCounts,
-               float gridCell)
+               float gridCell, bool firstHitOnly)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
@@ -336,6 +336,74 @@ __global__ void __launch_bounds__(128)
         return;
     }
     heapsort(seg, static_cast<int>(c), ByTreeTimeShape());
+
+    if (firstHitOnly)
+    {
+        // Registry::firstHitRayCast (Registry.hpp:866-1048): per tree, walk the leaf-box set in (entry, exit) order;
+        // a narrow hit that improves the best entry time re-arms the countdown to 5 more set entries; inactive
+        // shapes are skipped WITHOUT counting (the `continue` precedes the decrement).
+        bool have = false;
+        float bestEntry = FLT_MAX;
+        LeafHit best = seg[0];
+        uint32_t k = 0;
+        for (uint32_t tree = 0; tree < 3; ++tree)
+        {
+            uint32_t b = k;
+            while (k < c && seg[k].order == tree)
+                ++k;
+            // size of this tree's std::set = distinct (entry, exit) keys
+            uint32_t toCheck = 0;
+            for (uint32_t j = b; j < k; ++j)
+                if (j == b || seg[j].t0 != seg[j - 1].t0 || seg[j].t1 != seg[j - 1].t1)
+                    ++toCheck;
+            for (uint32_t j = b; j < k; ++j)
+            {
+                if (j != b && seg[j].t0 == seg[j - 1].t0 && seg[j].t1 == seg[j - 1].t1)
+                    continue;
+                const LeafHit h = seg[j];
+                const uint32_t meta = s.meta[h.shape];
+                if (!(meta & META_ACTIVE))
+                    continue;
+                ShapeRef S;
+                S.type = static_cast<int>(meta_type(meta));
+                S.count = static_cast<int>(meta_count(meta));
+                S.g = s.geom + static_cast<size_t>(h.shape) * 32;
+                const float4 x = s.xf[h.shape];
+                XF cur;
+                cur.tx = x.x;
+                cur.ty = x.y;
+                cur.s = x.z;
+                cur.c = x.w;
+                float t0n = 0.0f, t1n = 0.0f;
+                bool hit;
+                if (tree == 2u)
+                {
+                    const float4 p = s.pxf[h.shape], pa = s.pxa[h.shape], ca = s.xa[h.shape];
+                    XF prev;
+                    prev.tx = p.x;
+                    prev.ty = p.y;
+                    prev.s = p.z;
+                    prev.c = p.w;
+                    hit = ray_sweep(S, motion_between(prev, pa.x, pa.y, pa.z, cur, ca.x), q, second, t0n, t1n);
+                }
+                else
+                    hit = ray_shape(S, cur, q, second, t0n, t1n);
+                if (hit && t0n < bestEntry)
+                {
+                    bestEntry = t0n;
+                    best = LeafHit{t0n, t1n, h.shape, 0u};
+                    have = true;
+                    toCheck = 5;
+                }
+                if (--toCheck == 0)
+                    break;
+            }
+        }
+        if (have)
+            seg[0] = best;
+        finalCounts[i] = have ? 1u : 0u;
+        return;
+    }
 
     // leaf-box set dedupe, active check, narrowphase — survivors are compacted to the front in insertion order
     uint32_t kept = 0;
@@ -449,8 +517,23 @@ int c2d_host::exclusive_scan_u32(c2d_gpu_ctx* ctx, uint32_t* data, uint32_t n, D
     return 0;
 }
 
+static int raycast_impl(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, bool firstHitOnly,
+                        const c2d_hit_record** out_hits, const uint64_t** out_offsets, c2d_gpu_stats* stats);
+
 extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, const c2d_hit_record** out_hits,
                                const uint64_t** out_offsets, c2d_gpu_stats* stats)
+{
+    return raycast_impl(ctx, n, rays, false, out_hits, out_offsets, stats);
+}
+
+extern "C" int c2d_gpu_raycast_first(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, const c2d_hit_record** out_hits,
+                                     const uint64_t** out_offsets, c2d_gpu_stats* stats)
+{
+    return raycast_impl(ctx, n, rays, true, out_hits, out_offsets, stats);
+}
+
+static int raycast_impl(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, bool firstHitOnly,
+                        const c2d_hit_record** out_hits, const uint64_t** out_offsets, c2d_gpu_stats* stats)
 {
     const auto wall0 = std::chrono::steady_clock::now();
     cudaSetDevice(ctx->device);
@@ -494,7 +577,7 @@ extern "C" int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays
         leafHits += segTotal;
         C2D_CUDA(ctx, rb.segs.reserve(std::max<size_t>(segTotal, 1) * sizeof(LeafHit)));
         LeafHit* segs = reinterpret_cast<LeafHit*>(rb.segs.ptr);
-        k_ray_fill<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d, rb.counts.ptr, segs, rb.finalCounts.ptr, gridCell);
+        k_ray_fill<<<blocks_for(m, 128), 128, 0, s>>>(dr, m, t0, t1, t2, ctx->d, rb.counts.ptr, segs, rb.finalCounts.ptr, gridCell, firstHitOnly);
         ++ctx->launches;
         if (int rc = exclusive_scan_u32(ctx, rb.finalCounts.ptr, m, rb.sums, rb.totals.ptr + 1))
             return rc;

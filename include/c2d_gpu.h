@@ -170,8 +170,9 @@ int c2d_gpu_flush(c2d_gpu_ctx* ctx);
  * DynamicBVH.hpp:931-1031) + narrowphase (narrowPhaseCollision, Registry.hpp:608-710; collide / sweep).
  * *out_records points at context-owned pinned host memory valid until the next call on ctx.
  * Same-tree pairs are emitted with shapeA < shapeB; cross-tree pairs with A on the Dynamic/Bullet side.
- * Groups appear in the reference's order (Dyn x Static, Dyn x Dyn, Bullet x Static, Bullet x Dyn,
- * Bullet x Bullet), each sorted by (shapeA, shapeB).  `stats` may be NULL. */
+ * The ORDER of the records is unspecified (they are grouped by narrowphase code path); the reference's order
+ * (five groups, each sorted by (shapeA, shapeB), Registry.hpp:487-545) is obtained by sorting on
+ * (group, shapeA, shapeB) — parity is defined on the sorted tuples.  `stats` may be NULL. */
 int c2d_gpu_collide(c2d_gpu_ctx* ctx, const c2d_pair_record** out_records, uint64_t* out_count,
                     c2d_gpu_stats* stats);
 /* Same pipeline, results left on the device (no D2H of records): used to time the device-resident path.
@@ -183,6 +184,21 @@ int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats*
  * duplicates dropped like std::set does.  Buffers are context-owned pinned memory. */
 int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, const c2d_hit_record** out_hits,
                     const uint64_t** out_offsets, c2d_gpu_stats* stats);
+
+/* Registry::firstHitRayCast x n (Registry.hpp:866-1048): at most one hit per ray (out_offsets[i+1] - out_offsets[i]
+ * is 0 or 1) — the narrow hit with the smallest entry time found by the reference's search, which walks each tree's
+ * leaf-box hits in (entry, exit) order and stops 5 candidates after its last improvement. */
+int c2d_gpu_raycast_first(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, const c2d_hit_record** out_hits,
+                          const uint64_t** out_offsets, c2d_gpu_stats* stats);
+/* Registry::getCollisions (Registry.hpp:551-605) for the given shapes of one or more entities: every active listed
+ * shape queries the trees with its tight AABB (bullets: swept) and ITS MASK BITS, candidates go through
+ * narrowPhaseCollision.  Records are (queried shape, other shape); order unspecified. */
+int c2d_gpu_query_shapes(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const c2d_pair_record** out_records,
+                         uint64_t* out_count);
+/* Registry::areColliding (Registry.hpp:748-864) per shape pair: boolean narrowphase (bullets: boolean sweep),
+ * no broadphase; inactive shapes never collide. */
+int c2d_gpu_pairs_colliding(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapeA, const uint32_t* shapeB,
+                            uint8_t* out_colliding);
 
 /* ---- introspection (secondary oracles) --------------------------- */
 /* Tight (ShapeInstance::mBoundingBox) and fat (leaf) AABBs as (minx, miny, maxx, maxy); flushes first. */

@@ -14,10 +14,11 @@
 //
 // Differences a caller can observe (all documented in DESIGN.md):
 //   * the Registry is movable but not copyable (it owns device state);
-//   * inside one group of getCollidingPairs() the order of the pairs is by (shapeA, shapeB) as in the
-//     reference, but same-tree pairs always come out with shapeA < shapeB (the reference's A/B for those
-//     depends on its tree topology);
-//   * extensions: moveEntities() (batched moveEntity), lastQueryStats().
+//   * getCollidingPairs() returns the reference's SET of collisions in an unspecified order (the reference
+//     lists five body-type groups, each sorted by (shapeA, shapeB)); same-tree pairs always come out with
+//     shapeA < shapeB (the reference's A/B for those depends on its tree topology);
+//   * serialize / deserialize / operator== are not provided;
+//   * extensions: moveEntities(), stageMoves() / applyStagedMoves(), rayCastBatch(), lastQueryStats().
 #pragma once
 
 #include <colli2de/Manifold.hpp>
@@ -205,7 +206,11 @@ class Registry
     Transform getEntityTransform(EntityId id) const;
 
     std::vector<EntityCollision> getCollidingPairs();
+    std::vector<EntityCollision> getCollisions(EntityId id) const;
+    bool areColliding(EntityId a, EntityId b) const;
 
+    std::optional<RayHit> firstHitRayCast(Ray ray, BitMaskType maskBits = ~0ull) const;
+    std::optional<RayHit> firstHitRayCast(InfiniteRay ray, BitMaskType maskBits = ~0ull) const;
     std::set<RayHit> rayCast(Ray ray, BitMaskType maskBits = ~0ull) const;
     std::set<RayHit> rayCast(InfiniteRay ray, BitMaskType maskBits = ~0ull) const;
 
@@ -215,9 +220,25 @@ class Registry
     // ---- extensions (not in the reference) ------------------------------------------------------------
     // moveEntity(ids[i], deltas[i]) for every i, in order.
     void moveEntities(std::span<const EntityId> ids, std::span<const Translation> deltas);
-    // rayCast for a batch of rays; hits of ray i are result[i] in std::set order.
+    // rayCast for a batch of rays in ONE device pass (the single-ray calls above are latency bound: one thread
+    // walks the trees); hits of ray i are result[i] in std::set order.
     std::vector<std::vector<RayHit>> rayCastBatch(std::span<const Ray> rays, std::span<const InfiniteRay> infiniteRays,
                                                   BitMaskType maskBits = ~0ull) const;
+    // Mixed batch with one mask per ray: `second` is the end point (finite) or the direction (infinite).
+    struct RayQuery
+    {
+        Vec2 start;
+        Vec2 second;
+        BitMaskType maskBits = ~0ull;
+        bool infinite = false;
+    };
+    // Flat result: hits of query i are hits[offsets[i] .. offsets[i+1]).
+    struct RayBatchResult
+    {
+        std::vector<uint64_t> offsets;
+        std::vector<RayHit> hits;
+    };
+    RayBatchResult rayCastBatch(std::span<const RayQuery> queries) const;
     // Device-resident move batches: stageMoves() uploads moveEntity(ids[i], deltas[i]) for all i ONCE and returns
     // a handle; every applyStagedMoves(handle) then performs those moves with O(1) host work and no PCIe
     // traffic (the host-side transforms are brought up to date lazily, on the next call that reads them).
@@ -332,6 +353,55 @@ class Registry
     }
     template <typename RayT>
     std::set<RayHit> rayCastOne(RayT ray, BitMaskType maskBits, bool infinite) const;
+    template <typename RayT>
+    std::optional<RayHit> firstHitOne(RayT ray, BitMaskType maskBits, bool infinite) const;
+    template <typename RayT>
+    static c2d_ray packRay(RayT ray, BitMaskType maskBits, bool infinite)
+    {
+        c2d_ray r{};
+        r.sx = ray.start.x;
+        r.sy = ray.start.y;
+        if constexpr (std::is_same_v<RayT, Ray>)
+            r.ex = ray.end.x, r.ey = ray.end.y;
+        else
+            r.ex = ray.direction.x, r.ey = ray.direction.y;
+        r.mask = maskBits;
+        r.infinite = infinite ? 1u : 0u;
+        return r;
+    }
+    RayHit toRayHit(const c2d_hit_record& h) const
+    {
+        EntityId id;
+        if constexpr (kDirectTag)
+            id = std::bit_cast<EntityId>(h.entity);
+        else
+            id = mEntities[h.entity].id;
+        return RayHit{{id, h.shape}, Vec2{h.entry[0], h.entry[1]}, Vec2{h.exit[0], h.exit[1]}, h.entryTime, h.exitTime};
+    }
+    std::vector<EntityCollision> toCollisions(const c2d_pair_record* records, uint64_t count) const
+    {
+        if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
+                      std::is_trivially_copyable_v<EntityCollision>)
+        {
+            // the device wrote EntityCollision records: one block copy out of the pinned buffer
+            const auto* first = reinterpret_cast<const EntityCollision*>(records);
+            return std::vector<EntityCollision>(first, first + count);
+        }
+        else
+        {
+            std::vector<EntityCollision> out;
+            out.reserve(count);
+            for (uint64_t i = 0; i < count; ++i)
+            {
+                const c2d_pair_record& r = records[i];
+                EntityCollision c{mEntities[r.entityA].id, mEntities[r.entityB].id, r.shapeA, r.shapeB, Manifold{}};
+                static_assert(sizeof(Manifold) == sizeof(c2d_manifold));
+                std::memcpy(static_cast<void*>(&c.manifold), &r.manifold, sizeof(Manifold));
+                out.push_back(std::move(c));
+            }
+            return out;
+        }
+    }
 
     struct StagedMoves
     {
@@ -648,27 +718,52 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
     const c2d_pair_record* records = nullptr;
     uint64_t count = 0;
     check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
-    if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
-                  std::is_trivially_copyable_v<EntityCollision>)
-    {
-        // the device wrote EntityCollision records: one block copy out of the pinned buffer
-        const auto* first = reinterpret_cast<const EntityCollision*>(records);
-        return std::vector<EntityCollision>(first, first + count);
-    }
-    else
-    {
-        std::vector<EntityCollision> out;
-        out.reserve(count);
-        for (uint64_t i = 0; i < count; ++i)
+    return toCollisions(records, count);
+}
+
+// Registry::getCollisions (reference Registry.hpp:551-605): every active shape of the entity queries the trees
+// with its tight box and its mask bits; order of the result is unspecified.
+template <typename EntityId, PartitioningMethod Method>
+std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<EntityId, Method>::getCollisions(
+    EntityId id) const
+{
+    const uint32_t idx = indexOf(id);
+    C2D_DEBUG_ASSERT(idx != kNone);
+    std::vector<uint32_t> shapes;
+    for (uint32_t s = mEntities[idx].firstShape; s != kNone; s = mShapes[s].next)
+        shapes.push_back(s);
+    const c2d_pair_record* records = nullptr;
+    uint64_t count = 0;
+    check(c2d_gpu_query_shapes(mCtx, static_cast<uint32_t>(shapes.size()), shapes.data(), &records, &count));
+    return toCollisions(records, count);
+}
+
+// Registry::areColliding (reference Registry.hpp:748-864): all active shape pairs, no broadphase.
+template <typename EntityId, PartitioningMethod Method>
+bool Registry<EntityId, Method>::areColliding(EntityId a, EntityId b) const
+{
+    const uint32_t ia = indexOf(a), ib = indexOf(b);
+    C2D_DEBUG_ASSERT(ia != kNone, "Entity A does not exist");
+    C2D_DEBUG_ASSERT(ib != kNone, "Entity B does not exist");
+    const EntityInfo& ea = mEntities[ia];
+    const EntityInfo& eb = mEntities[ib];
+    if (ea.type == BodyType::Static && eb.type == BodyType::Static)
+        return false;
+    std::vector<uint32_t> sa, sb;
+    for (uint32_t x = ea.firstShape; x != kNone; x = mShapes[x].next)
+        for (uint32_t y = eb.firstShape; y != kNone; y = mShapes[y].next)
         {
-            const c2d_pair_record& r = records[i];
-            EntityCollision c{mEntities[r.entityA].id, mEntities[r.entityB].id, r.shapeA, r.shapeB, Manifold{}};
-            static_assert(sizeof(Manifold) == sizeof(c2d_manifold));
-            std::memcpy(static_cast<void*>(&c.manifold), &r.manifold, sizeof(Manifold));
-            out.push_back(std::move(c));
+            sa.push_back(x);
+            sb.push_back(y);
         }
-        return out;
-    }
+    if (sa.empty())
+        return false;
+    std::vector<uint8_t> flags(sa.size(), 0);
+    check(c2d_gpu_pairs_colliding(mCtx, static_cast<uint32_t>(sa.size()), sa.data(), sb.data(), flags.data()));
+    for (uint8_t f : flags)
+        if (f)
+            return true;
+    return false;
 }
 
 template <typename EntityId, PartitioningMethod Method>
@@ -685,31 +780,43 @@ std::set<typename Registry<EntityId, Method>::RayHit> Registry<EntityId, Method>
                                                                                              BitMaskType maskBits,
                                                                                              bool infinite) const
 {
-    c2d_ray r{};
-    r.sx = ray.start.x;
-    r.sy = ray.start.y;
-    if constexpr (std::is_same_v<RayT, Ray>)
-        r.ex = ray.end.x, r.ey = ray.end.y;
-    else
-        r.ex = ray.direction.x, r.ey = ray.direction.y;
-    r.mask = maskBits;
-    r.infinite = infinite ? 1u : 0u;
+    const c2d_ray r = packRay(ray, maskBits, infinite);
     const c2d_hit_record* hits = nullptr;
     const uint64_t* offsets = nullptr;
     check(c2d_gpu_raycast(mCtx, 1, &r, &hits, &offsets, &mStats));
     std::set<RayHit> out;
     for (uint64_t i = offsets[0]; i < offsets[1]; ++i)
-    {
-        const c2d_hit_record& h = hits[i];
-        EntityId id;
-        if constexpr (kDirectTag)
-            id = std::bit_cast<EntityId>(h.entity);
-        else
-            id = mEntities[h.entity].id;
-        out.insert(out.end(), RayHit{{id, h.shape}, Vec2{h.entry[0], h.entry[1]}, Vec2{h.exit[0], h.exit[1]},
-                                     h.entryTime, h.exitTime});
-    }
+        out.insert(out.end(), toRayHit(hits[i]));
     return out;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+template <typename RayT>
+std::optional<typename Registry<EntityId, Method>::RayHit> Registry<EntityId, Method>::firstHitOne(RayT ray,
+                                                                                                   BitMaskType maskBits,
+                                                                                                   bool infinite) const
+{
+    const c2d_ray r = packRay(ray, maskBits, infinite);
+    const c2d_hit_record* hits = nullptr;
+    const uint64_t* offsets = nullptr;
+    check(c2d_gpu_raycast_first(mCtx, 1, &r, &hits, &offsets, &mStats));
+    if (offsets[1] == offsets[0])
+        return std::nullopt;
+    return toRayHit(hits[offsets[0]]);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+std::optional<typename Registry<EntityId, Method>::RayHit> Registry<EntityId, Method>::firstHitRayCast(
+    Ray ray, BitMaskType maskBits) const
+{
+    return firstHitOne(ray, maskBits, false);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+std::optional<typename Registry<EntityId, Method>::RayHit> Registry<EntityId, Method>::firstHitRayCast(
+    InfiniteRay ray, BitMaskType maskBits) const
+{
+    return firstHitOne(ray, maskBits, true);
 }
 
 template <typename EntityId, PartitioningMethod Method>
@@ -744,17 +851,27 @@ std::vector<std::vector<typename Registry<EntityId, Method>::RayHit>> Registry<E
     {
         out[i].reserve(offsets[i + 1] - offsets[i]);
         for (uint64_t k = offsets[i]; k < offsets[i + 1]; ++k)
-        {
-            const c2d_hit_record& h = hits[k];
-            EntityId id;
-            if constexpr (kDirectTag)
-                id = std::bit_cast<EntityId>(h.entity);
-            else
-                id = mEntities[h.entity].id;
-            out[i].push_back(RayHit{{id, h.shape}, Vec2{h.entry[0], h.entry[1]}, Vec2{h.exit[0], h.exit[1]},
-                                    h.entryTime, h.exitTime});
-        }
+            out[i].push_back(toRayHit(hits[k]));
     }
+    return out;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+typename Registry<EntityId, Method>::RayBatchResult Registry<EntityId, Method>::rayCastBatch(
+    std::span<const RayQuery> queries) const
+{
+    std::vector<c2d_ray> packed;
+    packed.reserve(queries.size());
+    for (const RayQuery& q : queries)
+        packed.push_back(c2d_ray{q.start.x, q.start.y, q.second.x, q.second.y, q.maskBits, q.infinite ? 1u : 0u, 0u});
+    const c2d_hit_record* hits = nullptr;
+    const uint64_t* offsets = nullptr;
+    check(c2d_gpu_raycast(mCtx, static_cast<uint32_t>(packed.size()), packed.data(), &hits, &offsets, &mStats));
+    RayBatchResult out;
+    out.offsets.assign(offsets, offsets + packed.size() + 1);
+    out.hits.reserve(out.offsets.back());
+    for (uint64_t k = 0; k < out.offsets.back(); ++k)
+        out.hits.push_back(toRayHit(hits[k]));
     return out;
 }
 

@@ -1226,6 +1226,180 @@ uint64_t rn_raycast(rn_ctx* c, uint32_t n, const float* ray4, const uint8_t* inf
 }
 void rn_copy_hits(rn_ctx* c, void* out) { if (c->nhits) memcpy(out, c->hits, c->nhits * sizeof(hitrec_t)); }
 
+/* ---- getCollisions, Registry.hpp:551-605 --------------------------------------------------------------- */
+static void push_pair(rn_ctx* c, const entity_t* ea, const entity_t* eb, uint32_t sa, uint32_t sb, const manifold_t* m)
+{
+    c->pairs = (pairrec_t*)grow(c->pairs, sizeof(pairrec_t), c->npairs + 1, &c->cappairs);
+    pairrec_t* r = &c->pairs[c->npairs++];
+    memset(r, 0, sizeof(*r));
+    r->eA = ea->id; r->eB = eb->id; r->sA = sa; r->sB = sb; r->m = *m;
+}
+/* narrowPhaseCollision(queried, other) as reached from getCollisions: when exactly one side is a bullet the sweep is
+ * (bullet shape moving, other shape) whichever side was queried, and the record keeps (queried, other)
+ * (Registry.hpp:669-691) */
+static void narrow_phase_query(rn_ctx* c, uint32_t sa, uint32_t sb)
+{
+    const inst_t *A = &c->shapes[sa], *B = &c->shapes[sb];
+    const entity_t *ea = &c->ents[A->entity], *eb = &c->ents[B->entity];
+    if (A->entity == B->entity || !A->active || !B->active) return;
+    manifold_t m;
+    memset(&m, 0, sizeof(m));
+    float f;
+    int have;
+    if (ea->body == BULLET && eb->body == BULLET)
+    {
+        motion_t ma = {ea->previous, ea->transform, 1}, mb = {eb->previous, eb->transform, 1};
+        have = sweep_shapes(&A->shape, &ma, &B->shape, &mb, &f, &m);
+    }
+    else if (ea->body == BULLET)
+    {
+        motion_t ma = {ea->previous, ea->transform, 1}, mb = {eb->transform, eb->transform, 0};
+        have = sweep_shapes(&A->shape, &ma, &B->shape, &mb, &f, &m);
+    }
+    else if (eb->body == BULLET)
+    {
+        motion_t mb = {eb->previous, eb->transform, 1}, ma = {ea->transform, ea->transform, 0};
+        have = sweep_shapes(&B->shape, &mb, &A->shape, &ma, &f, &m);
+    }
+    else
+    {
+        collide_dispatch(&A->shape, &ea->transform, &B->shape, &eb->transform, &m);
+        have = m.pointCount > 0;
+    }
+    if (have) push_pair(c, ea, eb, sa, sb, &m);
+}
+uint64_t rn_get_collisions(rn_ctx* c, uint32_t id)
+{
+    c->npairs = 0;
+    entity_t* e = entity_of(c, id);
+    if (!e) return 0;
+    for (int body = 0; body < 3; ++body)
+    {
+        if (body == STATIC && e->body == STATIC) continue; /* Registry.hpp:598-601 */
+        for (uint32_t k = 0; k < e->nshapes; ++k)
+        {
+            const uint32_t q = e->shapes[k];
+            const inst_t* Q = &c->shapes[q];
+            if (!Q->active) continue;
+            box_t qb = Q->tight;
+            if (e->body == BULLET) { const box_t old = compute_aabb(&Q->shape, &e->previous); qb = box_combine(old, Q->tight); }
+            for (uint32_t s = 0; s < c->nshapes; ++s)
+            {
+                const inst_t* S = &c->shapes[s];
+                if (!S->alive || c->ents[S->entity].body != body) continue;
+                if ((S->category & Q->mask) == 0) continue; /* node.matchesMask(maskBits), DynamicBVH.hpp:725 */
+                if (!box_intersects(&S->fat, &qb)) continue;
+                narrow_phase_query(c, q, s);
+            }
+        }
+    }
+    return c->npairs;
+}
+
+/* ---- areColliding, Registry.hpp:748-864; boolSweepHelper Collision.hpp:126-149, 215-244 -------------------- */
+static int sweep_bool(const shape_t* a, const motion_t* ma, const shape_t* b, const motion_t* mb)
+{
+    if (collide_dispatch(a, &ma->start, b, &mb->start, NULL)) return 1;
+    for (int step = 1; step <= 8; ++step)
+    {
+        const float f = (float)step / 8.0f;
+        const xf_t ta = motion_at(ma, f), tb = motion_at(mb, f);
+        if (collide_dispatch(a, &ta, b, &tb, NULL)) return 1;
+    }
+    return 0;
+}
+static int entities_colliding(rn_ctx* c, uint32_t ida, uint32_t idb)
+{
+    entity_t *ea = entity_of(c, ida), *eb = entity_of(c, idb);
+    if (!ea || !eb) return 0;
+    if (ea->body == STATIC && eb->body == STATIC) return 0;
+    for (uint32_t i = 0; i < ea->nshapes; ++i)
+    {
+        const inst_t* A = &c->shapes[ea->shapes[i]];
+        if (!A->active) continue;
+        for (uint32_t j = 0; j < eb->nshapes; ++j)
+        {
+            const inst_t* B = &c->shapes[eb->shapes[j]];
+            if (!B->active) continue;
+            int hit;
+            if (ea->body == BULLET && eb->body == BULLET)
+            {
+                motion_t ma = {ea->previous, ea->transform, 1}, mb = {eb->previous, eb->transform, 1};
+                hit = sweep_bool(&A->shape, &ma, &B->shape, &mb);
+            }
+            else if (ea->body == BULLET)
+            {
+                motion_t ma = {ea->previous, ea->transform, 1}, mb = {eb->transform, eb->transform, 0};
+                hit = sweep_bool(&A->shape, &ma, &B->shape, &mb);
+            }
+            else if (eb->body == BULLET)
+            {
+                motion_t mb = {eb->previous, eb->transform, 1}, ma = {ea->transform, ea->transform, 0};
+                hit = sweep_bool(&B->shape, &mb, &A->shape, &ma);
+            }
+            else hit = collide_dispatch(&A->shape, &ea->transform, &B->shape, &eb->transform, NULL);
+            if (hit) return 1;
+        }
+    }
+    return 0;
+}
+void rn_are_colliding(rn_ctx* c, uint32_t n, const uint32_t* a, const uint32_t* b, uint8_t* out)
+{
+    for (uint32_t i = 0; i < n; ++i) out[i] = (uint8_t)entities_colliding(c, a[i], b[i]);
+}
+
+/* ---- firstHitRayCast, Registry.hpp:866-1048 ------------------------------------------------------------------ */
+void rn_first_hit_raycast(rn_ctx* c, uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
+                          uint8_t* found, void* out_hits32)
+{
+    hitrec_t* out = (hitrec_t*)out_hits32;
+    aabbhit_t* ah = (aabbhit_t*)malloc(sizeof(aabbhit_t) * (c->nshapes ? c->nshapes : 1));
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const ray_t r = ray_make(ray4 + 4 * i, infinite && infinite[i]);
+        const uint64_t mask = masks ? masks[i] : ~0ull;
+        float best = FLT_MAX;
+        found[i] = 0;
+        memset(&out[i], 0, sizeof(hitrec_t));
+        for (int body = 0; body < 3; ++body)
+        {
+            uint32_t m = 0;
+            for (uint32_t s = 0; s < c->nshapes; ++s)
+            {
+                const inst_t* S = &c->shapes[s];
+                if (!S->alive || c->ents[S->entity].body != body || (S->category & mask) == 0) continue;
+                float a, b;
+                if (box_ray(&S->fat, &r, &a, &b)) { ah[m].t0 = a; ah[m].t1 = b; ah[m].shape = s; ++m; }
+            }
+            qsort(ah, m, sizeof(aabbhit_t), cmp_aabbhit);
+            uint32_t setSize = 0;
+            for (uint32_t k = 0; k < m; ++k) if (!k || ah[k].t0 != ah[k - 1].t0 || ah[k].t1 != ah[k - 1].t1) ++setSize;
+            uint32_t toCheck = setSize;
+            for (uint32_t k = 0; k < m; ++k)
+            {
+                if (k && ah[k].t0 == ah[k - 1].t0 && ah[k].t1 == ah[k - 1].t1) continue;
+                const inst_t* S = &c->shapes[ah[k].shape];
+                const entity_t* e = &c->ents[S->entity];
+                if (!S->active) continue; /* the `continue` precedes the countdown */
+                float t0, t1;
+                const int hit = body == BULLET ? ray_sweep(&S->shape, &e->previous, &e->transform, &r, &t0, &t1)
+                                               : ray_shape(&S->shape, &e->transform, &r, &t0, &t1);
+                if (hit && t0 < best)
+                {
+                    best = t0;
+                    found[i] = 1;
+                    out[i].entity = e->id; out[i].shape = ah[k].shape; out[i].t0 = t0; out[i].t1 = t1;
+                    const v2 en = vadd(r.start, vmul(r.d, t0)), ex = vadd(r.start, vmul(r.d, t1));
+                    out[i].entry[0] = en.x; out[i].entry[1] = en.y; out[i].exit[0] = ex.x; out[i].exit[1] = ex.y;
+                    toCheck = 5; /* check 5 more after an improvement */
+                }
+                if (--toCheck == 0) break;
+            }
+        }
+    }
+    free(ah);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * batched free functions
  * ---------------------------------------------------------------------------------------------- */

@@ -12,6 +12,7 @@
 
 #include <array>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <malloc.h>
 #include <memory>
@@ -117,6 +118,10 @@ struct IRegistry
     virtual void moveEntity(uint32_t id, Translation d) = 0;
     virtual Transform getEntityTransform(uint32_t id) const = 0;
     virtual void getCollidingPairs(std::vector<PairRec>& out, double* seconds) = 0;
+    virtual void getCollisions(uint32_t id, std::vector<PairRec>& out) const = 0;
+    virtual bool areColliding(uint32_t a, uint32_t b) const = 0;
+    virtual bool firstHit(Ray r, uint64_t mask, HitRec& out) const = 0;
+    virtual bool firstHit(InfiniteRay r, uint64_t mask, HitRec& out) const = 0;
     virtual uint64_t countPairsDevice(double* seconds) = 0;
     virtual void* native() const = 0;
     virtual void stats(double* out16) const = 0;
@@ -125,6 +130,9 @@ struct IRegistry
     virtual void releaseStaged(int handle) = 0;
     virtual void rayCast(Ray r, uint64_t mask, std::vector<HitRec>& out) const = 0;
     virtual void rayCast(InfiniteRay r, uint64_t mask, std::vector<HitRec>& out) const = 0;
+    // all rays in one call where the backend has a batched entry point; false -> the caller loops rayCast()
+    virtual bool rayCastBatch(uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
+                              uint64_t* offsets, std::vector<HitRec>& out) const = 0;
     virtual size_t size() const = 0;
     virtual void clear() = 0;
 };
@@ -190,7 +198,49 @@ struct RegistryHolder final : IRegistry
         if (!pairs.empty())
             std::memcpy(out.data(), pairs.data(), pairs.size() * sizeof(PairRec));
     }
+    void getCollisions(uint32_t id, std::vector<PairRec>& out) const override
+    {
+        const auto pairs = reg.getCollisions(id);
+        out.resize(pairs.size());
+        if (!pairs.empty())
+            std::memcpy(out.data(), pairs.data(), pairs.size() * sizeof(PairRec));
+    }
+    bool areColliding(uint32_t a, uint32_t b) const override
+    {
+        return reg.areColliding(a, b);
+    }
+    template <typename RayT>
+    bool firstHitImpl(RayT r, uint64_t mask, HitRec& out) const
+    {
+        const auto h = reg.firstHitRayCast(r, mask);
+        if (!h)
+            return false;
+        out = HitRec{h->id.first, h->id.second, {h->entry.x, h->entry.y}, {h->exit.x, h->exit.y}, h->entryTime, h->exitTime};
+        return true;
+    }
+    bool firstHit(Ray r, uint64_t mask, HitRec& out) const override
+    {
+        return firstHitImpl(r, mask, out);
+    }
+    bool firstHit(InfiniteRay r, uint64_t mask, HitRec& out) const override
+    {
+        return firstHitImpl(r, mask, out);
+    }
 #if defined(RN_BACKEND_B200)
+    bool rayCastBatch(uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks, uint64_t* offsets,
+                      std::vector<HitRec>& out) const override
+    {
+        std::vector<typename Reg::RayQuery> q(n);
+        for (uint32_t i = 0; i < n; ++i)
+            q[i] = typename Reg::RayQuery{Vec2{ray4[4 * i], ray4[4 * i + 1]}, Vec2{ray4[4 * i + 2], ray4[4 * i + 3]},
+                                          masks ? masks[i] : ~0ull, infinite && infinite[i]};
+        const auto res = reg.rayCastBatch(std::span<const typename Reg::RayQuery>(q));
+        std::copy(res.offsets.begin(), res.offsets.end(), offsets);
+        out.reserve(res.hits.size());
+        for (const auto& h : res.hits)
+            out.push_back(HitRec{h.id.first, h.id.second, {h.entry.x, h.entry.y}, {h.exit.x, h.exit.y}, h.entryTime, h.exitTime});
+        return true;
+    }
     void* native() const override
     {
         return reg.nativeContext();
@@ -228,6 +278,10 @@ struct RegistryHolder final : IRegistry
     }
 #else
     std::vector<std::pair<std::vector<uint32_t>, std::vector<Translation>>> staged;
+    bool rayCastBatch(uint32_t, const float*, const uint8_t*, const uint64_t*, uint64_t*, std::vector<HitRec>&) const override
+    {
+        return false;
+    }
     void* native() const override
     {
         return nullptr;
@@ -533,6 +587,41 @@ uint64_t rn_count_colliding_pairs_device(rn_ctx* ctx, double* seconds)
     return 0;
 }
 
+uint64_t rn_get_collisions(rn_ctx* ctx, uint32_t id)
+{
+    RN_TRY(ctx)
+    ctx->reg->getCollisions(id, ctx->pairs);
+    return ctx->pairs.size();
+    RN_CATCH(ctx)
+    return 0;
+}
+
+void rn_are_colliding(rn_ctx* ctx, uint32_t n, const uint32_t* idsA, const uint32_t* idsB, uint8_t* out)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+        out[i] = ctx->reg->areColliding(idsA[i], idsB[i]) ? 1 : 0;
+    RN_CATCH(ctx)
+}
+
+void rn_first_hit_raycast(rn_ctx* ctx, uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
+                          uint8_t* out_found, void* out_hits32)
+{
+    RN_TRY(ctx)
+    auto* hits = static_cast<HitRec*>(out_hits32);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const float* r = ray4 + 4 * i;
+        const uint64_t mask = masks ? masks[i] : ~0ull;
+        hits[i] = HitRec{};
+        if (infinite && infinite[i])
+            out_found[i] = ctx->reg->firstHit(InfiniteRay{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}}, mask, hits[i]) ? 1 : 0;
+        else
+            out_found[i] = ctx->reg->firstHit(Ray{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}}, mask, hits[i]) ? 1 : 0;
+    }
+    RN_CATCH(ctx)
+}
+
 void* rn_native_context(rn_ctx* ctx)
 {
     return ctx->reg->native();
@@ -579,6 +668,13 @@ uint64_t rn_raycast(rn_ctx* ctx, uint32_t n, const float* ray4, const uint8_t* i
     RN_TRY(ctx)
     ctx->hits.clear();
     const auto t0 = std::chrono::steady_clock::now();
+    const bool single = std::getenv("RN_RAYCAST_SINGLE") != nullptr; // force the one-ray-per-call API
+    if (!single && ctx->reg->rayCastBatch(n, ray4, infinite, masks, offsets, ctx->hits))
+    {
+        if (seconds)
+            *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        return ctx->hits.size();
+    }
     for (uint32_t i = 0; i < n; ++i)
     {
         offsets[i] = ctx->hits.size();

@@ -73,6 +73,14 @@ int rn_stage_translations(rn_ctx*, uint32_t n, const uint32_t* ids, const float*
 void rn_apply_staged(rn_ctx*, int handle);
 void rn_release_staged(rn_ctx*, int handle);
 
+/* getCollisions(id): keeps the result like rn_get_colliding_pairs; returns the count (copy with rn_copy_pairs). */
+uint64_t rn_get_collisions(rn_ctx*, uint32_t id);
+/* areColliding(idsA[i], idsB[i]) for i < n */
+void rn_are_colliding(rn_ctx*, uint32_t n, const uint32_t* idsA, const uint32_t* idsB, uint8_t* out);
+/* firstHitRayCast() looped over n rays: out_found[i] = has_value, out_hits32[i] = the hit (zeroed when none) */
+void rn_first_hit_raycast(rn_ctx*, uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
+                          uint8_t* out_found, void* out_hits32);
+
 /* B200 only: the c2d_gpu_ctx* behind the Registry (Registry::nativeContext); NULL elsewhere. */
 void* rn_native_context(rn_ctx*);
 

@@ -127,6 +127,9 @@ def load(name: str) -> C.CDLL:
         "rn_count_colliding_pairs_device": (u64, [vp, pd]),
         "rn_query_stats": (None, [vp, pd]),
         "rn_native_context": (vp, [vp]),
+        "rn_get_collisions": (u64, [vp, u32]),
+        "rn_are_colliding": (None, [vp, u32, pu32, pu32, pu8]),
+        "rn_first_hit_raycast": (None, [vp, u32, pf, pu8, pu64, pu8, vp]),
         "rn_stage_translations": (i32, [vp, u32, pu32, pf]),
         "rn_apply_staged": (None, [vp, i32]),
         "rn_release_staged": (None, [vp, i32]),
@@ -309,6 +312,33 @@ class Backend:
     def release_staged(self, handle: int):
         self.lib.rn_release_staged(self.ctx, handle)
         self._check()
+
+    def get_collisions(self, entity_id: int):
+        n = int(self.lib.rn_get_collisions(self.ctx, int(entity_id)))
+        self._check()
+        out = np.zeros(n, PAIR_DTYPE)
+        if n:
+            self.lib.rn_copy_pairs(self.ctx, out.ctypes.data_as(C.c_void_p))
+        return out
+
+    def are_colliding(self, ids_a, ids_b) -> np.ndarray:
+        a, b = _u32(ids_a), _u32(ids_b)
+        out = np.zeros(len(a), np.uint8)
+        self.lib.rn_are_colliding(self.ctx, len(a), _p(a, C.c_uint32), _p(b, C.c_uint32), _p(out, C.c_uint8))
+        self._check()
+        return out
+
+    def first_hit_raycast(self, ray4, infinite=None, masks=None):
+        ray4 = _f32(ray4).reshape(-1, 4)
+        n = ray4.shape[0]
+        infinite = _u8(infinite if infinite is not None else np.zeros(n))
+        masks = _u64(masks) if masks is not None else None
+        found = np.zeros(n, np.uint8)
+        hits = np.zeros(n, HIT_DTYPE)
+        self.lib.rn_first_hit_raycast(self.ctx, n, _p(ray4, C.c_float), _p(infinite, C.c_uint8), _p(masks, C.c_uint64),
+                                      _p(found, C.c_uint8), hits.ctypes.data_as(C.c_void_p))
+        self._check()
+        return found, hits
 
     def raycast(self, ray4, infinite=None, masks=None, with_time=False):
         ray4 = _f32(ray4).reshape(-1, 4)

@@ -124,6 +124,8 @@ def sort_pairs(p):
 
 def manifold_close(a, b, rel=1e-5):
     """Per-record closeness of normals, points, anchors and separations within `rel` relative (north-star)."""
+    if len(a) == 0:
+        return np.ones(0, bool)
     ok = a["pointCount"] == b["pointCount"]
     fa = np.concatenate([a["normal"].reshape(len(a), -1), _pts(a)], axis=1)
     fb = np.concatenate([b["normal"].reshape(len(b), -1), _pts(b)], axis=1)
@@ -138,6 +140,8 @@ def _pts(p):
 
 
 def manifold_bits_equal(a, b):
+    if len(a) == 0:
+        return np.ones(0, bool)
     fa = np.concatenate([a["normal"].reshape(len(a), -1), _pts(a)], axis=1).view(np.uint32)
     fb = np.concatenate([b["normal"].reshape(len(b), -1), _pts(b)], axis=1).view(np.uint32)
     # +0 / -0 compare equal

@@ -72,3 +72,19 @@ def test_raycast_batch_matches(oracle):
         assert keys == sorted(set(keys))
     bad = _compare(exp, got, n, 0.0 if oracle == "oracle" else 0.01)
     print(f"rays vs {oracle}: {bad} of {n} differ (exact-tie resolution), hits {len(exp[1])}")
+
+
+def test_single_ray_api_equals_batch():
+    """The drop-in Registry::rayCast(ray) (one ray per call) and rayCastBatch give the same hits."""
+    import os
+
+    sc = _scene()
+    gpu = _prepare(SUBJECT, sc)
+    ray4, inf, masks = _rays(150)
+    batch = gpu.raycast(ray4, inf, masks)
+    os.environ["RN_RAYCAST_SINGLE"] = "1"
+    try:
+        single = gpu.raycast(ray4, inf, masks)
+    finally:
+        del os.environ["RN_RAYCAST_SINGLE"]
+    assert np.array_equal(batch[0], single[0]) and batch[1].tobytes() == single[1].tobytes()
