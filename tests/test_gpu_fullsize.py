@@ -121,7 +121,7 @@ def test_cfg5_rays_against_four_million_shapes():
     gpu = H.Backend(SUBJECT)
     scenes.populate(gpu, sc)
     _lap("cfg5 scene + populate gpu")
-    n = 200_000
+    n = 100_000
     ray4, inf = scenes.rays(n, 9535.0, seed=13)
     off, hits = gpu.raycast(ray4, inf)
     _lap("cfg5 gpu raycast")
