@@ -303,8 +303,18 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     kernels = {k: {"launches": c, "avg_ms": ms / max(c, 1), "share": ms / max(sum(v[1] for v in profile.values()), 1e-9),
                    "alg_gbs": (alg.get(k, 0.0) / (ms / max(c, 1) * 1e-3) / 1e9) if ms > 0 else 0.0}
                for k, (c, ms) in sorted(profile.items(), key=lambda kv: -kv[1][1])}
+    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tpath):
+        ncu_name = {"k_traverse<self>": "k_traverse<1>", "k_traverse<cross>": "k_traverse<0>"}.get(dom_name, dom_name)
+        rec = json.load(open(tpath)).get(ncu_name)
+        if rec:
+            traffic = rec["dram"]
+            traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_full_top_kernels_v2.csv "
+                           f"(cold-cache, serialised replay; {rec['launches_profiled']} launches)")
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_avg_ms,
                 "frame": {"alg_bytes": frame_alg, "achieved": frame_alg / (ms_per_step * 1e-3) / 1e9,
                           "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak},

@@ -600,40 +600,56 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
     const uint32_t n = min(fs->candCount, capacity);
     // the polygon bin of mode 0 is handled by k_narrow_filter_pp (8 lanes per pair)
     const uint32_t ppOff = fs->binOffset[CORE_PP], ppCnt = fs->binCount[CORE_PP];
-    for (uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 < n - ppCnt; i0 += gridDim.x * blockDim.x)
+    const uint32_t total = n - ppCnt;
+    const int lane = threadIdx.x & 31;
+    // warp-uniform trip count and an explicit reconvergence per iteration: without it the lanes that reject their
+    // pair early run ahead into the next iteration and the warp never executes the test code with a full mask
+    for (uint32_t base0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base0 < total; base0 += gridDim.x * blockDim.x)
     {
+        const uint32_t i0 = base0 + lane;
+        const bool valid = i0 < total;
         const uint32_t i = i0 < ppOff ? i0 : i0 + ppCnt;
-        const uint2 p = binned[i];
-        PairCtx c;
-        if (!load_pair(s, p, c))
-            continue;
+        uint2 p = make_uint2(0, 0);
         float fraction = 0.0f;
-        bool hit;
-        if (!c.bulletA && !c.bulletB)
+        bool hit = false;
+        if (valid)
         {
-            Manifold unused;
-            hit = narrow_test<false>(c.A, c.xa, c.B, c.xb, unused);
+            p = binned[i];
+            PairCtx c;
+            if (load_pair(s, p, c))
+            {
+                if (!c.bulletA && !c.bulletB)
+                {
+                    Manifold unused;
+                    hit = narrow_test<false>(c.A, c.xa, c.B, c.xb, unused);
+                }
+                else
+                {
+                    Motion moA, moB;
+                    load_motions(s, p, c, moA, moB);
+                    hit = sweep_search(c.A, moA, c.B, moB, fraction);
+                }
+            }
         }
-        else
-        {
-            Motion moA, moB;
-            load_motions(s, p, c, moA, moB);
-            hit = sweep_search(c.A, moA, c.B, moB, fraction);
-        }
-        if (!hit)
-            continue;
+        __syncwarp();
         // the bin of entry i: the binned array is the concatenation of the bins
-        int bin = 0;
+        int bin = 31;
+        if (hit)
+        {
+            bin = 0;
 #pragma unroll
-        for (int b = 1; b < 15; ++b)
-            bin += (i >= fs->binOffset[b]) ? 1 : 0;
-        cg::coalesced_group g = cg::coalesced_threads();
-        const cg::coalesced_group sameBin = cg::labeled_partition(g, bin);
+            for (int b = 1; b < 15; ++b)
+                bin += (i >= fs->binOffset[b]) ? 1 : 0;
+        }
+        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+        const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
-        if (sameBin.thread_rank() == 0)
-            base = atomicAdd(&fs->hitCount[bin], sameBin.size());
-        base = sameBin.shfl(base, 0);
-        hits[fs->binOffset[bin] + base + sameBin.thread_rank()] = make_uint4(p.x, p.y, __float_as_uint(fraction), 0u);
+        if (hit && lane == leader)
+            base = atomicAdd(&fs->hitCount[bin], __popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (hit)
+            hits[fs->binOffset[bin] + base + __popc(peers & ((1u << lane) - 1u))] =
+                make_uint4(p.x, p.y, __float_as_uint(fraction), 0u);
     }
 }
 
