@@ -439,33 +439,28 @@ __device__ __forceinline__ bool poly_poly(const PolyW& a, const XF& xa, const Po
     return true;
 }
 
-// polygon (A) - circle (B) (Collision.cpp:402-473 / 692-721)
+// polygon (A) - circle (B) (Collision.cpp:402-473 / 692-721).
+// Single pass over the edges straight from the geometry slot (no world-vertex array in local memory): edge i uses
+// v1 = apply(v[i]) and v2 = apply(v[(i + 1) % n]); v2 of one edge is v1 of the next, apply() is deterministic, so the
+// values are those of the reference.  isPointInsidePolygon (Collision.cpp:402-412) is folded into the same loop.
 template <bool kManifold>
-__device__ __forceinline__ bool poly_circle(const PolyW& p, const XF& xa, V2 cc, float radius, const XF& xb,
-                                            Manifold& m)
+__device__ __forceinline__ bool poly_circle(const float* __restrict__ g, int n, const XF& xa, V2 cc, float radius,
+                                            const XF& xb, Manifold& m)
 {
     const V2 center = apply(xb, cc);
-
-    // isPointInsidePolygon (Collision.cpp:402-412)
     bool isInside = true;
-    for (int i = 0; i < p.n; ++i)
-    {
-        if (dot(p.nrm[i], center - p.v[i]) > 0.0f)
-        {
-            isInside = false;
-            break;
-        }
-    }
-    if (!kManifold && isInside)
-        return true;
-
+    bool touching = false;
     float minDistSq = FLT_MAX;
     V2 closest = mk(0.0f, 0.0f);
     V2 normal = mk(1.0f, 0.0f);
-    for (int i = 0; i < p.n; ++i)
+    const V2 first = n > 0 ? apply(xa, mk(g[0], g[1])) : mk(0.0f, 0.0f);
+    V2 v1 = first;
+    for (int i = 0; i < n; ++i)
     {
-        const V2 v1 = p.v[i];
-        const V2 v2 = p.v[(i + 1) % p.n];
+        const V2 v2 = (i + 1 < n) ? apply(xa, mk(g[2 * i + 2], g[2 * i + 3])) : first;
+        const V2 edgeNormal = rot(xa, mk(g[16 + 2 * i], g[16 + 2 * i + 1]));
+        if (dot(edgeNormal, center - v1) > 0.0f)
+            isInside = false;
         const V2 edge = v2 - v1;
         const float edgeLenSq = lensq(edge);
         float edgeParam = 0.0f;
@@ -477,21 +472,21 @@ __device__ __forceinline__ bool poly_circle(const PolyW& p, const XF& xa, V2 cc,
         if (!kManifold)
         {
             if (distSq <= radius * radius)
-                return true;
-            continue;
+                touching = true;
         }
-        if (distSq < minDistSq)
+        else if (distSq < minDistSq)
         {
             minDistSq = distSq;
             closest = pointOnEdge;
             if (edgeParam > 0.0f && edgeParam < 1.0f)
-                normal = p.nrm[i];
+                normal = edgeNormal;
             else
-                normal = lensq(delta) > kEps * kEps ? normalize(delta) : p.nrm[i];
+                normal = lensq(delta) > kEps * kEps ? normalize(delta) : edgeNormal;
         }
+        v1 = v2;
     }
     if (!kManifold)
-        return false;
+        return isInside || touching;
 
     if (!isInside && minDistSq > radius * radius)
         return false;
@@ -593,11 +588,7 @@ __device__ inline bool narrow_test(const ShapeRef& A, const XF& xa, const ShapeR
     else if (S2.type == T_CIRCLE)
     {
         if (S1.type == T_POLYGON)
-        {
-            PolyW p;
-            poly_world(S1.g, S1.count, x1, p);
-            hit = poly_circle<kManifold>(p, x1, g2(S2.g, 0), S2.g[2], x2, m);
-        }
+            hit = poly_circle<kManifold>(S1.g, S1.count, x1, g2(S2.g, 0), S2.g[2], x2, m);
         else
             hit = capsule_circle<kManifold>(g2(S1.g, 0), g2(S1.g, 1), cap_radius(S1), x1, g2(S2.g, 0), S2.g[2], x2, m);
     }
