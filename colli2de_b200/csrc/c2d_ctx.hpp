@@ -179,10 +179,16 @@ struct c2d_gpu_ctx
 
     // mutation log
     uint32_t round = 1;
-    PinnedVec<FlagRec> flagLog;
-    PinnedVec<AddRec> addLog;
-    PinnedVec<TransRec> transLog;
-    PinnedVec<MoveRec> moveLog;
+    PinnedVec<FlagRec> flagLogs[2];
+    PinnedVec<AddRec> addLogs[2];
+    PinnedVec<TransRec> transLogs[2];
+    PinnedVec<MoveRec> moveLogs[2];
+    PinnedVec<FlagRec>* flagLog = &flagLogs[0]; // the set the host is logging into
+    PinnedVec<AddRec>* addLog = &addLogs[0];
+    PinnedVec<TransRec>* transLog = &transLogs[0];
+    PinnedVec<MoveRec>* moveLog = &moveLogs[0];
+    int logIndex = 0;
+    cudaEvent_t logConsumed[2] = {}; // recorded after the H2D copies of a set were enqueued
     std::vector<Round> rounds;
     DevBuf<FlagRec> dFlagLog;
     DevBuf<AddRec> dAddLog;

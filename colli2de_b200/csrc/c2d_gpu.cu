@@ -154,7 +154,7 @@ int ensure_shape_capacity(c2d_gpu_ctx* ctx, uint32_t want)
 void begin_round(c2d_gpu_ctx* ctx)
 {
     ++ctx->round;
-    ctx->rounds.push_back(Round{ctx->flagLog.size, ctx->addLog.size, ctx->transLog.size, ctx->moveLog.size, -1});
+    ctx->rounds.push_back(Round{ctx->flagLog->size, ctx->addLog->size, ctx->transLog->size, ctx->moveLog->size, -1});
 }
 
 // Makes sure an op of `phase` on `shape` can join the current round (strictly increasing phase per shape).
@@ -201,26 +201,26 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
     cudaStream_t s = ctx->stream;
     if (int rc = ensure_shape_capacity(ctx, ctx->shapeSlots))
         return rc;
-    const size_t nf = ctx->flagLog.size, na = ctx->addLog.size, nt = ctx->transLog.size, nm = ctx->moveLog.size;
+    const size_t nf = ctx->flagLog->size, na = ctx->addLog->size, nt = ctx->transLog->size, nm = ctx->moveLog->size;
     if (nf)
     {
         C2D_CUDA(ctx, ctx->dFlagLog.reserve(nf));
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dFlagLog.ptr, ctx->flagLog.data, nf * sizeof(FlagRec), cudaMemcpyHostToDevice, s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dFlagLog.ptr, ctx->flagLog->data, nf * sizeof(FlagRec), cudaMemcpyHostToDevice, s));
     }
     if (na)
     {
         C2D_CUDA(ctx, ctx->dAddLog.reserve(na));
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dAddLog.ptr, ctx->addLog.data, na * sizeof(AddRec), cudaMemcpyHostToDevice, s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dAddLog.ptr, ctx->addLog->data, na * sizeof(AddRec), cudaMemcpyHostToDevice, s));
     }
     if (nt)
     {
         C2D_CUDA(ctx, ctx->dTransLog.reserve(nt));
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dTransLog.ptr, ctx->transLog.data, nt * sizeof(TransRec), cudaMemcpyHostToDevice, s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dTransLog.ptr, ctx->transLog->data, nt * sizeof(TransRec), cudaMemcpyHostToDevice, s));
     }
     if (nm)
     {
         C2D_CUDA(ctx, ctx->dMoveLog.reserve(nm));
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dMoveLog.ptr, ctx->moveLog.data, nm * sizeof(MoveRec), cudaMemcpyHostToDevice, s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dMoveLog.ptr, ctx->moveLog->data, nm * sizeof(MoveRec), cudaMemcpyHostToDevice, s));
     }
     ctx->h2dBytes += nf * sizeof(FlagRec) + na * sizeof(AddRec) + nt * sizeof(TransRec) + nm * sizeof(MoveRec);
 
@@ -268,9 +268,16 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
         }
     }
     C2D_CUDA(ctx, cudaGetLastError());
-    // the pinned logs are reused by the next frame: the copies above must have been consumed
-    C2D_CUDA(ctx, cudaStreamSynchronize(s));
-    ctx->flagLog.size = ctx->addLog.size = ctx->transLog.size = ctx->moveLog.size = 0;
+    // The pinned logs are double buffered: the host keeps logging into the other set while these copies drain, and
+    // only waits (normally not at all) if that set's previous upload has not completed yet.
+    C2D_CUDA(ctx, cudaEventRecord(ctx->logConsumed[ctx->logIndex], s));
+    ctx->logIndex ^= 1;
+    ctx->flagLog = &ctx->flagLogs[ctx->logIndex];
+    ctx->addLog = &ctx->addLogs[ctx->logIndex];
+    ctx->transLog = &ctx->transLogs[ctx->logIndex];
+    ctx->moveLog = &ctx->moveLogs[ctx->logIndex];
+    C2D_CUDA(ctx, cudaEventSynchronize(ctx->logConsumed[ctx->logIndex]));
+    ctx->flagLog->size = ctx->addLog->size = ctx->transLog->size = ctx->moveLog->size = 0;
     ctx->rounds.clear();
     return 0;
 }
@@ -563,6 +570,8 @@ int c2d_gpu_create(int device, c2d_gpu_ctx** out_ctx)
     e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     for (int i = 0; i < 6 && e == cudaSuccess; ++i)
         e = cudaEventCreate(&ctx->ev[i]);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+        e = cudaEventCreateWithFlags(&ctx->logConsumed[i], cudaEventDisableTiming);
     if (e == cudaSuccess)
         e = cudaMalloc(reinterpret_cast<void**>(&ctx->dScratch), sizeof(FrameScratch));
     if (e == cudaSuccess)
@@ -603,6 +612,9 @@ void c2d_gpu_destroy(c2d_gpu_ctx* ctx)
             cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->eventPool)
         cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->logConsumed)
+        if (ev)
+            cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -616,7 +628,7 @@ int c2d_gpu_clear(c2d_gpu_ctx* ctx)
 {
     cudaSetDevice(ctx->device);
     C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->flagLog.size = ctx->addLog.size = ctx->transLog.size = ctx->moveLog.size = 0;
+    ctx->flagLog->size = ctx->addLog->size = ctx->transLog->size = ctx->moveLog->size = 0;
     ctx->rounds.clear();
     for (StagedBatch* sb : ctx->staged)
         delete sb;
@@ -691,7 +703,7 @@ int c2d_gpu_shape_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t entity_tag, uin
     claim(ctx, shape, PH_ADD);
     if (ctx->hostMeta[shape] & META_ALIVE)
         return fail(ctx, "c2d_gpu_shape_add: shape id is already in use");
-    AddRec* r = ctx->addLog.push();
+    AddRec* r = ctx->addLog->push();
     if (!r)
         return fail(ctx, "pinned host allocation failed");
     const uint32_t meta = type | (body << META_BODY_SHIFT) | META_ACTIVE | META_ALIVE | (vertex_count << META_COUNT_SHIFT);
@@ -716,7 +728,7 @@ int c2d_gpu_shape_remove(c2d_gpu_ctx* ctx, uint32_t shape)
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
         return fail(ctx, "c2d_gpu_shape_remove: unknown shape");
     claim(ctx, shape, PH_FLAG);
-    FlagRec* r = ctx->flagLog.push();
+    FlagRec* r = ctx->flagLog->push();
     if (!r)
         return fail(ctx, "pinned host allocation failed");
     r->shape = shape;
@@ -732,7 +744,7 @@ int c2d_gpu_shape_set_active(c2d_gpu_ctx* ctx, uint32_t shape, int active)
     if (shape >= ctx->hostMeta.size())
         return fail(ctx, "c2d_gpu_shape_set_active: unknown shape");
     claim(ctx, shape, PH_FLAG);
-    FlagRec* r = ctx->flagLog.push();
+    FlagRec* r = ctx->flagLog->push();
     if (!r)
         return fail(ctx, "pinned host allocation failed");
     r->shape = shape;
@@ -745,7 +757,7 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
         return fail(ctx, "c2d_gpu_shape_translate: unknown shape");
     claim(ctx, shape, PH_TRANS);
-    TransRec* r = ctx->transLog.push();
+    TransRec* r = ctx->transLog->push();
     if (!r)
         return fail(ctx, "pinned host allocation failed");
     r->shape = shape;
@@ -758,7 +770,7 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
 
 int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy)
 {
-    if (!ctx->transLog.reserve(ctx->transLog.size + n))
+    if (!ctx->transLog->reserve(ctx->transLog->size + n))
         return fail(ctx, "pinned host allocation failed");
     for (uint32_t i = 0; i < n; ++i)
         if (int rc = c2d_gpu_shape_translate(ctx, shapes[i], dxy[2 * i], dxy[2 * i + 1]))
@@ -771,7 +783,7 @@ int c2d_gpu_shape_move(c2d_gpu_ctx* ctx, uint32_t shape, const c2d_xf* xf)
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE) || !xf)
         return fail(ctx, "c2d_gpu_shape_move: unknown shape");
     claim(ctx, shape, PH_MOVE);
-    MoveRec* r = ctx->moveLog.push();
+    MoveRec* r = ctx->moveLog->push();
     if (!r)
         return fail(ctx, "pinned host allocation failed");
     r->shape = shape;

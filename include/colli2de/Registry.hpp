@@ -247,6 +247,10 @@ class Registry
     MoveBatch stageMoves(std::span<const EntityId> ids, std::span<const Translation> deltas);
     void applyStagedMoves(MoveBatch batch);
     void releaseStagedMoves(MoveBatch batch);
+    // getCollidingPairs() without the copy into a fresh std::vector: a view of the records in the library's pinned
+    // result buffer (or, for EntityIds that are not 4 trivially-copyable bytes, in an internal vector), valid until
+    // the next query on this Registry.
+    std::span<const EntityCollision> getCollidingPairsView();
     // Counters and CUDA-event timings of the last getCollidingPairs() / rayCast().
     const c2d_gpu_stats& lastQueryStats() const { return mStats; }
     // Runs the pipeline but leaves the records on the device; returns the number of colliding pairs.
@@ -439,6 +443,7 @@ class Registry
     std::vector<ShapeLink> mShapes;
     std::vector<ShapeId> mFreeShapeIds;
     mutable c2d_gpu_stats mStats{};
+    std::vector<EntityCollision> mViewStorage;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -719,6 +724,22 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
     uint64_t count = 0;
     check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
     return toCollisions(records, count);
+}
+
+template <typename EntityId, PartitioningMethod Method>
+std::span<const typename Registry<EntityId, Method>::EntityCollision> Registry<EntityId, Method>::getCollidingPairsView()
+{
+    const c2d_pair_record* records = nullptr;
+    uint64_t count = 0;
+    check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
+    if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
+                  std::is_trivially_copyable_v<EntityCollision>)
+        return std::span<const EntityCollision>(reinterpret_cast<const EntityCollision*>(records), count);
+    else
+    {
+        mViewStorage = toCollisions(records, count);
+        return std::span<const EntityCollision>(mViewStorage);
+    }
 }
 
 // Registry::getCollisions (reference Registry.hpp:551-605): every active shape of the entity queries the trees

@@ -1147,6 +1147,12 @@ uint64_t rn_get_colliding_pairs(rn_ctx* c, double* seconds)
     return c->npairs;
 }
 uint64_t rn_count_colliding_pairs_device(rn_ctx* c, double* seconds) { return rn_get_colliding_pairs(c, seconds); }
+uint64_t rn_get_colliding_pairs_view(rn_ctx* c, double* seconds, const void** records)
+{
+    const uint64_t n = rn_get_colliding_pairs(c, seconds);
+    *records = c->pairs;
+    return n;
+}
 void rn_copy_pairs(rn_ctx* c, void* out) { if (c->npairs) memcpy(out, c->pairs, c->npairs * sizeof(pairrec_t)); }
 
 /* ---- rayCast, Registry.hpp:1050-1182; DynamicBVH::piercingRaycast 775-806 / 853-884 ------------------- */

@@ -123,6 +123,7 @@ struct IRegistry
     virtual bool firstHit(Ray r, uint64_t mask, HitRec& out) const = 0;
     virtual bool firstHit(InfiniteRay r, uint64_t mask, HitRec& out) const = 0;
     virtual uint64_t countPairsDevice(double* seconds) = 0;
+    virtual uint64_t pairsView(double* seconds, const void** records) = 0;
     virtual void* native() const = 0;
     virtual void stats(double* out16) const = 0;
     virtual int stage(uint32_t n, const uint32_t* ids, const float* dxy) = 0;
@@ -227,6 +228,15 @@ struct RegistryHolder final : IRegistry
         return firstHitImpl(r, mask, out);
     }
 #if defined(RN_BACKEND_B200)
+    uint64_t pairsView(double* seconds, const void** records) override
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        const auto view = reg.getCollidingPairsView();
+        if (seconds)
+            *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *records = view.data();
+        return view.size();
+    }
     bool rayCastBatch(uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks, uint64_t* offsets,
                       std::vector<HitRec>& out) const override
     {
@@ -278,6 +288,16 @@ struct RegistryHolder final : IRegistry
     }
 #else
     std::vector<std::pair<std::vector<uint32_t>, std::vector<Translation>>> staged;
+    std::vector<typename Reg::EntityCollision> viewStorage;
+    uint64_t pairsView(double* seconds, const void** records) override
+    {
+        const auto t0 = std::chrono::steady_clock::now();
+        viewStorage = reg.getCollidingPairs();
+        if (seconds)
+            *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *records = viewStorage.data();
+        return viewStorage.size();
+    }
     bool rayCastBatch(uint32_t, const float*, const uint8_t*, const uint64_t*, uint64_t*, std::vector<HitRec>&) const override
     {
         return false;
@@ -620,6 +640,14 @@ void rn_first_hit_raycast(rn_ctx* ctx, uint32_t n, const float* ray4, const uint
             out_found[i] = ctx->reg->firstHit(Ray{Vec2{r[0], r[1]}, Vec2{r[2], r[3]}}, mask, hits[i]) ? 1 : 0;
     }
     RN_CATCH(ctx)
+}
+
+uint64_t rn_get_colliding_pairs_view(rn_ctx* ctx, double* seconds, const void** records)
+{
+    RN_TRY(ctx)
+    return ctx->reg->pairsView(seconds, records);
+    RN_CATCH(ctx)
+    return 0;
 }
 
 void* rn_native_context(rn_ctx* ctx)

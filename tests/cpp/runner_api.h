@@ -81,6 +81,10 @@ void rn_are_colliding(rn_ctx*, uint32_t n, const uint32_t* idsA, const uint32_t*
 void rn_first_hit_raycast(rn_ctx*, uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
                           uint8_t* out_found, void* out_hits32);
 
+/* getCollidingPairs() through the zero-copy extension (B200: Registry::getCollidingPairsView, a view of the pinned
+ * result buffer; reference: getCollidingPairs() into a kept vector).  *records stays valid until the next query. */
+uint64_t rn_get_colliding_pairs_view(rn_ctx*, double* seconds, const void** records);
+
 /* B200 only: the c2d_gpu_ctx* behind the Registry (Registry::nativeContext); NULL elsewhere. */
 void* rn_native_context(rn_ctx*);
 

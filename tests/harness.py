@@ -127,6 +127,7 @@ def load(name: str) -> C.CDLL:
         "rn_count_colliding_pairs_device": (u64, [vp, pd]),
         "rn_query_stats": (None, [vp, pd]),
         "rn_native_context": (vp, [vp]),
+        "rn_get_colliding_pairs_view": (u64, [vp, pd, C.POINTER(vp)]),
         "rn_get_collisions": (u64, [vp, u32]),
         "rn_are_colliding": (None, [vp, u32, pu32, pu32, pu8]),
         "rn_first_hit_raycast": (None, [vp, u32, pf, pu8, pu64, pu8, vp]),
@@ -312,6 +313,16 @@ class Backend:
     def release_staged(self, handle: int):
         self.lib.rn_release_staged(self.ctx, handle)
         self._check()
+
+    def get_colliding_pairs_view(self):
+        """(records copied out of the view, seconds of the API call only)"""
+        sec, ptr = C.c_double(0.0), C.c_void_p()
+        n = int(self.lib.rn_get_colliding_pairs_view(self.ctx, C.byref(sec), C.byref(ptr)))
+        self._check()
+        out = np.zeros(n, PAIR_DTYPE)
+        if n:
+            C.memmove(out.ctypes.data, ptr.value, n * PAIR_DTYPE.itemsize)
+        return out, sec.value
 
     def get_collisions(self, entity_id: int):
         n = int(self.lib.rn_get_collisions(self.ctx, int(entity_id)))
