@@ -243,7 +243,10 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     value = pairs_all / elapsed
 
     # ---- end-to-end arm: host buffers through the drop-in API ----------------------------------------------------
-    e2e_times, move_times, e2e_pairs, h2d, d2h = [], [], 0, 0.0, 0.0
+    from colli2de_b200 import sharding
+    from tests.harness import PAIR_DTYPE
+
+    e2e_times, move_times, e2e_pairs, h2d, d2h, gather_times = [], [], 0, 0.0, 0.0, []
     for f in range(2 + K):
         d = scenes.jitter(rng, n_dyn, 0.5)
         if f == 2:
@@ -255,9 +258,22 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         sec = C.c_double(0.0)
         n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
         b._check()
+        tg = 0.0
+        if world > 1:
+            # every rank holds the pairs of its Morton slab: gather the 84-byte records to rank 0 over NCCL
+            recs = np.zeros(n, PAIR_DTYPE)
+            if n:
+                b.lib.rn_copy_pairs(b.ctx, recs.ctypes.data_as(C.c_void_p))
+            tg = time.perf_counter()
+            gathered = sharding.gather_records(recs, dst=0)
+            torch.cuda.synchronize()
+            tg = time.perf_counter() - tg
+            if rank == 0 and f == 2:
+                assert len(np.unique(gathered[["shapeA", "shapeB"]])) == len(gathered), "duplicate pair across slabs"
         if f >= 2:
             st = b.stats()
-            e2e_times.append(sec.value)
+            e2e_times.append(sec.value + tg)
+            gather_times.append(tg)
             move_times.append(tm)
             e2e_pairs += n
             h2d += st["h2d_bytes"]
@@ -345,6 +361,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         "e2e": {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
                 "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "moves_host_ms": 1e3 * float(np.mean(move_times)),
+                "gather_ms_per_step": 1e3 * float(np.mean(gather_times)) if gather_times else 0.0,
                 "view_ms_per_step": 1e3 * float(np.mean(view_times)),
                 "view_call": "Registry::getCollidingPairsView() (extension: span over the pinned result buffer)",
                 "call": "c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity"},

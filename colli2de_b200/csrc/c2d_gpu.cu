@@ -466,12 +466,12 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         C2D_TIMED(ctx, "k_bin_count", k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch));
         C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
         C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
-        C2D_TIMED(ctx, "k_narrow_filter", k_narrow_filter<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
-        C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 8, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
+        C2D_TIMED(ctx, "k_narrow_filter", k_narrow_filter<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+        C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
         C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
-        C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 8, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+        C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                          static_cast<uint32_t>(ctx->out.capacity)));
-        C2D_TIMED(ctx, "k_narrow_manifold", k_narrow_manifold<<<148 * 8, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+        C2D_TIMED(ctx, "k_narrow_manifold", k_narrow_manifold<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                          static_cast<uint32_t>(ctx->out.capacity)));
         ctx->launches += 8;
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
