@@ -247,6 +247,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     from tests.harness import PAIR_DTYPE
 
     e2e_times, move_times, e2e_pairs, h2d, d2h, gather_times = [], [], 0, 0.0, 0.0, []
+    pinned = {}
     for f in range(2 + K):
         d = scenes.jitter(rng, n_dyn, 0.5)
         if f == 2:
@@ -256,20 +257,24 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         b.move_translate(dyn, d)
         tm = time.perf_counter() - tm
         sec = C.c_double(0.0)
-        n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
-        b._check()
         tg = 0.0
-        if world > 1:
-            # every rank holds the pairs of its Morton slab: gather the 84-byte records to rank 0 over NCCL
-            recs = np.zeros(n, PAIR_DTYPE)
-            if n:
-                b.lib.rn_copy_pairs(b.ctx, recs.ctypes.data_as(C.c_void_p))
+        if world == 1:
+            n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
+            b._check()
+        else:
+            # every rank computes the pairs of its Morton slab on the device (the move log goes H2D inside the call),
+            # the 84-byte records are gathered GPU-to-GPU over NCCL and downloaded once on rank 0
+            n = int(b.lib.rn_count_colliding_pairs_device(b.ctx, C.byref(sec)))
+            b._check()
+            dist.barrier()  # the untimed per-entity move logging skews the ranks: do not count that wait as gather time
             tg = time.perf_counter()
-            gathered = sharding.gather_records(recs, dst=0)
+            ptr, cnt = capi.device_records(ctx)
+            gathered, total = sharding.gather_device_records(ptr, cnt, PAIR_DTYPE.itemsize, dst=0, pinned=pinned)
             torch.cuda.synchronize()
             tg = time.perf_counter() - tg
             if rank == 0 and f == 2:
-                assert len(np.unique(gathered[["shapeA", "shapeB"]])) == len(gathered), "duplicate pair across slabs"
+                recs = np.frombuffer(gathered.tobytes(), dtype=PAIR_DTYPE)
+                assert len(recs) == total and len(np.unique(recs[["shapeA", "shapeB"]])) == total, "duplicate pair across slabs"
         if f >= 2:
             st = b.stats()
             e2e_times.append(sec.value + tg)

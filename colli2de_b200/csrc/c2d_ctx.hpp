@@ -211,6 +211,7 @@ struct c2d_gpu_ctx
     c2d_host::DevBuf<c2d_dev::PairOut> out;
     c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
     uint64_t lastCandidates = 0;
+    uint64_t lastPairs = 0;
     c2d_host::RayBuffers rays;
     c2d_host::GridBuffers grid;
     c2d_host::QueryBuffers query;

@@ -501,6 +501,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         ++ctx->launches;
     }
     ctx->lastCandidates = candCount;
+    ctx->lastPairs = pairCount;
 
     if (download && pairCount)
     {
@@ -892,6 +893,15 @@ int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t, const c2d_ray*, const c2d_hit_re
     return fail(ctx, "c2d_gpu_raycast: not built");
 }
 #endif
+
+int c2d_gpu_device_records(c2d_gpu_ctx* ctx, const void** out_device_ptr, uint64_t* out_count)
+{
+    if (out_device_ptr)
+        *out_device_ptr = ctx->out.ptr;
+    if (out_count)
+        *out_count = ctx->lastPairs;
+    return 0;
+}
 
 int c2d_gpu_read_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* out_tight4, float* out_fat4)
 {

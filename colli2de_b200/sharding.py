@@ -60,3 +60,41 @@ def gather_records(records: np.ndarray, dst: int = 0) -> np.ndarray | None:
     out = [np.frombuffer(parts[r][: int(counts[r].item()) * item].cpu().numpy().tobytes(), dtype=records.dtype)
            for r in range(world)]
     return np.concatenate(out) if out else records[:0]
+
+
+class _DeviceBytes:
+    """Wraps a raw device pointer for torch.as_tensor (CUDA array interface v2)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def gather_device_records(ptr: int, count: int, itemsize: int, dst: int = 0, pinned: dict | None = None):
+    """GPU-to-GPU gather (NCCL) of each rank's `count` records of `itemsize` bytes living at device address `ptr`.
+    Rank `dst` gets (host uint8 array of all records, total count) — downloaded once into a reusable pinned buffer;
+    the other ranks get (None, total count)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[rank] = count
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    host_counts = counts.cpu().tolist()
+    width = max(host_counts) * itemsize
+    send = torch.zeros(max(width, 1), dtype=torch.uint8, device=dev)
+    if count:
+        send[: count * itemsize] = torch.as_tensor(_DeviceBytes(ptr, count * itemsize), device=dev)
+    parts = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+    dist.gather(send, parts, dst=dst)
+    total = int(sum(host_counts))
+    if rank != dst:
+        return None, total
+    packed = torch.cat([parts[r][: host_counts[r] * itemsize] for r in range(world)])
+    if pinned is not None:
+        buf = pinned.get("buf")
+        if buf is None or buf.numel() < packed.numel():
+            buf = torch.empty(max(packed.numel(), 1) * 2, dtype=torch.uint8, pin_memory=True)
+            pinned["buf"] = buf
+        out = buf[: packed.numel()]
+        out.copy_(packed, non_blocking=False)
+        return out.numpy(), total
+    return packed.cpu().numpy(), total

@@ -178,6 +178,10 @@ int c2d_gpu_collide(c2d_gpu_ctx* ctx, const c2d_pair_record** out_records, uint6
 /* Same pipeline, results left on the device (no D2H of records): used to time the device-resident path.
  * out_count receives the number of colliding pairs. */
 int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* stats);
+/* Device address and count of the 84-byte records produced by the last c2d_gpu_collide / c2d_gpu_collide_device
+ * (valid until the next query on ctx): lets a multi-GPU driver gather the per-slab results GPU-to-GPU (NCCL)
+ * without a host round trip. */
+int c2d_gpu_device_records(c2d_gpu_ctx* ctx, const void** out_device_ptr, uint64_t* out_count);
 /* Registry::rayCast x n (Registry.hpp:1050-1182; DynamicBVH::piercingRaycast 775-806/853-884;
  * raycast(shape) RaycastShapes.cpp; sweep(shape, ray) Collision.hpp:323-344).  Hits of ray i are
  * out_hits[out_offsets[i] .. out_offsets[i+1]) ordered by (entryTime, exitTime) with exact-key
