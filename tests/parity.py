@@ -93,12 +93,13 @@ def adjudicate(name: str, ref: H.Backend, idx: SceneIndex, shapeA, shapeB):
     return man, hit
 
 
-def expected_pairs(name: str, ref: H.Backend, idx: SceneIndex, ref_pairs):
+def expected_pairs(name: str, ref: H.Backend, idx: SceneIndex, ref_pairs, return_dropped=False):
     """Canonical expected records from the reference's getCollidingPairs output:
     swapped same-tree pairs get their manifold re-evaluated by the reference's own collide/sweep in canonical
     orientation.  Returns (records sorted by key, number of orientation-ambiguous pairs dropped)."""
     can, swap = canonicalise(ref_pairs, idx)
     dropped = 0
+    dropped_records = can[:0]
     if swap.any():
         i = np.nonzero(swap)[0]
         man, hit = adjudicate(name, ref, idx, can["shapeA"][i], can["shapeB"][i])
@@ -107,6 +108,7 @@ def expected_pairs(name: str, ref: H.Backend, idx: SceneIndex, ref_pairs):
         keep = np.ones(len(can), bool)
         keep[i[~hit]] = False  # colliding only in the reference's own orientation (seg-seg noise, D8)
         dropped = int((~hit).sum())
+        dropped_records = can[~keep]
         can = can[keep]
     order = np.argsort(pair_keys(can), order=("eA", "sA", "eB", "sB"), kind="stable")
     can = can[order]
@@ -115,6 +117,8 @@ def expected_pairs(name: str, ref: H.Backend, idx: SceneIndex, ref_pairs):
     keys = pair_keys(can)
     first = np.ones(len(can), bool)
     first[1:] = keys[1:] != keys[:-1]
+    if return_dropped:
+        return can[first], dropped_records
     return can[first], dropped
 
 
