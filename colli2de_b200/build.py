@@ -73,6 +73,20 @@ def build_runner(force: bool = False) -> str:
     return RUNNER_LIB
 
 
+API_CHECK = os.path.join(HERE, "api_check")
+
+
+def build_api_check(force: bool = False) -> str:
+    """tests/cpp/api_check.cpp: an "application" using the drop-in headers with non-uint32 EntityIds."""
+    src = os.path.join(REPO, "tests", "cpp", "api_check.cpp")
+    inc = os.path.join(REPO, "include")
+    deps = [src, GPU_LIB, os.path.join(inc, "colli2de", "Registry.hpp"), os.path.join(inc, "c2d_gpu.h")]
+    if force or not _newer(API_CHECK, deps):
+        _run(["g++", "-std=c++23", "-O2", "-DENABLE_ASSERT", "-I" + inc, src, "-o", API_CHECK, "-L" + HERE, "-lc2d_gpu",
+              "-Wl,-rpath,$ORIGIN"])
+    return API_CHECK
+
+
 def build_oracles():
     targets = ["ref"] + (["oracle"] if os.path.exists(os.path.join(REPO, "oracle", "c2d_oracle.c")) else [])
     _run(["make", "-C", os.path.join(REPO, "oracle"), *targets])
@@ -81,6 +95,7 @@ def build_oracles():
 def build_all(force: bool = False):
     build_gpu_lib(force)
     build_runner(force)
+    build_api_check(force)
     build_oracles()
 
 
