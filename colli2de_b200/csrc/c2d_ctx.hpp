@@ -106,6 +106,10 @@ struct RayBuffers
     PinnedVec<c2d_hit_record> hostHits;
     PinnedVec<uint64_t> hostOffsets;
     PinnedVec<uint32_t> hostOffsets32;
+    // small-batch (block-per-ray) path
+    DevBuf<unsigned char> smallHeaders;
+    PinnedVec<unsigned char> hostSmall;
+    PinnedVec<c2d_hit_record> hostReorder;
 };
 
 // buffers of the uniform-grid broadphase (c2d_grid.cu)

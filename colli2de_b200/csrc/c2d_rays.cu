@@ -506,6 +506,327 @@ TreeView view_of(const c2d_gpu_ctx* ctx, int body)
 
 } // namespace
 
+// ---------------------------------------------------------------------------------------------------------
+// Small batches (the reference's one-ray-per-call rayCast / firstHitRayCast): ONE fused kernel, one 256-thread
+// block per ray.  The thread-per-ray pipeline above is a throughput design — a single long ray would be walked,
+// sorted and narrow-phased by one thread (milliseconds at 1 M shapes).  Here the block pops up to 256 nodes of a
+// shared stack per step, collects the leaf-box hits in shared memory, bitonic-sorts them, runs the narrowphase one
+// hit per thread and bitonic-sorts the survivors; the std::set semantics are the ones described at the top of the
+// file.  A ray with more than kSmallCap leaf-box hits (or a frontier above kSmallStack) sets an overflow flag and the
+// caller falls back to the general pipeline.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kSmallThreads = 256;
+constexpr int kSmallCap = 2048;   // leaf-box hits per ray held in shared memory (32 KB)
+constexpr int kSmallStack = 2048; // traversal frontier (8 KB)
+
+struct SmallHeader // per ray, downloaded in one copy
+{
+    uint32_t count;    // final hits
+    uint32_t base;     // first record in the packed output
+    uint32_t leafHits; // leaf-box hits (statistics)
+    uint32_t overflow; // 1: fall back to the general pipeline
+};
+
+template <typename Less>
+__device__ void bitonic_sort_shared(LeafHit* a, int n, Less less)
+{
+    // n is a power of two; all threads of the block participate
+    for (int k = 2; k <= n; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            for (int i = threadIdx.x; i < n; i += blockDim.x)
+            {
+                const int ixj = i ^ j;
+                if (ixj > i)
+                {
+                    const bool up = (i & k) == 0;
+                    const LeafHit x = a[i], y = a[ixj];
+                    if (up ? less(y, x) : less(x, y))
+                    {
+                        a[i] = y;
+                        a[ixj] = x;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__device__ __forceinline__ bool narrow_ray_hit(const ShapeArrays& s, const LeafHit& h, uint32_t tree, const RayQ& q,
+                                               V2 second, float& a, float& b)
+{
+    const uint32_t meta = s.meta[h.shape];
+    ShapeRef S;
+    S.type = static_cast<int>(meta_type(meta));
+    S.count = static_cast<int>(meta_count(meta));
+    S.g = s.geom + static_cast<size_t>(h.shape) * 32;
+    const float4 x = s.xf[h.shape];
+    XF cur;
+    cur.tx = x.x;
+    cur.ty = x.y;
+    cur.s = x.z;
+    cur.c = x.w;
+    if (tree == 2u)
+    {
+        const float4 p = s.pxf[h.shape], pa = s.pxa[h.shape], ca = s.xa[h.shape];
+        XF prev;
+        prev.tx = p.x;
+        prev.ty = p.y;
+        prev.s = p.z;
+        prev.c = p.w;
+        return ray_sweep(S, motion_between(prev, pa.x, pa.y, pa.z, cur, ca.x), q, second, a, b);
+    }
+    return ray_shape(S, cur, q, second, a, b);
+}
+
+__global__ void __launch_bounds__(kSmallThreads)
+    k_ray_small(const RayIn* __restrict__ rays, uint32_t n, TreeView t0, TreeView t1, TreeView t2, ShapeArrays s,
+                float gridCell, bool firstHitOnly, SmallHeader* __restrict__ headers, uint32_t* __restrict__ cursor,
+                c2d_hit_record* __restrict__ out, uint32_t outCapacity)
+{
+    __shared__ LeafHit hits[kSmallCap];
+    __shared__ int stack[kSmallStack];
+    __shared__ int stackSize, hitCount, keptCount, overflow, outBase;
+    const uint32_t rayIdx = blockIdx.x;
+    if (rayIdx >= n)
+        return;
+    V2 second;
+    const RayIn r = rays[rayIdx];
+    const RayQ q = make_ray(r, second);
+    const RayQ bq = box_ray_of(q, gridCell);
+    const TreeView trees[3] = {t0, t1, t2};
+    if (threadIdx.x == 0)
+    {
+        stackSize = hitCount = keptCount = overflow = 0;
+    }
+    __syncthreads();
+
+    // ---- traversal: (tree << 28 | node) entries, up to 256 popped per step
+    if (threadIdx.x < 3)
+    {
+        const TreeView& t = trees[threadIdx.x];
+        if (t.n == 1)
+        {
+            const uint32_t shape = t.sorted[0];
+            const float4 b = s.fat[shape];
+            float a0, a1;
+            if ((s.category[shape] & r.mask) != 0 && ray_box(bq, b.x, b.y, b.z, b.w, a0, a1))
+                hits[atomicAdd(&hitCount, 1)] = LeafHit{a0, a1, shape, threadIdx.x};
+        }
+        else if (t.n > 1)
+            stack[atomicAdd(&stackSize, 1)] = static_cast<int>(threadIdx.x << 28);
+    }
+    __syncthreads();
+    while (true)
+    {
+        const int size = stackSize;
+        if (size == 0 || overflow)
+            break;
+        const int take = size < kSmallThreads ? size : kSmallThreads;
+        int entry = -1;
+        if (static_cast<int>(threadIdx.x) < take)
+            entry = stack[size - 1 - threadIdx.x];
+        __syncthreads();
+        if (threadIdx.x == 0)
+            stackSize = size - take;
+        __syncthreads();
+        if (entry >= 0)
+        {
+            const uint32_t tree = static_cast<uint32_t>(entry) >> 28;
+            const BvhNode N = trees[tree].nodes[entry & 0x0fffffff];
+            float a0, a1;
+            if ((N.catL & r.mask) != 0 && ray_box(bq, N.boxL.x, N.boxL.y, N.boxL.z, N.boxL.w, a0, a1))
+            {
+                if (N.left < 0)
+                {
+                    const int at = atomicAdd(&hitCount, 1);
+                    if (at < kSmallCap)
+                        hits[at] = LeafHit{a0, a1, trees[tree].sorted[~N.left], tree};
+                    else
+                        overflow = 1;
+                }
+                else
+                {
+                    const int at = atomicAdd(&stackSize, 1);
+                    if (at < kSmallStack)
+                        stack[at] = static_cast<int>(tree << 28) | N.left;
+                    else
+                        overflow = 1;
+                }
+            }
+            if ((N.catR & r.mask) != 0 && ray_box(bq, N.boxR.x, N.boxR.y, N.boxR.z, N.boxR.w, a0, a1))
+            {
+                if (N.right < 0)
+                {
+                    const int at = atomicAdd(&hitCount, 1);
+                    if (at < kSmallCap)
+                        hits[at] = LeafHit{a0, a1, trees[tree].sorted[~N.right], tree};
+                    else
+                        overflow = 1;
+                }
+                else
+                {
+                    const int at = atomicAdd(&stackSize, 1);
+                    if (at < kSmallStack)
+                        stack[at] = static_cast<int>(tree << 28) | N.right;
+                    else
+                        overflow = 1;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    if (overflow)
+    {
+        if (threadIdx.x == 0)
+            headers[rayIdx] = SmallHeader{0u, 0u, static_cast<uint32_t>(hitCount), 1u};
+        return;
+    }
+    const int c = hitCount;
+    // ---- sort the leaf-box hits by (tree, entry, exit, shape); pad to a power of two with +inf keys
+    int padded = 1;
+    while (padded < c)
+        padded <<= 1;
+    for (int i = c + threadIdx.x; i < padded; i += blockDim.x)
+        hits[i] = LeafHit{FLT_MAX, FLT_MAX, 0xffffffffu, 0xffffffffu};
+    __syncthreads();
+    bitonic_sort_shared(hits, padded, ByTreeTimeShape());
+
+    if (firstHitOnly)
+    {
+        // the reference's countdown is inherently sequential (Registry.hpp:866-1048); one thread walks the sorted sets
+        if (threadIdx.x == 0)
+        {
+            bool have = false;
+            float bestEntry = FLT_MAX;
+            LeafHit best = hits[0];
+            int k = 0;
+            for (uint32_t tree = 0; tree < 3; ++tree)
+            {
+                const int b = k;
+                while (k < c && hits[k].order == tree)
+                    ++k;
+                uint32_t toCheck = 0;
+                for (int j = b; j < k; ++j)
+                    if (j == b || hits[j].t0 != hits[j - 1].t0 || hits[j].t1 != hits[j - 1].t1)
+                        ++toCheck;
+                for (int j = b; j < k; ++j)
+                {
+                    if (j != b && hits[j].t0 == hits[j - 1].t0 && hits[j].t1 == hits[j - 1].t1)
+                        continue;
+                    if (!(s.meta[hits[j].shape] & META_ACTIVE))
+                        continue;
+                    float a0 = 0.0f, a1 = 0.0f;
+                    if (narrow_ray_hit(s, hits[j], tree, q, second, a0, a1) && a0 < bestEntry)
+                    {
+                        bestEntry = a0;
+                        best = LeafHit{a0, a1, hits[j].shape, 0u};
+                        have = true;
+                        toCheck = 5;
+                    }
+                    if (--toCheck == 0)
+                        break;
+                }
+            }
+            uint32_t base = 0;
+            if (have)
+            {
+                base = atomicAdd(cursor, 1u);
+                if (base < outCapacity)
+                {
+                    const V2 en = q.start + q.d * best.t0, ex = q.start + q.d * best.t1;
+                    out[base] = c2d_hit_record{s.entity[best.shape], best.shape, {en.x, en.y}, {ex.x, ex.y}, best.t0, best.t1};
+                }
+            }
+            headers[rayIdx] = SmallHeader{have ? 1u : 0u, base, static_cast<uint32_t>(c), 0u};
+        }
+        return;
+    }
+
+    // ---- leaf-box set dedupe, active check, narrowphase: one sorted entry per thread; survivors keep their sorted
+    // position as insertion index and are compacted in any order (the final sort orders them)
+    LeafHit mine[kSmallCap / kSmallThreads];
+    bool keep[kSmallCap / kSmallThreads];
+#pragma unroll
+    for (int u = 0; u < kSmallCap / kSmallThreads; ++u)
+    {
+        const int i = threadIdx.x + u * kSmallThreads;
+        keep[u] = false;
+        if (i < c)
+        {
+            const LeafHit h = hits[i];
+            const bool dup = i > 0 && hits[i - 1].order == h.order && hits[i - 1].t0 == h.t0 && hits[i - 1].t1 == h.t1;
+            if (!dup && (s.meta[h.shape] & META_ACTIVE))
+            {
+                float a0 = 0.0f, a1 = 0.0f;
+                if (narrow_ray_hit(s, h, h.order, q, second, a0, a1))
+                {
+                    keep[u] = true;
+                    mine[u] = LeafHit{a0, a1, h.shape, static_cast<uint32_t>(i)};
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kSmallCap / kSmallThreads; ++u)
+        if (keep[u])
+            hits[atomicAdd(&keptCount, 1)] = mine[u];
+    __syncthreads();
+    const int kept = keptCount;
+    padded = 1;
+    while (padded < kept)
+        padded <<= 1;
+    for (int i = kept + threadIdx.x; i < padded; i += blockDim.x)
+        hits[i] = LeafHit{FLT_MAX, FLT_MAX, 0xffffffffu, 0xffffffffu};
+    __syncthreads();
+    bitonic_sort_shared(hits, padded, ByTimeInsertion());
+    // ---- final std::set: drop entries whose (entry, exit) equals the previous one; ordered compaction by a block scan
+    __shared__ int scan[kSmallThreads];
+    int local = 0;
+    constexpr int kPer = kSmallCap / kSmallThreads;
+    bool flag[kPer];
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+    {
+        const int i = threadIdx.x * kPer + u;
+        flag[u] = i < kept && (i == 0 || hits[i - 1].t0 != hits[i].t0 || hits[i - 1].t1 != hits[i].t1);
+        local += flag[u] ? 1 : 0;
+    }
+    scan[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 1; o < kSmallThreads; o <<= 1)
+    {
+        const int v = threadIdx.x >= o ? scan[threadIdx.x - o] : 0;
+        __syncthreads();
+        scan[threadIdx.x] += v;
+        __syncthreads();
+    }
+    const int total = scan[kSmallThreads - 1];
+    if (threadIdx.x == 0)
+        outBase = static_cast<int>(atomicAdd(cursor, static_cast<uint32_t>(total)));
+    __syncthreads();
+    int pos = outBase + scan[threadIdx.x] - local;
+#pragma unroll
+    for (int u = 0; u < kPer; ++u)
+    {
+        const int i = threadIdx.x * kPer + u;
+        if (flag[u])
+        {
+            if (static_cast<uint32_t>(pos) < outCapacity)
+            {
+                const LeafHit h = hits[i];
+                const V2 en = q.start + q.d * h.t0, ex = q.start + q.d * h.t1;
+                out[pos] = c2d_hit_record{s.entity[h.shape], h.shape, {en.x, en.y}, {ex.x, ex.y}, h.t0, h.t1};
+            }
+            ++pos;
+        }
+    }
+    if (threadIdx.x == 0)
+        headers[rayIdx] = SmallHeader{static_cast<uint32_t>(total), static_cast<uint32_t>(outBase), static_cast<uint32_t>(c), 0u};
+}
+
 int c2d_host::exclusive_scan_u32(c2d_gpu_ctx* ctx, uint32_t* data, uint32_t n, DevBuf<uint32_t>& sums, uint32_t* dTotal)
 {
     const uint32_t nblocks = (n + 1023) / 1024;
@@ -555,6 +876,89 @@ static int raycast_impl(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, bool 
 
     const TreeView t0 = view_of(ctx, 0), t1 = view_of(ctx, 1), t2 = view_of(ctx, 2);
     const float gridCell = ctx->broadphase == C2D_BROADPHASE_GRID ? static_cast<float>(static_cast<int32_t>(ctx->cellSize)) : 0.0f;
+
+    // ---- small batches: one fused kernel, one block per ray (falls through to the general path on overflow)
+    constexpr uint32_t kSmallBatch = 64;
+    if (n > 0 && n <= kSmallBatch)
+    {
+        const uint32_t outCap = kSmallBatch * kSmallCap;
+        C2D_CUDA(ctx, rb.dRays.reserve(kSmallBatch));
+        C2D_CUDA(ctx, rb.smallHeaders.reserve(kSmallBatch * sizeof(SmallHeader) + 16));
+        C2D_CUDA(ctx, rb.out.reserve(outCap));
+        if (!rb.hostSmall.reserve(kSmallBatch * sizeof(SmallHeader) + 16) || !rb.hostHits.reserve(outCap))
+            return fail(ctx, "pinned host allocation failed");
+        SmallHeader* dHeaders = reinterpret_cast<SmallHeader*>(rb.smallHeaders.ptr + 16);
+        uint32_t* dCursor = reinterpret_cast<uint32_t*>(rb.smallHeaders.ptr);
+        C2D_CUDA(ctx, cudaMemsetAsync(dCursor, 0, 16, s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(rb.dRays.ptr, rays, static_cast<size_t>(n) * sizeof(c2d_ray), cudaMemcpyHostToDevice, s));
+        k_ray_small<<<n, kSmallThreads, 0, s>>>(reinterpret_cast<const RayIn*>(rb.dRays.ptr), n, t0, t1, t2, ctx->d, gridCell,
+                                                firstHitOnly, dHeaders, dCursor, rb.out.ptr, outCap);
+        ++ctx->launches;
+        // header block + the first records in ONE copy; a second copy only if there are more
+        constexpr uint32_t kEager = 64;
+        C2D_CUDA(ctx, cudaMemcpyAsync(rb.hostSmall.data, rb.smallHeaders.ptr, 16 + static_cast<size_t>(n) * sizeof(SmallHeader),
+                                      cudaMemcpyDeviceToHost, s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(rb.hostHits.data, rb.out.ptr, kEager * sizeof(c2d_hit_record), cudaMemcpyDeviceToHost, s));
+        C2D_CUDA(ctx, cudaStreamSynchronize(s));
+        C2D_CUDA(ctx, cudaGetLastError());
+        const uint32_t produced = *reinterpret_cast<const uint32_t*>(rb.hostSmall.data);
+        const SmallHeader* hh = reinterpret_cast<const SmallHeader*>(rb.hostSmall.data + 16);
+        bool overflowed = produced > outCap;
+        for (uint32_t i = 0; i < n; ++i)
+            overflowed = overflowed || hh[i].overflow != 0;
+        if (!overflowed)
+        {
+            if (produced > kEager)
+            {
+                C2D_CUDA(ctx, cudaMemcpyAsync(rb.hostHits.data + kEager, rb.out.ptr + kEager,
+                                              static_cast<size_t>(produced - kEager) * sizeof(c2d_hit_record),
+                                              cudaMemcpyDeviceToHost, s));
+                C2D_CUDA(ctx, cudaStreamSynchronize(s));
+            }
+            // the blocks packed their hits in completion order: bring them into ray order
+            if (n == 1)
+            {
+                rb.hostOffsets.data[0] = 0;
+                rb.hostOffsets.data[1] = hh[0].count;
+                leafHits = hh[0].leafHits;
+                totalHits = hh[0].count;
+            }
+            else
+            {
+                if (!rb.hostReorder.reserve(std::max<uint32_t>(produced, 1)))
+                    return fail(ctx, "pinned host allocation failed");
+                for (uint32_t i = 0; i < n; ++i)
+                {
+                    rb.hostOffsets.data[i] = totalHits;
+                    std::memcpy(rb.hostReorder.data + totalHits, rb.hostHits.data + hh[i].base,
+                                static_cast<size_t>(hh[i].count) * sizeof(c2d_hit_record));
+                    totalHits += hh[i].count;
+                    leafHits += hh[i].leafHits;
+                }
+                rb.hostOffsets.data[n] = totalHits;
+                std::memcpy(rb.hostHits.data, rb.hostReorder.data, static_cast<size_t>(totalHits) * sizeof(c2d_hit_record));
+            }
+            rb.hostHits.size = totalHits;
+            if (out_hits)
+                *out_hits = rb.hostHits.data;
+            if (out_offsets)
+                *out_offsets = rb.hostOffsets.data;
+            if (stats)
+            {
+                std::memset(stats, 0, sizeof(*stats));
+                stats->shapes_alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
+                stats->candidates = leafHits;
+                stats->pairs = totalHits;
+                stats->h2d_bytes = static_cast<uint64_t>(n) * sizeof(c2d_ray);
+                stats->d2h_bytes = 16 + static_cast<uint64_t>(n) * sizeof(SmallHeader) + std::max<uint64_t>(produced, kEager) * sizeof(c2d_hit_record);
+                stats->kernel_launches = ctx->launches;
+                stats->ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+            }
+            return 0;
+        }
+        totalHits = 0;
+        leafHits = 0;
+    }
     const uint32_t kChunk = 1u << 20;
     for (uint32_t first = 0; first < n; first += kChunk)
     {
