@@ -179,7 +179,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.lib()  # fail loudly if libc2d_gpu.so is missing
-    b = H.Backend("b200")
+    b = H.Backend("b200", 1 if args.grid_cell > 0 else 0, max(args.grid_cell, 1))
     scenes.populate(b, scene)
     ctx = b.native_context()
     capi.set_shard(ctx, rank, world)
@@ -361,6 +361,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                    "l2": "inputs larger than L2 (fresh 16 MB move batch per frame; ~255 MB shape state + ~100 MB "
                          "sort/tree buffers rewritten every frame vs 126 MB L2), no explicit flush",
                    "lbvh_rebuild_period": args.rebuild_period,
+                   "broadphase": f"uniform grid, cell {args.grid_cell}" if args.grid_cell > 0 else "LBVH",
                    "pairs_per_frame": pairs_per_frame, "candidates_per_frame": cand_per_frame * world,
                    "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()}},
         "e2e": {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
@@ -385,6 +386,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid-cell", type=int, default=0,
+                    help="> 0: use Registry<Grid>(cell) = the uniform-grid sort-and-sweep broadphase instead of the LBVH")
     ap.add_argument("--rebuild-period", type=int, default=4,
                     help="LBVH topology rebuilt every N-th frame, bottom-up refit in between (1 = every frame)")
     args = ap.parse_args()
