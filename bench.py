@@ -108,9 +108,23 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_scene(name: str):
+def build_scene(name: str, scale: int = 1):
+    """The workload; scale > 1 builds the scale-times larger world of the weak-scaling runs (same density)."""
     n_dyn, n_sta, box, clustered = WORKLOADS[name]
-    return scenes.mixed_scene(n_dyn, n_sta, box, clustered=clustered), n_dyn, n_sta
+    return (scenes.mixed_scene(n_dyn * scale, n_sta * scale, box * scale ** 0.5, clustered=clustered),
+            n_dyn * scale, n_sta * scale)
+
+
+HALO_MARGIN = 32.0  # > largest fat-box interaction distance (~10) + the random-walk drift of a bench run
+
+
+def local_slab(scene, rank: int, world: int):
+    """Sub-scene of spatial slab `rank` (owned shapes + halo copies) and the mask of the halo copies in it."""
+    from colli2de_b200 import sharding
+
+    owned, ghost = sharding.slab_selection(scene["ent_xf3"][:, 0], rank, world, HALO_MARGIN)
+    local = np.nonzero(owned | ghost)[0]
+    return {k: v[local] for k, v in scene.items()}, ghost[local], local
 
 
 def measured_peak_gbs():
@@ -180,11 +194,22 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.lib()  # fail loudly if libc2d_gpu.so is missing
     b = H.Backend("b200", 1 if args.grid_cell > 0 else 0, max(args.grid_cell, 1))
-    scenes.populate(b, scene)
+    weak = world > 1 and args.scaling in ("auto", "weak")
+    n_total_dyn, n_total_sta = n_dyn, n_sta
+    if weak:
+        # this rank's spatial slab of the N-times larger world + halo copies of the neighbours' boundary shapes
+        scene, ghost_mask, local_index = local_slab(scene, rank, world)
+        ids = scenes.populate(b, scene)
+        b.set_ghost(ids[ghost_mask], np.ones(int(ghost_mask.sum()), np.uint8))
+        dyn = scene["ent_id"][scene["ent_body"] != 0]
+        n_dyn, n_sta = len(dyn), len(scene["ent_id"]) - len(dyn)
+    else:
+        scenes.populate(b, scene)
+        dyn = np.arange(n_dyn, dtype=np.uint32)
     ctx = b.native_context()
-    capi.set_shard(ctx, rank, world)
+    if not weak:
+        capi.set_shard(ctx, rank, world)
     capi.set_rebuild_period(ctx, args.rebuild_period)
-    dyn = np.arange(n_dyn, dtype=np.uint32)
     K, W = args.steps, args.warmup
 
     def barrier():
@@ -208,7 +233,16 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
 
     # ---- device-resident arm: move batches staged in HBM before the timed region -------------------------------
     rng = scenes.LCG(2024)
-    handles = [b.stage_translations(dyn, scenes.jitter(rng, n_dyn, 0.5)) for _ in range(W + K)]
+
+    def frame_moves():
+        """The frame's move of every dynamic entity this rank holds.  Weak mode: the moves are a function of the global
+        entity id (every rank draws the world's stream and keeps its slab), so halo copies move exactly like their
+        originals without any exchange."""
+        if not weak:
+            return scenes.jitter(rng, n_dyn, 0.5)
+        return scenes.jitter(rng, n_total_dyn, 0.5)[dyn]
+
+    handles = [b.stage_translations(dyn, frame_moves()) for _ in range(W + K)]
     for h in handles[:W]:
         b.apply_staged(h)
         b.count_pairs_device()
@@ -249,10 +283,9 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     e2e_times, move_times, e2e_pairs, h2d, d2h, gather_times = [], [], 0, 0.0, 0.0, []
     pinned = {}
     for f in range(2 + K):
-        d = scenes.jitter(rng, n_dyn, 0.5)
+        d = frame_moves()
         if f == 2:
             barrier()
-            te0 = time.perf_counter()
         tm = time.perf_counter()
         b.move_translate(dyn, d)
         tm = time.perf_counter() - tm
@@ -274,7 +307,8 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
             tg = time.perf_counter() - tg
             if rank == 0 and f == 2:
                 recs = np.frombuffer(gathered.tobytes(), dtype=PAIR_DTYPE)
-                assert len(recs) == total and len(np.unique(recs[["shapeA", "shapeB"]])) == total, "duplicate pair across slabs"
+                key = ["entityA", "entityB"] if weak else ["shapeA", "shapeB"]  # shape ids are rank-local in weak mode
+                assert len(recs) == total and len(np.unique(recs[key])) == total, "duplicate pair across slabs"
         if f >= 2:
             st = b.stats()
             e2e_times.append(sec.value + tg)
@@ -286,7 +320,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     # same loop through the zero-copy extension (a view of the pinned result buffer instead of a fresh std::vector)
     view_times = []
     for f in range(1 + min(K, 8)):
-        b.move_translate(dyn, scenes.jitter(rng, n_dyn, 0.5))
+        b.move_translate(dyn, frame_moves())
         sec, ptr = C.c_double(0.0), C.c_void_p()
         b.lib.rn_get_colliding_pairs_view(b.ctx, C.byref(sec), C.byref(ptr))
         b._check()
@@ -353,11 +387,15 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.workload}: {n_dyn} dynamic mixed circle/capsule/segment/polygon + {n_sta} static "
                                f"polygons, per-frame jitter U(-0.5,0.5)^2, LCG seed 4242 (SURVEY.md 8(d) cfg 3)",
-                   "parallelism": f"morton-slab x{world}" if world > 1 else "single GPU",
+                   "parallelism": ("single GPU" if world == 1 else
+                                   f"weak: {world} x the workload ({n_total_dyn} dynamic + {n_total_sta} static in one world), one "
+                                   f"equal-population x-slab per GPU + halo copies within {HALO_MARGIN} units, owner rule, no "
+                                   f"data-path collective (rank 0 slab: {n_dyn} dynamic + {n_sta} static incl. halo)" if weak else
+                                   f"strong: fixed workload mirrored on {world} GPUs, query leaves sharded by Morton-rank slab"),
                    "l2": "inputs larger than L2 (fresh 16 MB move batch per frame; ~255 MB shape state + ~100 MB "
                          "sort/tree buffers rewritten every frame vs 126 MB L2), no explicit flush",
                    "lbvh_rebuild_period": args.rebuild_period,
@@ -386,6 +424,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
+                    help="multi-GPU mode: weak = the world grows with N (N x the workload, every rank owns one spatial slab "
+                         "+ halo copies, no data-path collective); strong = the fixed workload mirrored on every rank, "
+                         "query leaves sharded by Morton slab.  auto = weak for N > 1")
     ap.add_argument("--grid-cell", type=int, default=0,
                     help="> 0: use Registry<Grid>(cell) = the uniform-grid sort-and-sweep broadphase instead of the LBVH")
     ap.add_argument("--rebuild-period", type=int, default=4,
@@ -397,11 +439,12 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        scene, n_dyn, n_sta = build_scene(args.workload)
+        weak = args.gpus > 1 and args.scaling in ("auto", "weak")
+        scene, n_dyn, n_sta = build_scene(args.workload, args.gpus if weak else 1)
         r = run_reference(args, scene, n_dyn, as_baseline=False)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": f"{args.workload}: {n_dyn} dynamic + {n_sta} static (same scene and seed as the own arm)",
                            "pairs_per_frame": r["pairs_per_frame"]},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")},
@@ -410,7 +453,8 @@ def main():
         print(json.dumps(line))
         return 0
 
-    scene, n_dyn, n_sta = build_scene(args.workload)
+    weak = world > 1 and args.scaling in ("auto", "weak")
+    scene, n_dyn, n_sta = build_scene(args.workload, world if weak else 1)
     out = run_b200(args, scene, n_dyn, n_sta, rank, world, local)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:

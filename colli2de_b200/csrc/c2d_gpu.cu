@@ -753,6 +753,19 @@ int c2d_gpu_shape_set_active(c2d_gpu_ctx* ctx, uint32_t shape, int active)
     return 0;
 }
 
+int c2d_gpu_shape_set_ghost(c2d_gpu_ctx* ctx, uint32_t shape, int ghost)
+{
+    if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
+        return fail(ctx, "c2d_gpu_shape_set_ghost: unknown shape");
+    claim(ctx, shape, PH_FLAG);
+    FlagRec* r = ctx->flagLog->push();
+    if (!r)
+        return fail(ctx, "pinned host allocation failed");
+    r->shape = shape;
+    r->op = ghost ? 3u : 4u;
+    return 0;
+}
+
 int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy)
 {
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))

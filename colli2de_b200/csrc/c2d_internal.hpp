@@ -15,6 +15,7 @@ constexpr uint32_t META_TYPE_MASK = 0x3u;
 constexpr uint32_t META_BODY_SHIFT = 2;
 constexpr uint32_t META_ACTIVE = 1u << 4;
 constexpr uint32_t META_ALIVE = 1u << 5;
+constexpr uint32_t META_GHOST = 1u << 6; // halo copy of a shape owned by another rank (multi-GPU slabs)
 constexpr uint32_t META_COUNT_SHIFT = 8;
 
 __host__ __device__ inline uint32_t meta_type(uint32_t m) { return m & META_TYPE_MASK; }
@@ -25,7 +26,7 @@ __host__ __device__ inline uint32_t meta_count(uint32_t m) { return (m >> META_C
 struct FlagRec // 8 B: remove / activate / deactivate
 {
     uint32_t shape;
-    uint32_t op; // 0 remove, 1 activate, 2 deactivate
+    uint32_t op; // 0 remove, 1 activate, 2 deactivate, 3 mark ghost, 4 clear ghost
 };
 struct TransRec // 16 B: moveEntity(id, Translation) for one shape
 {

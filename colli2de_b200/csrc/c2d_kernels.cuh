@@ -58,8 +58,12 @@ __global__ void __launch_bounds__(256) k_apply_flags(const FlagRec* __restrict__
         m &= ~META_ALIVE;
     else if (r.op == 1)
         m |= META_ACTIVE;
-    else
+    else if (r.op == 2)
         m &= ~META_ACTIVE;
+    else if (r.op == 3)
+        m |= META_GHOST;
+    else
+        m &= ~META_GHOST;
     s.meta[r.shape] = m;
 }
 
@@ -564,6 +568,17 @@ __device__ __forceinline__ bool load_pair(const ShapeArrays& s, uint2 p, PairCtx
     // self-collision and inactive shapes are rejected here, not in the broadphase (Registry.hpp:619-624)
     if (c.ea == c.eb || !(ma & META_ACTIVE) || !(mb & META_ACTIVE))
         return false;
+    // Multi-GPU owner rule: every rank holds its slab plus halo ("ghost") copies of the neighbours'
+    // boundary shapes.  A pair belongs to exactly one rank: the one that OWNS the pair's owner shape — shape A for
+    // cross-tree pairs (the Dynamic / Bullet side), the shape of the entity with the smaller tag for same-tree pairs
+    // (entity tags are global, local shape ids are not).
+    if ((ma | mb) & META_GHOST)
+    {
+        const bool sameTree = meta_body(ma) == meta_body(mb);
+        const uint32_t ownerMeta = (!sameTree || c.ea < c.eb) ? ma : mb;
+        if (ownerMeta & META_GHOST)
+            return false;
+    }
     c.A.type = static_cast<int>(meta_type(ma));
     c.A.count = static_cast<int>(meta_count(ma));
     c.A.g = s.geom + static_cast<size_t>(p.x) * 32;

@@ -98,3 +98,25 @@ def gather_device_records(ptr: int, count: int, itemsize: int, dst: int = 0, pin
         out.copy_(packed, non_blocking=False)
         return out.numpy(), total
     return packed.cpu().numpy(), total
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Spatial slabs with halo ("ghost") copies — the weak-scaling decomposition of a large world
+# ---------------------------------------------------------------------------------------------------------------
+def slab_edges(x: np.ndarray, world: int) -> np.ndarray:
+    """world + 1 x-coordinates cutting the shapes into `world` slabs of (almost) equal population (quantiles, so a
+    clustered world is balanced too); edges[0] = -inf, edges[-1] = +inf."""
+    order = np.sort(np.asarray(x, np.float64))
+    cuts = [order[(len(order) * r) // world] for r in range(1, world)]
+    return np.array([-np.inf, *cuts, np.inf])
+
+
+def slab_selection(x: np.ndarray, rank: int, world: int, margin: float):
+    """(owned mask, ghost mask) of slab `rank`: owned = centre in [edge_r, edge_r+1); ghosts = centres of the other
+    slabs within `margin` of this slab.  `margin` must exceed the largest interaction distance (fat box extents)
+    plus the drift accumulated while the decomposition is kept."""
+    e = slab_edges(x, world)
+    lo, hi = e[rank], e[rank + 1]
+    owned = (x >= lo) & (x < hi)
+    near = (x >= lo - margin) & (x < hi + margin)
+    return owned, near & ~owned

@@ -145,6 +145,11 @@ int c2d_gpu_shape_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t entity_tag, uin
 int c2d_gpu_shape_remove(c2d_gpu_ctx* ctx, uint32_t shape);
 /* Registry::setShapeActive (Registry.hpp:353-358). */
 int c2d_gpu_shape_set_active(c2d_gpu_ctx* ctx, uint32_t shape, int active);
+/* Multi-GPU slabs (no reference counterpart): marks a shape as a halo ("ghost") copy of a shape another rank owns.
+ * Ghosts take part in the broadphase and narrowphase like any shape, but a pair whose OWNER shape (shape A of a
+ * cross-tree pair; the shape of the entity with the smaller tag of a same-tree pair) is a ghost is left to the rank
+ * that owns it, so the union of all ranks' results has every pair exactly once. */
+int c2d_gpu_shape_set_ghost(c2d_gpu_ctx* ctx, uint32_t shape, int ghost);
 /* Registry::moveEntity(id, Translation) per shape (Registry.hpp:434-453 -> translateDynamicShape /
  * translateBulletShape 214-231 -> DynamicBVH::moveProxy 386-417): tight box shifted, bullets sweep
  * combine(old, new), fat-leaf rule, previous transform captured for bullets, translation += d. */

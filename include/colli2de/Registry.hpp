@@ -251,6 +251,9 @@ class Registry
     // result buffer (or, for EntityIds that are not 4 trivially-copyable bytes, in an internal vector), valid until
     // the next query on this Registry.
     std::span<const EntityCollision> getCollidingPairsView();
+    // Multi-GPU slabs: marks a shape as the halo copy of a shape owned by another rank's Registry (see
+    // c2d_gpu_shape_set_ghost in c2d_gpu.h for the owner rule that keeps the union of the ranks' results duplicate free).
+    void setShapeGhost(ShapeId shapeId, bool isGhost = true) { check(c2d_gpu_shape_set_ghost(mCtx, shapeId, isGhost ? 1 : 0)); }
     // Counters and CUDA-event timings of the last getCollidingPairs() / rayCast().
     const c2d_gpu_stats& lastQueryStats() const { return mStats; }
     // Runs the pipeline but leaves the records on the device; returns the number of colliding pairs.

@@ -763,6 +763,7 @@ typedef struct
     uint64_t category, mask;
     uint32_t entity;      /* entity slot */
     int active, alive;
+    int ghost;            /* multi-GPU halo copy (extension, see include/c2d_gpu.h c2d_gpu_shape_set_ghost) */
 } inst_t;
 
 typedef struct { uint32_t eA, eB, sA, sB; manifold_t m; } pairrec_t;   /* 84 bytes */
@@ -935,6 +936,10 @@ void rn_remove_entities(rn_ctx* c, uint32_t n, const uint32_t* ids) /* Registry.
         --c->live;
     }
 }
+void rn_set_ghost(rn_ctx* c, uint32_t n, const uint32_t* ids, const uint8_t* ghost)
+{
+    for (uint32_t i = 0; i < n; ++i) c->shapes[ids[i]].ghost = ghost[i] != 0;
+}
 void rn_set_active(rn_ctx* c, uint32_t n, const uint32_t* ids, const uint8_t* active) /* Registry.hpp:353-358 */
 {
     for (uint32_t i = 0; i < n; ++i) c->shapes[ids[i]].active = active[i] != 0;
@@ -1074,6 +1079,12 @@ static void narrow_phase(rn_ctx* c, uint32_t sa, uint32_t sb)
     const entity_t *ea = &c->ents[A->entity], *eb = &c->ents[B->entity];
     if (A->entity == B->entity) return;
     if (!A->active || !B->active) return;
+    if (A->ghost || B->ghost)
+    {
+        /* owner rule: shape A of a cross-tree pair, the shape of the entity with the smaller id of a same-tree pair */
+        const inst_t* owner = (ea->body != eb->body || ea->id < eb->id) ? A : B;
+        if (owner->ghost) return;
+    }
     manifold_t m;
     memset(&m, 0, sizeof(m));
     int have;

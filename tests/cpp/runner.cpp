@@ -125,6 +125,7 @@ struct IRegistry
     virtual uint64_t countPairsDevice(double* seconds) = 0;
     virtual uint64_t pairsView(double* seconds, const void** records) = 0;
     virtual void* native() const = 0;
+    virtual void setGhost(ShapeId s, bool g) = 0;
     virtual void stats(double* out16) const = 0;
     virtual int stage(uint32_t n, const uint32_t* ids, const float* dxy) = 0;
     virtual void applyStaged(int handle) = 0;
@@ -228,6 +229,10 @@ struct RegistryHolder final : IRegistry
         return firstHitImpl(r, mask, out);
     }
 #if defined(RN_BACKEND_B200)
+    void setGhost(ShapeId s, bool g) override
+    {
+        reg.setShapeGhost(s, g);
+    }
     uint64_t pairsView(double* seconds, const void** records) override
     {
         const auto t0 = std::chrono::steady_clock::now();
@@ -289,6 +294,10 @@ struct RegistryHolder final : IRegistry
 #else
     std::vector<std::pair<std::vector<uint32_t>, std::vector<Translation>>> staged;
     std::vector<typename Reg::EntityCollision> viewStorage;
+    void setGhost(ShapeId, bool) override
+    {
+        throw std::runtime_error("ghost shapes are an extension of the B200 build");
+    }
     uint64_t pairsView(double* seconds, const void** records) override
     {
         const auto t0 = std::chrono::steady_clock::now();
@@ -648,6 +657,14 @@ uint64_t rn_get_colliding_pairs_view(rn_ctx* ctx, double* seconds, const void** 
     return ctx->reg->pairsView(seconds, records);
     RN_CATCH(ctx)
     return 0;
+}
+
+void rn_set_ghost(rn_ctx* ctx, uint32_t n, const uint32_t* shape_ids, const uint8_t* ghost)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+        ctx->reg->setGhost(shape_ids[i], ghost[i] != 0);
+    RN_CATCH(ctx)
 }
 
 void* rn_native_context(rn_ctx* ctx)

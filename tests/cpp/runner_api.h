@@ -85,6 +85,9 @@ void rn_first_hit_raycast(rn_ctx*, uint32_t n, const float* ray4, const uint8_t*
  * result buffer; reference: getCollidingPairs() into a kept vector).  *records stays valid until the next query. */
 uint64_t rn_get_colliding_pairs_view(rn_ctx*, double* seconds, const void** records);
 
+/* Multi-GPU halo copies (extension; B200 and the C oracle): see c2d_gpu_shape_set_ghost in include/c2d_gpu.h. */
+void rn_set_ghost(rn_ctx*, uint32_t n, const uint32_t* shape_ids, const uint8_t* ghost);
+
 /* B200 only: the c2d_gpu_ctx* behind the Registry (Registry::nativeContext); NULL elsewhere. */
 void* rn_native_context(rn_ctx*);
 

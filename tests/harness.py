@@ -127,6 +127,7 @@ def load(name: str) -> C.CDLL:
         "rn_count_colliding_pairs_device": (u64, [vp, pd]),
         "rn_query_stats": (None, [vp, pd]),
         "rn_native_context": (vp, [vp]),
+        "rn_set_ghost": (None, [vp, u32, pu32, pu8]),
         "rn_get_colliding_pairs_view": (u64, [vp, pd, C.POINTER(vp)]),
         "rn_get_collisions": (u64, [vp, u32]),
         "rn_are_colliding": (None, [vp, u32, pu32, pu32, pu8]),
@@ -230,6 +231,11 @@ class Backend:
     def set_active(self, shape_ids, active):
         s, a = _u32(shape_ids), _u8(active)
         self.lib.rn_set_active(self.ctx, len(s), _p(s, C.c_uint32), _p(a, C.c_uint8))
+        self._check()
+
+    def set_ghost(self, shape_ids, ghost):
+        s, g = _u32(shape_ids), _u8(ghost)
+        self.lib.rn_set_ghost(self.ctx, len(s), _p(s, C.c_uint32), _p(g, C.c_uint8))
         self._check()
 
     def move_translate(self, ids, dxy):

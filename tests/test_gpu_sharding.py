@@ -1,0 +1,80 @@
+"""GPU: the multi-GPU decompositions on ONE device (ranks emulated as separate contexts, run one after the other):
+  * strong: every rank mirrors the scene and owns a Morton-rank slab of the query leaves (c2d_gpu_set_shard);
+  * weak: every rank holds only its spatial slab plus halo copies (c2d_gpu_shape_set_ghost + the owner rule).
+In both the union of the ranks' pair lists must equal the single-registry result, each pair exactly once."""
+import numpy as np
+import pytest
+
+from colli2de_b200 import capi, scenes, sharding
+from tests import harness as H, parity as P
+
+pytestmark = pytest.mark.gpu
+
+SUBJECT = "b200"
+
+
+def _entity_keys(p):
+    a = np.minimum(p["entityA"], p["entityB"]).astype(np.uint64)
+    b = np.maximum(p["entityA"], p["entityB"]).astype(np.uint64)
+    return np.sort(a << np.uint64(32) | b)
+
+
+def _scene():
+    sc = scenes.mixed_scene(30000, 3000, 800.0, seed=19, clustered=True)
+    sc["ent_body"][::35] = 2
+    return sc
+
+
+def _moves(sc, frames=3):
+    rng = scenes.LCG(5)
+    return [scenes.jitter(rng, len(sc["ent_id"]), 0.6) for _ in range(frames)]
+
+
+@pytest.mark.parametrize("method,world", [(0, 2), (0, 5), (1, 3)])
+def test_strong_query_slabs(method, world):
+    sc = _scene()
+    movable = sc["ent_body"] != 0
+    full = H.Backend(SUBJECT, method, 24)
+    scenes.populate(full, sc)
+    ranks = []
+    for r in range(world):
+        b = H.Backend(SUBJECT, method, 24)
+        scenes.populate(b, sc)
+        capi.set_shard(b.native_context(), r, world)
+        ranks.append(b)
+    for d in _moves(sc):
+        for b in [full] + ranks:
+            b.move_translate(sc["ent_id"][movable], d[movable])
+        want = P.sort_pairs(full.get_colliding_pairs())
+        parts = [b.get_colliding_pairs() for b in ranks]
+        assert all(len(p) > 0 for p in parts)
+        got = P.sort_pairs(np.concatenate(parts))
+        assert got.tobytes() == want.tobytes()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_weak_spatial_slabs_with_ghosts(world):
+    sc = _scene()
+    x = sc["ent_xf3"][:, 0]
+    full = H.Backend(SUBJECT)
+    scenes.populate(full, sc)
+    ranks = []
+    for r in range(world):
+        owned, ghost = sharding.slab_selection(x, r, world, margin=40.0)
+        local = np.nonzero(owned | ghost)[0]
+        b = H.Backend(SUBJECT)
+        ids = scenes.populate(b, {k: v[local] for k, v in sc.items()})
+        b.set_ghost(ids[ghost[local]], np.ones(int(ghost[local].sum()), np.uint8))
+        ranks.append((b, local))
+        assert 0.8 * len(x) / world < owned.sum() < 1.2 * len(x) / world  # balanced despite the clustering
+    movable = sc["ent_body"] != 0
+    for d in _moves(sc):
+        full.move_translate(sc["ent_id"][movable], d[movable])
+        for b, local in ranks:
+            m = movable[local]
+            b.move_translate(sc["ent_id"][local][m], d[local][m])
+        want = _entity_keys(full.get_colliding_pairs())
+        got = np.sort(np.concatenate([_entity_keys(b.get_colliding_pairs()) for b, _ in ranks]))
+        assert len(np.unique(got)) == len(got), "a pair was reported by two ranks"
+        assert np.array_equal(want, got)
+        assert len(want) > 5000

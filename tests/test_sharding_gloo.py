@@ -57,3 +57,52 @@ def test_slab_bounds_partition():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _ghost_worker(rank, world, port, out_dir):
+    """Weak-scaling decomposition: each rank holds ONLY its slab + halo copies; the owner rule must make the union of
+    the ranks' results equal to the single-registry result, each pair once."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = scenes.mixed_scene(4000, 400, 300.0, seed=15, clustered=True)
+    sc["ent_body"][::30] = 2
+    x = sc["ent_xf3"][:, 0]
+    owned, ghost = sharding.slab_selection(x, rank, world, margin=40.0)
+    local = np.nonzero(owned | ghost)[0]
+    sub = {k: v[local] for k, v in sc.items()}
+    b = H.Backend("oracle")
+    ids = scenes.populate(b, sub)  # entity ids stay global, shape ids are local
+    b.set_ghost(ids[ghost[local]], np.ones(int(ghost[local].sum()), np.uint8))
+    rng = scenes.LCG(3)
+    for frame in range(3):
+        d = scenes.jitter(rng, len(sc["ent_id"]), 0.6)  # every rank can generate any shape's move (replicated input)
+        movable = sc["ent_body"][local] != 0
+        b.move_translate(sc["ent_id"][local][movable], d[local][movable])
+    mine = b.get_colliding_pairs()
+    keys = np.stack([np.minimum(mine["entityA"], mine["entityB"]), np.maximum(mine["entityA"], mine["entityB"])], 1)
+    gathered = sharding.gather_records(np.ascontiguousarray(keys).view([("a", "<u4"), ("b", "<u4")]).ravel(), dst=0)
+    if rank == 0:
+        full = H.Backend("oracle")
+        scenes.populate(full, sc)
+        rng = scenes.LCG(3)
+        for frame in range(3):
+            d = scenes.jitter(rng, len(sc["ent_id"]), 0.6)
+            movable = sc["ent_body"] != 0
+            full.move_translate(sc["ent_id"][movable], d[movable])
+        fp = full.get_colliding_pairs()
+        fk = np.stack([np.minimum(fp["entityA"], fp["entityB"]), np.maximum(fp["entityA"], fp["entityB"])], 1)
+        want = np.sort(fk[:, 0].astype(np.uint64) << np.uint64(32) | fk[:, 1])
+        got = np.sort(gathered["a"].astype(np.uint64) << np.uint64(32) | gathered["b"])
+        assert len(got) == len(np.unique(got)), "a pair was reported by two ranks"
+        assert np.array_equal(want, got), (len(want), len(got))
+        assert len(want) > 1000
+        open(os.path.join(out_dir, "ok"), "w").write(str(len(want)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not H.available("oracle"), reason="needs oracle/libc2d_oracle.so")
+@pytest.mark.parametrize("world", [2, 3])
+def test_slabs_with_ghosts_and_owner_rule(tmp_path, world):
+    port = _free_port()
+    mp.spawn(_ghost_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert os.path.exists(tmp_path / "ok")
