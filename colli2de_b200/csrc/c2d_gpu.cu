@@ -401,7 +401,14 @@ void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)
     const uint32_t hi = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * (ctx->shardRank + 1) / ctx->shardWorld);
     if (hi <= lo)
         return;
-    C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+    // few queries (bullets, whose swept leaves overlap hundreds of boxes): one WARP per query leaf
+    if (static_cast<uint64_t>(hi - lo) * 32 <= 148ull * 2048 * 4)
+        C2D_TIMED(ctx, SELF ? "k_traverse_warp<self>" : "k_traverse_warp<cross>",
+                  k_traverse_warp<SELF><<<blocks_for(static_cast<size_t>(hi - lo) * 32, 128), 128, 0, ctx->stream>>>(
+                      q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
+                      static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount));
+    else
+        C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
         q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
         static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount));
     ++ctx->launches;

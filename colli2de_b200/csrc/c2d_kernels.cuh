@@ -468,6 +468,155 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Warp-per-query variant for SMALL query sets with large boxes (bullets: the leaf is a swept, displacement-fattened
+// box that overlaps hundreds of leaves).  One thread per query would leave the GPU idle (10 k threads) and serialise
+// each long traversal; here the 32 lanes of a warp pop up to 32 nodes of a shared stack per step and push / emit
+// through ballots.  Same candidate semantics as k_traverse.
+constexpr int kWarpStack = 1024;
+
+template <bool SELF>
+__device__ void lane_dfs(int root, uint32_t i, uint32_t qs, const float4& qb, uint64_t qc,
+                         const uint32_t* __restrict__ tSorted, const BvhNode* __restrict__ nodes,
+                         uint2* __restrict__ out, uint32_t capacity, uint32_t* counter)
+{
+    // overflow fallback of k_traverse_warp: a plain per-lane stack traversal of one subtree
+    int stack[64];
+    int sp = 0;
+    int node = root;
+    while (true)
+    {
+        const BvhNode N = nodes[node];
+        bool hitL = box_overlap(qb, N.boxL) && (qc & N.catL) != 0 && (!SELF || N.lastL > static_cast<int>(i));
+        bool hitR = box_overlap(qb, N.boxR) && (qc & N.catR) != 0 && (!SELF || N.lastR > static_cast<int>(i));
+        if (hitL && N.left < 0)
+        {
+            const uint32_t ts = tSorted[~N.left];
+            emit_pair(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts, out, capacity, counter);
+            hitL = false;
+        }
+        if (hitR && N.right < 0)
+        {
+            const uint32_t ts = tSorted[~N.right];
+            emit_pair(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts, out, capacity, counter);
+            hitR = false;
+        }
+        if (hitL)
+        {
+            if (hitR && sp < 64)
+                stack[sp++] = N.right;
+            node = N.left;
+        }
+        else if (hitR)
+            node = N.right;
+        else
+        {
+            if (sp == 0)
+                break;
+            node = stack[--sp];
+        }
+    }
+}
+
+template <bool SELF>
+__global__ void __launch_bounds__(128)
+    k_traverse_warp(const uint32_t* __restrict__ qSorted, uint32_t qn, uint32_t qLo, uint32_t qHi,
+                    const uint32_t* __restrict__ tSorted, uint32_t tn, const BvhNode* __restrict__ nodes,
+                    const float4* __restrict__ fat, const uint64_t* __restrict__ category, uint2* __restrict__ out,
+                    uint32_t capacity, uint32_t* counter)
+{
+    __shared__ int stacks[4][kWarpStack];
+    const int lane = threadIdx.x & 31;
+    int* stack = stacks[threadIdx.x >> 5];
+    const uint32_t i = qLo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (i >= qHi || i >= qn || tn == 0)
+        return; // warp-uniform
+    const uint32_t qs = qSorted[i];
+    const float4 qb = fat[qs];
+    const uint64_t qc = category[qs];
+    if (tn == 1)
+    {
+        if (!SELF && lane == 0)
+        {
+            const uint32_t ts = tSorted[0];
+            if ((qc & category[ts]) != 0 && box_overlap(qb, fat[ts]))
+                emit_pair(qs, ts, out, capacity, counter);
+        }
+        return;
+    }
+    const uint32_t ltMask = (1u << lane) - 1u;
+    int size = 1;
+    if (lane == 0)
+        stack[0] = 0;
+    __syncwarp();
+    while (size > 0)
+    {
+        const int take = size < 32 ? size : 32;
+        const int node = lane < take ? stack[size - 1 - lane] : -1;
+        __syncwarp();
+        size -= take;
+        bool pushL = false, pushR = false, emitL = false, emitR = false;
+        int4 links = make_int4(0, 0, 0, 0);
+        if (node >= 0)
+        {
+            const float4* np = reinterpret_cast<const float4*>(nodes + node);
+            const float4 boxL = __ldg(np);
+            const float4 boxR = __ldg(np + 1);
+            links = __ldg(reinterpret_cast<const int4*>(np + 2));
+            const ulonglong2 cats = __ldg(reinterpret_cast<const ulonglong2*>(np + 3));
+            const bool hitL = box_overlap(qb, boxL) && (qc & cats.x) != 0 && (!SELF || links.z > static_cast<int>(i));
+            const bool hitR = box_overlap(qb, boxR) && (qc & cats.y) != 0 && (!SELF || links.w > static_cast<int>(i));
+            emitL = hitL && links.x < 0;
+            emitR = hitR && links.y < 0;
+            pushL = hitL && links.x >= 0;
+            pushR = hitR && links.y >= 0;
+        }
+        // pushes
+        const uint32_t bL = __ballot_sync(0xffffffffu, pushL), bR = __ballot_sync(0xffffffffu, pushR);
+        const int posL = size + __popc(bL & ltMask);
+        const int posR = size + __popc(bL) + __popc(bR & ltMask);
+        if (pushL)
+        {
+            if (posL < kWarpStack)
+                stack[posL] = links.x;
+            else
+                lane_dfs<SELF>(links.x, i, qs, qb, qc, tSorted, nodes, out, capacity, counter);
+        }
+        if (pushR)
+        {
+            if (posR < kWarpStack)
+                stack[posR] = links.y;
+            else
+                lane_dfs<SELF>(links.y, i, qs, qb, qc, tSorted, nodes, out, capacity, counter);
+        }
+        size = min(size + __popc(bL) + __popc(bR), kWarpStack);
+        // emits: one atomic per step
+        const uint32_t eL = __ballot_sync(0xffffffffu, emitL), eR = __ballot_sync(0xffffffffu, emitR);
+        const int total = __popc(eL) + __popc(eR);
+        if (total)
+        {
+            uint32_t base = 0;
+            if (lane == 0)
+                base = atomicAdd(counter, static_cast<uint32_t>(total));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (emitL)
+            {
+                const uint32_t idx = base + __popc(eL & ltMask);
+                const uint32_t ts = tSorted[~links.x];
+                if (idx < capacity)
+                    out[idx] = make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
+            }
+            if (emitR)
+            {
+                const uint32_t idx = base + __popc(eL) + __popc(eR & ltMask);
+                const uint32_t ts = tSorted[~links.y];
+                if (idx < capacity)
+                    out[idx] = make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // K6 — narrowphase.  Candidates are binned by (mode, core) so a warp runs one code path:
 //   mode 0 collide (no bullet), 1 sweep with A = bullet moving, 2 sweep with both moving
@@ -606,6 +755,40 @@ __device__ __forceinline__ void load_motions(const ShapeArrays& s, uint2 p, cons
         moB = motion_fixed(c.xb);
 }
 
+// Conservative early-out for translation-only sweeps.  The broadphase candidate comes from the bullet's LEAF box
+// (swept and displacement-fattened, DynamicBVH.hpp:386-400) which is far larger than the region the shape really
+// sweeps.  For delta-angle == 0 every sample transform of sweepHelper is a translation between start and end with the
+// same (libm) sin/cos, so the shape stays inside the union of its AABBs at the two ends (plus its AABB at the STORED
+// start transform, used by the t = 0 test).  If that union and the other body's are further apart than a margin that
+// dwarfs the narrowphase slack (1e-6) and float rounding, none of the <= 19 boolean tests can succeed: skipping them
+// cannot change the result.
+__device__ __forceinline__ Box swept_extent(const ShapeRef& S, const Motion& mo)
+{
+    Box b = compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, mo.start);
+    if (mo.moving)
+    {
+        XF t = mo.start;
+        t.s = mo.csin;
+        t.c = mo.ccos;
+        b = box_combine(b, compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, t));
+        t.tx = mo.start.tx + mo.dx;
+        t.ty = mo.start.ty + mo.dy;
+        b = box_combine(b, compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, t));
+    }
+    return b;
+}
+
+__device__ __forceinline__ bool sweep_cannot_hit(const ShapeRef& A, const Motion& ma, const ShapeRef& B, const Motion& mb)
+{
+    if ((ma.moving && ma.da != 0.0f) || (mb.moving && mb.da != 0.0f))
+        return false; // rotating sweep: no cheap bound
+    const Box a = swept_extent(A, ma), b = swept_extent(B, mb);
+    const float scale = fmaxf(fmaxf(fmaxf(fabsf(a.minx), fabsf(a.maxx)), fmaxf(fabsf(a.miny), fabsf(a.maxy))),
+                              fmaxf(fmaxf(fabsf(b.minx), fabsf(b.maxx)), fmaxf(fabsf(b.miny), fabsf(b.maxy))));
+    const float margin = 1e-3f + 1e-5f * scale;
+    return a.minx > b.maxx + margin || b.minx > a.maxx + margin || a.miny > b.maxy + margin || b.miny > a.maxy + margin;
+}
+
 // Phase 1: boolean test (areColliding / sweepHelper) of every binned candidate; hits are compacted per bin
 // into hits[binOffset[bin] + k] = (shapeA, shapeB, fraction bits, 0).  Most candidates are rejected here by
 // the cheap early-out paths, so the expensive manifold code of phase 2 runs on full warps of real hits.
@@ -642,7 +825,7 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
                 {
                     Motion moA, moB;
                     load_motions(s, p, c, moA, moB);
-                    hit = sweep_search(c.A, moA, c.B, moB, fraction);
+                    hit = !sweep_cannot_hit(c.A, moA, c.B, moB) && sweep_search(c.A, moA, c.B, moB, fraction);
                 }
             }
         }
