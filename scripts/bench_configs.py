@@ -66,7 +66,7 @@ def main():
     ray4, inf = scenes.rays(args.rays, 9535.0, seed=13)
     b = H.Backend("b200")
     scenes.populate(b, sc)
-    b.raycast(ray4[:1000], inf[:1000])
+    b.raycast(ray4, inf)  # first call sizes the device / pinned buffers (GBs of cudaMalloc / cudaHostAlloc)
     t = time.perf_counter()
     off, hits, sec = b.raycast(ray4, inf, with_time=True)
     st = b.stats()
