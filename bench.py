@@ -122,9 +122,11 @@ def local_slab(scene, rank: int, world: int):
     """Sub-scene of spatial slab `rank` (owned shapes + halo copies) and the mask of the halo copies in it."""
     from colli2de_b200 import sharding
 
-    owned, ghost = sharding.slab_selection(scene["ent_xf3"][:, 0], rank, world, HALO_MARGIN)
+    x = scene["ent_xf3"][:, 0]
+    owned, ghost = sharding.slab_selection(x, rank, world, HALO_MARGIN)
+    exports = sharding.slab_exports(x, rank, world, HALO_MARGIN)
     local = np.nonzero(owned | ghost)[0]
-    return {k: v[local] for k, v in scene.items()}, ghost[local], local
+    return {k: v[local] for k, v in scene.items()}, ghost[local], local, owned, exports
 
 
 def measured_peak_gbs():
@@ -198,7 +200,12 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     n_total_dyn, n_total_sta = n_dyn, n_sta
     if weak:
         # this rank's spatial slab of the N-times larger world + halo copies of the neighbours' boundary shapes
-        scene, ghost_mask, local_index = local_slab(scene, rank, world)
+        world_body = scene["ent_body"]
+        world_ids = scene["ent_id"]
+        scene, ghost_mask, local_index, owned_mask, export_mask = local_slab(scene, rank, world)
+        owned_dyn = world_ids[owned_mask & (world_body != 0)]
+        export_dyn = world_ids[export_mask & (world_body != 0)]
+        ghost_dyn = np.sort(scene["ent_id"][ghost_mask & (scene["ent_body"] != 0)])
         ids = scenes.populate(b, scene)
         b.set_ghost(ids[ghost_mask], np.ones(int(ghost_mask.sum()), np.uint8))
         dyn = scene["ent_id"][scene["ent_body"] != 0]
@@ -280,14 +287,27 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     from colli2de_b200 import sharding
     from tests.harness import PAIR_DTYPE
 
-    e2e_times, move_times, e2e_pairs, h2d, d2h, gather_times = [], [], 0, 0.0, 0.0, []
+    e2e_times, move_times, e2e_pairs, h2d, d2h, gather_times, exchange_times = [], [], 0, 0.0, 0.0, [], []
     pinned = {}
     for f in range(2 + K):
-        d = frame_moves()
+        tx = 0.0
+        if weak:
+            # the exchange step of the decomposition: a rank decides the moves of the entities it OWNS; the moves of its
+            # boundary entities reach the neighbours' halo copies through one NCCL all-gather per frame
+            d_world = scenes.jitter(rng, n_total_dyn, 0.5)
+            dist.barrier()
+            tx = time.perf_counter()
+            all_ids, all_d = sharding.exchange_boundary_moves(export_dyn, d_world[export_dyn])
+            take = np.isin(all_ids, ghost_dyn)
+            step_ids = np.concatenate([owned_dyn, all_ids[take]])
+            d = np.concatenate([d_world[owned_dyn], all_d[take]])
+            tx = time.perf_counter() - tx
+        else:
+            step_ids, d = dyn, frame_moves()
         if f == 2:
             barrier()
         tm = time.perf_counter()
-        b.move_translate(dyn, d)
+        b.move_translate(step_ids, d)
         tm = time.perf_counter() - tm
         sec = C.c_double(0.0)
         tg = 0.0
@@ -311,8 +331,9 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                 assert len(recs) == total and len(np.unique(recs[key])) == total, "duplicate pair across slabs"
         if f >= 2:
             st = b.stats()
-            e2e_times.append(sec.value + tg)
+            e2e_times.append(sec.value + tg + tx)
             gather_times.append(tg)
+            exchange_times.append(tx)
             move_times.append(tm)
             e2e_pairs += n
             h2d += st["h2d_bytes"]
@@ -394,7 +415,9 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                    "parallelism": ("single GPU" if world == 1 else
                                    f"weak: {world} x the workload ({n_total_dyn} dynamic + {n_total_sta} static in one world), one "
                                    f"equal-population x-slab per GPU + halo copies within {HALO_MARGIN} units, owner rule, no "
-                                   f"data-path collective (rank 0 slab: {n_dyn} dynamic + {n_sta} static incl. halo)" if weak else
+                                   f"data-path collective in the device-resident loop (moves are a function of the global id); the e2e "
+                                   f"loop exchanges the boundary moves with one NCCL all-gather per frame "
+                                   f"(rank 0 slab: {n_dyn} dynamic + {n_sta} static incl. halo)" if weak else
                                    f"strong: fixed workload mirrored on {world} GPUs, query leaves sharded by Morton-rank slab"),
                    "l2": "inputs larger than L2 (fresh 16 MB move batch per frame; ~255 MB shape state + ~100 MB "
                          "sort/tree buffers rewritten every frame vs 126 MB L2), no explicit flush",
@@ -406,6 +429,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                 "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "moves_host_ms": 1e3 * float(np.mean(move_times)),
                 "gather_ms_per_step": 1e3 * float(np.mean(gather_times)) if gather_times else 0.0,
+                "boundary_exchange_ms_per_step": 1e3 * float(np.mean(exchange_times)) if exchange_times else 0.0,
                 "view_ms_per_step": 1e3 * float(np.mean(view_times)),
                 "view_call": "Registry::getCollidingPairsView() (extension: span over the pinned result buffer)",
                 "call": "c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity"},

@@ -120,3 +120,40 @@ def slab_selection(x: np.ndarray, rank: int, world: int, margin: float):
     owned = (x >= lo) & (x < hi)
     near = (x >= lo - margin) & (x < hi + margin)
     return owned, near & ~owned
+
+
+def slab_exports(x: np.ndarray, rank: int, world: int, margin: float) -> np.ndarray:
+    """Mask of the shapes OWNED by `rank` that some neighbour holds as a halo copy (within `margin` of a slab edge)."""
+    e = slab_edges(x, world)
+    lo, hi = e[rank], e[rank + 1]
+    owned = (x >= lo) & (x < hi)
+    return owned & ((x < lo + margin) | (x >= hi - margin))
+
+
+def exchange_boundary_moves(ids: np.ndarray, dxy: np.ndarray):
+    """The per-frame exchange step of the slab decomposition: every rank contributes the moves (entity id, dx, dy) of
+    its boundary shapes; everybody receives all of them (one all-gather of the counts, one padded all-gather of the
+    12-byte records — NCCL over NVLink on GPUs, gloo in the CPU tests) and applies the ones that match its halo copies.
+    Returns (ids, dxy) of all ranks concatenated."""
+    ids = np.ascontiguousarray(ids, np.uint32)
+    dxy = np.ascontiguousarray(dxy, np.float32).reshape(-1, 2)
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return ids, dxy
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = _device()
+    counts = torch.zeros(world, dtype=torch.int64, device=dev)
+    counts[rank] = len(ids)
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    host_counts = counts.cpu().tolist()
+    width = max(max(host_counts), 1)
+    send = torch.zeros((width, 3), dtype=torch.float32, device=dev)
+    if len(ids):
+        rec = np.empty((len(ids), 3), np.float32)
+        rec[:, 0] = ids.view(np.float32)  # bit pattern of the id travels in a float lane
+        rec[:, 1:] = dxy
+        send[: len(ids)] = torch.from_numpy(rec).to(dev)
+    recv = [torch.empty_like(send) for _ in range(world)]
+    dist.all_gather(recv, send)
+    parts = [recv[r][: host_counts[r]].cpu().numpy() for r in range(world)]
+    allrec = np.concatenate(parts) if parts else np.zeros((0, 3), np.float32)
+    return np.ascontiguousarray(allrec[:, 0]).view(np.uint32), np.ascontiguousarray(allrec[:, 1:])

@@ -106,3 +106,56 @@ def test_slabs_with_ghosts_and_owner_rule(tmp_path, world):
     port = _free_port()
     mp.spawn(_ghost_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     assert os.path.exists(tmp_path / "ok")
+
+
+def _exchange_worker(rank, world, port, out_dir):
+    """Like _ghost_worker, but a rank only KNOWS the moves of the shapes it owns: the halo copies receive theirs through
+    sharding.exchange_boundary_moves (the data-path collective of the decomposition)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sc = scenes.mixed_scene(4000, 400, 300.0, seed=25, clustered=False)
+    x = sc["ent_xf3"][:, 0]
+    margin = 40.0
+    owned, ghost = sharding.slab_selection(x, rank, world, margin)
+    exports = sharding.slab_exports(x, rank, world, margin)
+    local = np.nonzero(owned | ghost)[0]
+    b = H.Backend("oracle")
+    ids = scenes.populate(b, {k: v[local] for k, v in sc.items()})
+    b.set_ghost(ids[ghost[local]], np.ones(int(ghost[local].sum()), np.uint8))
+    movable = sc["ent_body"] != 0
+    ghost_ids = np.sort(sc["ent_id"][ghost & movable])
+    for frame in range(3):
+        # moves of the OWNED shapes only (a private stream per rank would do; here a function of id and frame)
+        mine = sc["ent_id"][owned & movable]
+        r = np.random.default_rng(1000 * frame + 7)
+        d_all = r.uniform(-0.6, 0.6, (len(sc["ent_id"]), 2)).astype(np.float32)  # stands in for "what the owner decided"
+        d_mine = d_all[mine]
+        exp = sc["ent_id"][exports & movable]
+        all_ids, all_d = sharding.exchange_boundary_moves(exp, d_all[exp])
+        sel = np.isin(all_ids, ghost_ids)
+        assert set(all_ids[sel].tolist()) == set(ghost_ids.tolist()), "a halo copy did not receive its move"
+        b.move_translate(np.concatenate([mine, all_ids[sel]]), np.concatenate([d_mine, all_d[sel]]))
+    p = b.get_colliding_pairs()
+    keys = np.stack([np.minimum(p["entityA"], p["entityB"]), np.maximum(p["entityA"], p["entityB"])], 1)
+    gathered = sharding.gather_records(np.ascontiguousarray(keys).view([("a", "<u4"), ("b", "<u4")]).ravel(), dst=0)
+    if rank == 0:
+        full = H.Backend("oracle")
+        scenes.populate(full, sc)
+        for frame in range(3):
+            r = np.random.default_rng(1000 * frame + 7)
+            d_all = r.uniform(-0.6, 0.6, (len(sc["ent_id"]), 2)).astype(np.float32)
+            full.move_translate(sc["ent_id"][movable], d_all[movable])
+        fp = full.get_colliding_pairs()
+        fk = np.stack([np.minimum(fp["entityA"], fp["entityB"]), np.maximum(fp["entityA"], fp["entityB"])], 1)
+        want = np.sort(fk[:, 0].astype(np.uint64) << np.uint64(32) | fk[:, 1])
+        got = np.sort(gathered["a"].astype(np.uint64) << np.uint64(32) | gathered["b"])
+        assert np.array_equal(want, got), (len(want), len(got))
+        open(os.path.join(out_dir, "ok"), "w").write(str(len(want)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(not H.available("oracle"), reason="needs oracle/libc2d_oracle.so")
+def test_boundary_move_exchange_world2(tmp_path):
+    port = _free_port()
+    mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok")
