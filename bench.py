@@ -299,9 +299,9 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
             tx = time.perf_counter()
             all_ids, all_d = sharding.exchange_boundary_moves(export_dyn, d_world[export_dyn])
             take = np.isin(all_ids, ghost_dyn)
+            tx = time.perf_counter() - tx
             step_ids = np.concatenate([owned_dyn, all_ids[take]])
             d = np.concatenate([d_world[owned_dyn], all_d[take]])
-            tx = time.perf_counter() - tx
         else:
             step_ids, d = dyn, frame_moves()
         if f == 2:
