@@ -80,13 +80,6 @@ struct __align__(16) BvhNode
 };
 static_assert(sizeof(BvhNode) == 64, "node is one 64-byte record");
 
-struct Tree
-{
-    uint32_t n;          // leaves
-    uint32_t* sorted;    // shape id by Morton rank
-    BvhNode* nodes;      // n - 1 internal nodes, root = 0
-};
-
 // frame scratch: [0..3] bounds tree 0 (minx, miny, maxx, maxy as ordered uints), [4..7] tree 1, [8..11] tree 2,
 // then counters.
 struct FrameScratch
