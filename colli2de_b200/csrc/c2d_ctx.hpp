@@ -4,9 +4,12 @@
 #include "c2d_internal.hpp"
 
 #include "../../include/c2d_gpu.h"
+#include "c2d_copy_pool.hpp"
 
+#include <chrono>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -216,6 +219,15 @@ struct c2d_gpu_ctx
     c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
     uint64_t lastCandidates = 0;
     uint64_t lastPairs = 0;
+    struct FrameState // one c2d_gpu_collide_begin .. c2d_gpu_collide_end bracket
+    {
+        bool open = false;
+        std::chrono::steady_clock::time_point wall0{};
+        uint32_t retries = 0;
+        uint64_t d2h = 0;
+    } frame;
+    std::unique_ptr<c2d_host::CopyPool> copyPool; // created by the first large copy-out
+    std::vector<cudaEvent_t> copyEvents;          // one per in-flight chunk of c2d_gpu_collide_fetch
     c2d_host::RayBuffers rays;
     c2d_host::GridBuffers grid;
     c2d_host::QueryBuffers query;

@@ -12,6 +12,7 @@
 #include "c2d_kernels.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -414,15 +415,59 @@ void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)
     ++ctx->launches;
 }
 
-int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRecords, uint64_t* outCount,
-                 c2d_gpu_stats* stats)
+void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats);
+
+// One attempt at traversal + narrowphase with the current pair-list capacities; everything is enqueued on the
+// stream, the frame counters follow in an asynchronous copy to the pinned FrameScratch.
+int pipeline_attempt(c2d_gpu_ctx* ctx)
 {
-    const auto wall0 = std::chrono::steady_clock::now();
+    cudaStream_t s = ctx->stream;
+    if (ctx->broadphase == C2D_BROADPHASE_GRID)
+    {
+        ProfScope ps(ctx, "grid_broadphase(extent+count+scan+fill+sort+gather+pairs)");
+        if (int rc = grid_broadphase(ctx))
+            return rc;
+    }
+    else
+    {
+        // groups in the reference's order (Registry.hpp:487-545)
+        launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC);
+        launch_traverse<true>(ctx, C2D_DYNAMIC, C2D_DYNAMIC);
+        launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
+        launch_traverse<false>(ctx, C2D_BULLET, C2D_DYNAMIC);
+        launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
+    }
+    C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+
+    const uint32_t cap = static_cast<uint32_t>(ctx->cand.capacity);
+    const uint32_t grid = 148 * 4;
+    C2D_TIMED(ctx, "k_bin_count", k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch));
+    C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
+    C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
+    C2D_TIMED(ctx, "k_narrow_filter", k_narrow_filter<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+    C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
+    C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
+    C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                     static_cast<uint32_t>(ctx->out.capacity)));
+    C2D_TIMED(ctx, "k_narrow_manifold", k_narrow_manifold<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                     static_cast<uint32_t>(ctx->out.capacity)));
+    ctx->launches += 8;
+    C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+    C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
+    ctx->frame.d2h += sizeof(FrameScratch);
+    return 0;
+}
+
+// Replays the mutation log, refreshes the trees and enqueues the first attempt; returns without waiting for the GPU.
+int pipeline_begin(c2d_gpu_ctx* ctx)
+{
+    if (ctx->frame.open)
+        return fail(ctx, "c2d_gpu_collide_begin: the previous frame was not closed with c2d_gpu_collide_end");
+    ctx->frame = c2d_gpu_ctx::FrameState{};
+    ctx->frame.wall0 = std::chrono::steady_clock::now();
     cudaStream_t s = ctx->stream;
     ctx->launches = 0;
     ctx->h2dBytes = 0;
-    uint32_t retries = 0;
-    uint64_t d2h = 0;
 
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
     if (int rc = flush(ctx))
@@ -431,8 +476,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
 
     C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
     ++ctx->launches;
-    const bool useGrid = ctx->broadphase == C2D_BROADPHASE_GRID;
-    if (!useGrid) // the grid broadphase needs no tree; rays build them on demand (ensure_trees)
+    if (ctx->broadphase != C2D_BROADPHASE_GRID) // the grid broadphase needs no tree; rays build them on demand (ensure_trees)
         for (int body = 0; body < 3; ++body)
             if (ctx->treeDirty[body])
                 if (int rc = build_tree(ctx, body))
@@ -447,45 +491,25 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
     }
     if (ctx->out.capacity == 0)
         C2D_CUDA(ctx, ctx->out.reserve(1u << 15));
+    if (int rc = pipeline_attempt(ctx))
+        return rc;
+    ctx->frame.open = true;
+    return 0;
+}
 
+// Waits for the attempt in flight; on a pair-list overflow grows the lists and re-runs traversal + narrowphase
+// (boxes and trees are unchanged).
+int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
+{
+    if (!ctx->frame.open)
+        return fail(ctx, "c2d_gpu_collide_end without c2d_gpu_collide_begin");
+    ctx->frame.open = false;
+    cudaStream_t s = ctx->stream;
     uint32_t candCount = 0, pairCount = 0;
     while (true)
     {
-        if (useGrid)
-        {
-            ProfScope ps(ctx, "grid_broadphase(extent+count+scan+fill+sort+gather+pairs)");
-            if (int rc = grid_broadphase(ctx))
-                return rc;
-        }
-        else
-        {
-        // groups in the reference's order (Registry.hpp:487-545)
-        launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC);
-        launch_traverse<true>(ctx, C2D_DYNAMIC, C2D_DYNAMIC);
-        launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
-        launch_traverse<false>(ctx, C2D_BULLET, C2D_DYNAMIC);
-        launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
-        }
-        C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
-
-        const uint32_t cap = static_cast<uint32_t>(ctx->cand.capacity);
-        const uint32_t grid = 148 * 4;
-        C2D_TIMED(ctx, "k_bin_count", k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch));
-        C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
-        C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
-        C2D_TIMED(ctx, "k_narrow_filter", k_narrow_filter<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
-        C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
-        C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
-        C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
-                                         static_cast<uint32_t>(ctx->out.capacity)));
-        C2D_TIMED(ctx, "k_narrow_manifold", k_narrow_manifold<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
-                                         static_cast<uint32_t>(ctx->out.capacity)));
-        ctx->launches += 8;
-        C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
         C2D_CUDA(ctx, cudaStreamSynchronize(s));
         C2D_CUDA(ctx, cudaGetLastError());
-        d2h += sizeof(FrameScratch);
         candCount = ctx->hScratch->candCount;
         pairCount = ctx->hScratch->outCount;
         if (ctx->hScratch->clipOverflow)
@@ -494,8 +518,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         const bool outOverflow = pairCount > ctx->out.capacity;
         if (!candOverflow && !outOverflow)
             break;
-        // pair-list overflow: grow and re-run traversal + narrowphase (boxes and trees are unchanged)
-        ++retries;
+        ++ctx->frame.retries;
         if (candOverflow)
         {
             C2D_CUDA(ctx, ctx->cand.reserve(static_cast<size_t>(candCount) + candCount / 4));
@@ -506,44 +529,69 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
             C2D_CUDA(ctx, ctx->out.reserve(static_cast<size_t>(pairCount) + pairCount / 4));
         C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
         ++ctx->launches;
+        if (int rc = pipeline_attempt(ctx))
+            return rc;
     }
     ctx->lastCandidates = candCount;
     ctx->lastPairs = pairCount;
+    if (ctx->profiling)
+        collect_profile(ctx);
+    if (stats)
+        fill_stats(ctx, stats);
+    return 0;
+}
 
-    if (download && pairCount)
+void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
+{
+    std::memset(stats, 0, sizeof(*stats));
+    stats->shapes_alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
+    stats->candidates = ctx->lastCandidates;
+    stats->pairs = ctx->lastPairs;
+    stats->h2d_bytes = ctx->h2dBytes;
+    stats->d2h_bytes = ctx->frame.d2h;
+    stats->kernel_launches = ctx->launches;
+    stats->retries = ctx->frame.retries;
+    cudaEventElapsedTime(&stats->ms_refit, ctx->ev[0], ctx->ev[1]);
+    cudaEventElapsedTime(&stats->ms_build, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&stats->ms_broad, ctx->ev[2], ctx->ev[3]);
+    cudaEventElapsedTime(&stats->ms_narrow, ctx->ev[3], ctx->ev[4]);
+    cudaEventElapsedTime(&stats->ms_device, ctx->ev[0], ctx->ev[4]);
+    stats->ms_total =
+        std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->frame.wall0).count();
+}
+
+// Records of the last frame -> the library's pinned buffer (one copy), for the pointer-returning entry points.
+int download_records(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
+{
+    const uint64_t pairCount = ctx->lastPairs;
+    if (pairCount)
     {
         if (!ctx->hostOut.reserve(pairCount))
             return fail(ctx, "pinned host allocation failed");
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hostOut.data, ctx->out.ptr, static_cast<size_t>(pairCount) * sizeof(PairOut),
-                                      cudaMemcpyDeviceToHost, s));
-        C2D_CUDA(ctx, cudaStreamSynchronize(s));
-        d2h += static_cast<uint64_t>(pairCount) * sizeof(PairOut);
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+        C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->frame.d2h += pairCount * sizeof(PairOut);
     }
-    if (ctx->profiling)
-        collect_profile(ctx);
+    if (stats)
+        fill_stats(ctx, stats);
+    return 0;
+}
+
+int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRecords, uint64_t* outCount,
+                 c2d_gpu_stats* stats)
+{
+    if (int rc = pipeline_begin(ctx))
+        return rc;
+    if (int rc = pipeline_end(ctx, download ? nullptr : stats))
+        return rc;
+    if (download)
+        if (int rc = download_records(ctx, stats))
+            return rc;
     if (outRecords)
         *outRecords = reinterpret_cast<const c2d_pair_record*>(ctx->hostOut.data);
     if (outCount)
-        *outCount = pairCount;
-
-    if (stats)
-    {
-        std::memset(stats, 0, sizeof(*stats));
-        stats->shapes_alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
-        stats->candidates = candCount;
-        stats->pairs = pairCount;
-        stats->h2d_bytes = ctx->h2dBytes;
-        stats->d2h_bytes = d2h;
-        stats->kernel_launches = ctx->launches;
-        stats->retries = retries;
-        cudaEventElapsedTime(&stats->ms_refit, ctx->ev[0], ctx->ev[1]);
-        cudaEventElapsedTime(&stats->ms_build, ctx->ev[1], ctx->ev[2]);
-        cudaEventElapsedTime(&stats->ms_broad, ctx->ev[2], ctx->ev[3]);
-        cudaEventElapsedTime(&stats->ms_narrow, ctx->ev[3], ctx->ev[4]);
-        cudaEventElapsedTime(&stats->ms_device, ctx->ev[0], ctx->ev[4]);
-        stats->ms_total =
-            std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
-    }
+        *outCount = ctx->lastPairs;
     return 0;
 }
 
@@ -619,6 +667,9 @@ void c2d_gpu_destroy(c2d_gpu_ctx* ctx)
         if (ev)
             cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->eventPool)
+        cudaEventDestroy(ev);
+    ctx->copyPool.reset();
+    for (cudaEvent_t ev : ctx->copyEvents)
         cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->logConsumed)
         if (ev)
@@ -905,6 +956,149 @@ int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats*
 {
     cudaSetDevice(ctx->device);
     return run_pipeline(ctx, false, nullptr, out_count, stats);
+}
+
+// ---- copy-out straight into caller storage -------------------------------------------------------------------
+namespace
+{
+constexpr uint64_t kPoolThresholdBytes = 4ull << 20; // smaller results: one copy on the calling thread
+constexpr uint64_t kFetchChunkBytes = 1ull << 20;
+constexpr uint32_t kMaxFetchChunks = 64;
+
+c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
+{
+    if (!ctx->copyPool)
+    {
+        unsigned helpers = std::thread::hardware_concurrency() / 2;
+        helpers = helpers > 8 ? 8 : helpers;
+        if (const char* env = std::getenv("C2D_GPU_COPY_THREADS"))
+            helpers = static_cast<unsigned>(std::strtoul(env, nullptr, 10));
+        helpers = helpers > 64 ? 64 : helpers;
+        ctx->copyPool = std::make_unique<c2d_host::CopyPool>(helpers > 0 ? helpers - 1 : 0); // the caller is a worker too
+    }
+    return ctx->copyPool.get();
+}
+} // namespace
+
+int c2d_gpu_collide_begin(c2d_gpu_ctx* ctx)
+{
+    cudaSetDevice(ctx->device);
+    if (ctx->frame.open) // abandoned bracket (the caller unwound between begin and end): drain it
+    {
+        if (ctx->copyPool)
+            ctx->copyPool->wait();
+        cudaStreamSynchronize(ctx->stream);
+        ctx->frame.open = false;
+    }
+    return pipeline_begin(ctx);
+}
+
+int c2d_gpu_prefault(c2d_gpu_ctx* ctx, void* dst, uint64_t bytes)
+{
+    if (!dst || bytes < kPoolThresholdBytes)
+        return 0;
+    c2d_host::CopyPool* pool = copy_pool(ctx);
+    const unsigned workers = pool->helpers();
+    if (workers == 0)
+        return 0;
+    const uint64_t page = 4096;
+    char* base = static_cast<char*>(dst);
+    pool->launch([=](unsigned index) {
+        // interleaved 2 MB stripes: neighbouring threads fault neighbouring regions (and whole huge pages with THP)
+        const uint64_t stripe = 2ull << 20;
+        for (uint64_t lo = static_cast<uint64_t>(index) * stripe; lo < bytes; lo += static_cast<uint64_t>(workers) * stripe)
+        {
+            const uint64_t hi = lo + stripe < bytes ? lo + stripe : bytes;
+            for (uint64_t off = lo; off < hi; off += page)
+                *reinterpret_cast<volatile char*>(base + off) = 0;
+        }
+    });
+    return 0;
+}
+
+int c2d_gpu_collide_end(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* stats)
+{
+    cudaSetDevice(ctx->device);
+    const int rc = pipeline_end(ctx, stats);
+    if (ctx->copyPool)
+        ctx->copyPool->wait(); // the pre-fault job must not outlive the caller's storage
+    if (out_count)
+        *out_count = rc ? 0 : ctx->lastPairs;
+    return rc;
+}
+
+int c2d_gpu_collide_fetch(c2d_gpu_ctx* ctx, c2d_pair_record* dst, uint64_t count, c2d_gpu_stats* stats)
+{
+    cudaSetDevice(ctx->device);
+    if (count > ctx->lastPairs)
+        return fail(ctx, "c2d_gpu_collide_fetch: more records requested than the last frame produced");
+    if (count && !dst)
+        return fail(ctx, "c2d_gpu_collide_fetch: dst is NULL");
+    const uint64_t total = count * sizeof(PairOut);
+    if (count && !ctx->hostOut.reserve(count))
+        return fail(ctx, "pinned host allocation failed");
+    cudaStream_t s = ctx->stream;
+    const char* src = reinterpret_cast<const char*>(ctx->out.ptr);
+    char* stage = reinterpret_cast<char*>(ctx->hostOut.data);
+    char* out = reinterpret_cast<char*>(dst);
+    if (total < kPoolThresholdBytes)
+    {
+        if (total)
+        {
+            C2D_CUDA(ctx, cudaMemcpyAsync(stage, src, total, cudaMemcpyDeviceToHost, s));
+            C2D_CUDA(ctx, cudaStreamSynchronize(s));
+            std::memcpy(out, stage, total);
+        }
+    }
+    else
+    {
+        c2d_host::CopyPool* pool = copy_pool(ctx);
+        pool->wait();
+        uint64_t chunk = kFetchChunkBytes;
+        if ((total + chunk - 1) / chunk > kMaxFetchChunks)
+            chunk = ((total + kMaxFetchChunks - 1) / kMaxFetchChunks + 4095) & ~4095ull;
+        const uint32_t chunks = static_cast<uint32_t>((total + chunk - 1) / chunk);
+        while (ctx->copyEvents.size() < chunks)
+        {
+            cudaEvent_t ev = nullptr;
+            C2D_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->copyEvents.push_back(ev);
+        }
+        for (uint32_t k = 0; k < chunks; ++k)
+        {
+            const uint64_t off = k * chunk, len = off + chunk < total ? chunk : total - off;
+            C2D_CUDA(ctx, cudaMemcpyAsync(stage + off, src + off, len, cudaMemcpyDeviceToHost, s));
+            C2D_CUDA(ctx, cudaEventRecord(ctx->copyEvents[k], s));
+        }
+        // every worker (helpers + this thread) takes the next chunk whose device-to-host copy has landed
+        std::atomic<uint32_t> next{0};
+        std::atomic<int> cudaErr{0};
+        const int device = ctx->device;
+        const cudaEvent_t* events = ctx->copyEvents.data();
+        auto work = [&, device, events, chunk, chunks, total, stage, out](unsigned) {
+            cudaSetDevice(device);
+            for (uint32_t k = next.fetch_add(1); k < chunks; k = next.fetch_add(1))
+            {
+                const cudaError_t e = cudaEventSynchronize(events[k]);
+                if (e != cudaSuccess)
+                {
+                    cudaErr.store(static_cast<int>(e));
+                    continue;
+                }
+                const uint64_t off = k * chunk, len = off + chunk < total ? chunk : total - off;
+                std::memcpy(out + off, stage + off, len);
+            }
+        };
+        pool->launch(work);
+        work(pool->helpers());
+        pool->wait();
+        if (cudaErr.load())
+            return fail(ctx, std::string("c2d_gpu_collide_fetch: ") + cudaGetErrorString(static_cast<cudaError_t>(cudaErr.load())));
+    }
+    ctx->frame.d2h += total;
+    if (stats)
+        fill_stats(ctx, stats);
+    return 0;
 }
 
 #ifndef C2D_HAVE_RAYS

@@ -183,6 +183,19 @@ int c2d_gpu_collide(c2d_gpu_ctx* ctx, const c2d_pair_record** out_records, uint6
 /* Same pipeline, results left on the device (no D2H of records): used to time the device-resident path.
  * out_count receives the number of colliding pairs. */
 int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* stats);
+/* The copy-out of Registry::getCollidingPairs (Registry.hpp:464-549 returns a fresh std::vector, reserved from the
+ * previous frame's count, 467 and 547) without the pinned-buffer detour of c2d_gpu_collide:
+ *   c2d_gpu_collide_begin   replays the log and enqueues the whole pipeline, returns while the GPU works;
+ *   c2d_gpu_prefault        (optional) helper threads touch the pages of the storage the caller reserved meanwhile;
+ *   c2d_gpu_collide_end     waits (re-running on a pair-list overflow), joins the pre-fault, reports the count;
+ *   c2d_gpu_collide_fetch   copies `count` (<= the frame's count) records into `dst`: chunked device-to-host copies
+ *                           into pinned staging, moved on to `dst` by the helper threads as they land.
+ * Helper threads: min(8, hardware threads / 2) including the caller, C2D_GPU_COPY_THREADS overrides (1 = none);
+ * results below 4 MB are copied by the calling thread alone.  Records are the same as c2d_gpu_collide's. */
+int c2d_gpu_collide_begin(c2d_gpu_ctx* ctx);
+int c2d_gpu_prefault(c2d_gpu_ctx* ctx, void* dst, uint64_t bytes);
+int c2d_gpu_collide_end(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* stats);
+int c2d_gpu_collide_fetch(c2d_gpu_ctx* ctx, c2d_pair_record* dst, uint64_t count, c2d_gpu_stats* stats);
 /* Device address and count of the 84-byte records produced by the last c2d_gpu_collide / c2d_gpu_collide_device
  * (valid until the next query on ctx): lets a multi-GPU driver gather the per-slab results GPU-to-GPU (NCCL)
  * without a host round trip. */

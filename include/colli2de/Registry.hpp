@@ -46,6 +46,41 @@
 namespace c2d
 {
 
+namespace detail
+{
+// Sets the size of a vector of trivially copyable records WITHOUT value-initialising the new elements, so that the
+// library's copy threads can fill the storage in parallel (std::vector::resize would zero 35 MB on one thread first).
+// Only libstdc++'s layout is known here; elsewhere the caller falls back to the single-threaded range constructor.
+#if defined(__GLIBCXX__) && !defined(_GLIBCXX_DEBUG) && !defined(_GLIBCXX_SANITIZE_VECTOR)
+inline constexpr bool kHasUninitializedResize = true;
+template <typename T>
+struct VectorSizeAccess : std::vector<T>
+{
+    static void set(std::vector<T>& v, std::size_t n)
+    {
+        static_assert(std::is_trivially_copyable_v<T> && std::is_trivially_destructible_v<T>);
+        static_assert(sizeof(VectorSizeAccess) == sizeof(std::vector<T>));
+        auto& self = static_cast<VectorSizeAccess&>(v);
+        self._M_impl._M_finish = self._M_impl._M_start + n;
+    }
+};
+template <typename T>
+void resizeUninitialized(std::vector<T>& v, std::size_t n)
+{
+    if (v.capacity() < n)
+        v.reserve(n);
+    VectorSizeAccess<T>::set(v, n);
+}
+#else
+inline constexpr bool kHasUninitializedResize = false;
+template <typename T>
+void resizeUninitialized(std::vector<T>& v, std::size_t n)
+{
+    v.resize(n);
+}
+#endif
+} // namespace detail
+
 using ShapeId = uint32_t;
 using BitMaskType = uint64_t;
 
@@ -187,6 +222,7 @@ class Registry
             mPendingApplies = std::move(o.mPendingApplies);
             mStructureEpoch = o.mStructureEpoch;
             mStats = o.mStats;
+            mPreviousAllCollisionsCount = o.mPreviousAllCollisionsCount;
         }
         return *this;
     }
@@ -447,6 +483,7 @@ class Registry
     std::vector<ShapeId> mFreeShapeIds;
     mutable c2d_gpu_stats mStats{};
     std::vector<EntityCollision> mViewStorage;
+    uint32_t mPreviousAllCollisionsCount = 1024; // reference Registry.hpp:168
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -706,6 +743,7 @@ template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::clear()
 {
     check(c2d_gpu_clear(mCtx));
+    mPreviousAllCollisionsCount = 1000; // reference Registry.hpp:1202
     ++mStructureEpoch;
     mStaged.clear();
     mPendingApplies.clear();
@@ -723,10 +761,30 @@ void Registry<EntityId, Method>::clear()
 template <typename EntityId, PartitioningMethod Method>
 std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<EntityId, Method>::getCollidingPairs()
 {
-    const c2d_pair_record* records = nullptr;
-    uint64_t count = 0;
-    check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
-    return toCollisions(records, count);
+    if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
+                  std::is_trivially_copyable_v<EntityCollision> && detail::kHasUninitializedResize)
+    {
+        // the device writes EntityCollision records: reserve the result from the previous frame's count like the
+        // reference does (Registry.hpp:467, 547), let the library touch its pages while the GPU works, then have
+        // the records copied straight into it
+        check(c2d_gpu_collide_begin(mCtx));
+        std::vector<EntityCollision> out;
+        out.reserve(static_cast<std::size_t>(mPreviousAllCollisionsCount) + mPreviousAllCollisionsCount / 8 + 64);
+        check(c2d_gpu_prefault(mCtx, static_cast<void*>(out.data()), out.capacity() * sizeof(EntityCollision)));
+        uint64_t count = 0;
+        check(c2d_gpu_collide_end(mCtx, &count, &mStats));
+        detail::resizeUninitialized(out, count);
+        check(c2d_gpu_collide_fetch(mCtx, reinterpret_cast<c2d_pair_record*>(out.data()), count, &mStats));
+        mPreviousAllCollisionsCount = static_cast<uint32_t>(count);
+        return out;
+    }
+    else
+    {
+        const c2d_pair_record* records = nullptr;
+        uint64_t count = 0;
+        check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
+        return toCollisions(records, count);
+    }
 }
 
 template <typename EntityId, PartitioningMethod Method>
