@@ -113,6 +113,16 @@ struct RayBuffers
     DevBuf<unsigned char> smallHeaders;
     PinnedVec<unsigned char> hostSmall;
     PinnedVec<c2d_hit_record> hostReorder;
+    DevBuf<c2d_hit_record> packed; // hits in block-completion order, before the gather into ray order
+    // rays with more leaf-box hits than the shared-memory kernel holds (global-scratch path)
+    DevBuf<unsigned char> heavy;
+    DevBuf<uint32_t> heavyIndex;
+    PinnedVec<unsigned char> hostHeavy;
+    // result of the last run: on the host (latency path) or ray-ordered per chunk on the device
+    bool resultOnHost = true;
+    uint64_t totalHits = 0;
+    std::vector<std::unique_ptr<DevBuf<c2d_hit_record>>> chunkOut;
+    std::vector<uint64_t> chunkCount;
 };
 
 // buffers of the uniform-grid broadphase (c2d_grid.cu)
@@ -227,7 +237,8 @@ struct c2d_gpu_ctx
         uint64_t d2h = 0;
     } frame;
     std::unique_ptr<c2d_host::CopyPool> copyPool; // created by the first large copy-out
-    std::vector<cudaEvent_t> copyEvents;          // one per in-flight chunk of c2d_gpu_collide_fetch
+    std::vector<cudaEvent_t> copyEvents;          // one per in-flight chunk of copy_out
+    c2d_host::PinnedVec<unsigned char> copyStage; // pinned staging of copy_out (one 64 MB wave)
     c2d_host::RayBuffers rays;
     c2d_host::GridBuffers grid;
     c2d_host::QueryBuffers query;
@@ -249,6 +260,8 @@ int fail(c2d_gpu_ctx* ctx, const std::string& msg);
 int flush(c2d_gpu_ctx* ctx);        // replays the mutation log
 int ensure_trees(c2d_gpu_ctx* ctx); // flush + rebuild of the dirty trees (launches k_frame_init first)
 int upload_members(c2d_gpu_ctx* ctx, int body); // host member list of one tree -> device, if it changed
+int copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, uint64_t bytes); // device -> pageable, threaded
+int copy_host(c2d_gpu_ctx* ctx, const void* srcHost, void* dstHost, uint64_t bytes);  // pinned -> pageable, threaded
 // c2d_rays.cu
 int exclusive_scan_u32(c2d_gpu_ctx* ctx, uint32_t* data, uint32_t n, DevBuf<uint32_t>& sums, uint32_t* dTotal);
 // c2d_grid.cu

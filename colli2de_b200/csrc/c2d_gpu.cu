@@ -958,12 +958,14 @@ int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats*
     return run_pipeline(ctx, false, nullptr, out_count, stats);
 }
 
+} // extern "C"
+
 // ---- copy-out straight into caller storage -------------------------------------------------------------------
 namespace
 {
 constexpr uint64_t kPoolThresholdBytes = 4ull << 20; // smaller results: one copy on the calling thread
 constexpr uint64_t kFetchChunkBytes = 1ull << 20;
-constexpr uint32_t kMaxFetchChunks = 64;
+constexpr uint32_t kFetchWaveChunks = 64; // pinned staging = 64 MB, refilled wave by wave
 
 c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
 {
@@ -979,6 +981,105 @@ c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
     return ctx->copyPool.get();
 }
 } // namespace
+
+// Device memory -> caller (pageable) memory: device-to-host copies of 1 MB chunks into pinned staging, moved on to
+// `dst` by the helper threads (and this thread) as each chunk lands.
+int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, uint64_t total)
+{
+    if (!total)
+        return 0;
+    cudaStream_t s = ctx->stream;
+    const char* src = static_cast<const char*>(srcDevice);
+    char* out = static_cast<char*>(dstHost);
+    if (total < kPoolThresholdBytes)
+    {
+        if (!ctx->copyStage.reserve(total))
+            return fail(ctx, "pinned host allocation failed");
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->copyStage.data, src, total, cudaMemcpyDeviceToHost, s));
+        C2D_CUDA(ctx, cudaStreamSynchronize(s));
+        std::memcpy(out, ctx->copyStage.data, total);
+        return 0;
+    }
+    c2d_host::CopyPool* pool = copy_pool(ctx);
+    pool->wait();
+    const uint64_t waveBytes = kFetchWaveChunks * kFetchChunkBytes;
+    if (!ctx->copyStage.reserve(waveBytes))
+        return fail(ctx, "pinned host allocation failed");
+    while (ctx->copyEvents.size() < kFetchWaveChunks)
+    {
+        cudaEvent_t ev = nullptr;
+        C2D_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->copyEvents.push_back(ev);
+    }
+    char* stage = reinterpret_cast<char*>(ctx->copyStage.data);
+    const int device = ctx->device;
+    const cudaEvent_t* events = ctx->copyEvents.data();
+    for (uint64_t wave = 0; wave < total; wave += waveBytes)
+    {
+        const uint64_t bytes = wave + waveBytes < total ? waveBytes : total - wave;
+        const uint32_t chunks = static_cast<uint32_t>((bytes + kFetchChunkBytes - 1) / kFetchChunkBytes);
+        for (uint32_t k = 0; k < chunks; ++k)
+        {
+            const uint64_t off = k * kFetchChunkBytes, len = off + kFetchChunkBytes < bytes ? kFetchChunkBytes : bytes - off;
+            C2D_CUDA(ctx, cudaMemcpyAsync(stage + off, src + wave + off, len, cudaMemcpyDeviceToHost, s));
+            C2D_CUDA(ctx, cudaEventRecord(ctx->copyEvents[k], s));
+        }
+        // every worker (helpers + this thread) takes the next chunk whose device-to-host copy has landed
+        std::atomic<uint32_t> next{0};
+        std::atomic<int> cudaErr{0};
+        char* dst = out + wave;
+        auto work = [&next, &cudaErr, device, events, chunks, bytes, stage, dst](unsigned) {
+            cudaSetDevice(device);
+            for (uint32_t k = next.fetch_add(1); k < chunks; k = next.fetch_add(1))
+            {
+                const cudaError_t e = cudaEventSynchronize(events[k]);
+                if (e != cudaSuccess)
+                {
+                    cudaErr.store(static_cast<int>(e));
+                    continue;
+                }
+                const uint64_t off = k * kFetchChunkBytes, len = off + kFetchChunkBytes < bytes ? kFetchChunkBytes : bytes - off;
+                std::memcpy(dst + off, stage + off, len);
+            }
+        };
+        pool->launch(work);
+        work(pool->helpers());
+        pool->wait();
+        if (cudaErr.load())
+            return fail(ctx, std::string("copy_out: ") + cudaGetErrorString(static_cast<cudaError_t>(cudaErr.load())));
+    }
+    return 0;
+}
+
+// Host memory (the library's pinned result buffer) -> caller memory, split over the helper threads.
+int c2d_host::copy_host(c2d_gpu_ctx* ctx, const void* srcHost, void* dstHost, uint64_t total)
+{
+    if (total < kPoolThresholdBytes)
+    {
+        if (total)
+            std::memcpy(dstHost, srcHost, total);
+        return 0;
+    }
+    c2d_host::CopyPool* pool = copy_pool(ctx);
+    pool->wait();
+    const uint32_t chunks = static_cast<uint32_t>((total + kFetchChunkBytes - 1) / kFetchChunkBytes);
+    std::atomic<uint32_t> next{0};
+    const char* src = static_cast<const char*>(srcHost);
+    char* dst = static_cast<char*>(dstHost);
+    auto work = [&next, chunks, total, src, dst](unsigned) {
+        for (uint32_t k = next.fetch_add(1); k < chunks; k = next.fetch_add(1))
+        {
+            const uint64_t off = k * kFetchChunkBytes, len = off + kFetchChunkBytes < total ? kFetchChunkBytes : total - off;
+            std::memcpy(dst + off, src + off, len);
+        }
+    };
+    pool->launch(work);
+    work(pool->helpers());
+    pool->wait();
+    return 0;
+}
+
+extern "C" {
 
 int c2d_gpu_collide_begin(c2d_gpu_ctx* ctx)
 {
@@ -1035,66 +1136,8 @@ int c2d_gpu_collide_fetch(c2d_gpu_ctx* ctx, c2d_pair_record* dst, uint64_t count
     if (count && !dst)
         return fail(ctx, "c2d_gpu_collide_fetch: dst is NULL");
     const uint64_t total = count * sizeof(PairOut);
-    if (count && !ctx->hostOut.reserve(count))
-        return fail(ctx, "pinned host allocation failed");
-    cudaStream_t s = ctx->stream;
-    const char* src = reinterpret_cast<const char*>(ctx->out.ptr);
-    char* stage = reinterpret_cast<char*>(ctx->hostOut.data);
-    char* out = reinterpret_cast<char*>(dst);
-    if (total < kPoolThresholdBytes)
-    {
-        if (total)
-        {
-            C2D_CUDA(ctx, cudaMemcpyAsync(stage, src, total, cudaMemcpyDeviceToHost, s));
-            C2D_CUDA(ctx, cudaStreamSynchronize(s));
-            std::memcpy(out, stage, total);
-        }
-    }
-    else
-    {
-        c2d_host::CopyPool* pool = copy_pool(ctx);
-        pool->wait();
-        uint64_t chunk = kFetchChunkBytes;
-        if ((total + chunk - 1) / chunk > kMaxFetchChunks)
-            chunk = ((total + kMaxFetchChunks - 1) / kMaxFetchChunks + 4095) & ~4095ull;
-        const uint32_t chunks = static_cast<uint32_t>((total + chunk - 1) / chunk);
-        while (ctx->copyEvents.size() < chunks)
-        {
-            cudaEvent_t ev = nullptr;
-            C2D_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-            ctx->copyEvents.push_back(ev);
-        }
-        for (uint32_t k = 0; k < chunks; ++k)
-        {
-            const uint64_t off = k * chunk, len = off + chunk < total ? chunk : total - off;
-            C2D_CUDA(ctx, cudaMemcpyAsync(stage + off, src + off, len, cudaMemcpyDeviceToHost, s));
-            C2D_CUDA(ctx, cudaEventRecord(ctx->copyEvents[k], s));
-        }
-        // every worker (helpers + this thread) takes the next chunk whose device-to-host copy has landed
-        std::atomic<uint32_t> next{0};
-        std::atomic<int> cudaErr{0};
-        const int device = ctx->device;
-        const cudaEvent_t* events = ctx->copyEvents.data();
-        auto work = [&, device, events, chunk, chunks, total, stage, out](unsigned) {
-            cudaSetDevice(device);
-            for (uint32_t k = next.fetch_add(1); k < chunks; k = next.fetch_add(1))
-            {
-                const cudaError_t e = cudaEventSynchronize(events[k]);
-                if (e != cudaSuccess)
-                {
-                    cudaErr.store(static_cast<int>(e));
-                    continue;
-                }
-                const uint64_t off = k * chunk, len = off + chunk < total ? chunk : total - off;
-                std::memcpy(out + off, stage + off, len);
-            }
-        };
-        pool->launch(work);
-        work(pool->helpers());
-        pool->wait();
-        if (cudaErr.load())
-            return fail(ctx, std::string("c2d_gpu_collide_fetch: ") + cudaGetErrorString(static_cast<cudaError_t>(cudaErr.load())));
-    }
+    if (int rc = c2d_host::copy_out(ctx, ctx->out.ptr, dst, total))
+        return rc;
     ctx->frame.d2h += total;
     if (stats)
         fill_stats(ctx, stats);

@@ -207,6 +207,13 @@ int c2d_gpu_device_records(c2d_gpu_ctx* ctx, const void** out_device_ptr, uint64
 int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, const c2d_hit_record** out_hits,
                     const uint64_t** out_offsets, c2d_gpu_stats* stats);
 
+/* c2d_gpu_raycast / c2d_gpu_raycast_first with the copy-out of c2d_gpu_collide_fetch: _begin runs the batch and
+ * reports the total number of hits and the per-ray offsets (context-owned, n + 1 entries); _fetch copies all `count`
+ * (== that total) records into caller storage with the helper threads, straight from the device. */
+int c2d_gpu_raycast_begin(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, int first_hit_only, uint64_t* out_total,
+                          const uint64_t** out_offsets, c2d_gpu_stats* stats);
+int c2d_gpu_raycast_fetch(c2d_gpu_ctx* ctx, c2d_hit_record* dst, uint64_t count, c2d_gpu_stats* stats);
+
 /* Registry::firstHitRayCast x n (Registry.hpp:866-1048): at most one hit per ray (out_offsets[i+1] - out_offsets[i]
  * is 0 or 1) — the narrow hit with the smallest entry time found by the reference's search, which walks each tree's
  * leaf-box hits in (entry, exit) order and stops 5 candidates after its last improvement. */

@@ -31,6 +31,7 @@
 
 #include <bit>
 #include <cmath>
+#include <cstddef>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -58,7 +59,8 @@ struct VectorSizeAccess : std::vector<T>
 {
     static void set(std::vector<T>& v, std::size_t n)
     {
-        static_assert(std::is_trivially_copyable_v<T> && std::is_trivially_destructible_v<T>);
+        // bit-copyable in practice: std::pair members make RaycastHit formally non-trivially-copyable (assignment)
+        static_assert(std::is_trivially_copy_constructible_v<T> && std::is_trivially_destructible_v<T>);
         static_assert(sizeof(VectorSizeAccess) == sizeof(std::vector<T>));
         auto& self = static_cast<VectorSizeAccess&>(v);
         self._M_impl._M_finish = self._M_impl._M_start + n;
@@ -946,14 +948,34 @@ typename Registry<EntityId, Method>::RayBatchResult Registry<EntityId, Method>::
     packed.reserve(queries.size());
     for (const RayQuery& q : queries)
         packed.push_back(c2d_ray{q.start.x, q.start.y, q.second.x, q.second.y, q.maskBits, q.infinite ? 1u : 0u, 0u});
-    const c2d_hit_record* hits = nullptr;
-    const uint64_t* offsets = nullptr;
-    check(c2d_gpu_raycast(mCtx, static_cast<uint32_t>(packed.size()), packed.data(), &hits, &offsets, &mStats));
     RayBatchResult out;
-    out.offsets.assign(offsets, offsets + packed.size() + 1);
-    out.hits.reserve(out.offsets.back());
-    for (uint64_t k = 0; k < out.offsets.back(); ++k)
-        out.hits.push_back(toRayHit(hits[k]));
+    if constexpr (kDirectTag && sizeof(RayHit) == sizeof(c2d_hit_record) && std::is_standard_layout_v<RayHit> &&
+                  std::is_trivially_copy_constructible_v<RayHit> && std::is_trivially_destructible_v<RayHit> &&
+                  detail::kHasUninitializedResize)
+    {
+        // the device writes RaycastHit records ({entity, shape}, entry, exit, entryTime, exitTime): they are copied
+        // straight from the device into the result vector by the library's copy threads
+        static_assert(offsetof(RayHit, entry) == offsetof(c2d_hit_record, entry) &&
+                      offsetof(RayHit, exit) == offsetof(c2d_hit_record, exit) &&
+                      offsetof(RayHit, entryTime) == offsetof(c2d_hit_record, entryTime) &&
+                      offsetof(RayHit, exitTime) == offsetof(c2d_hit_record, exitTime));
+        uint64_t total = 0;
+        const uint64_t* offsets = nullptr;
+        check(c2d_gpu_raycast_begin(mCtx, static_cast<uint32_t>(packed.size()), packed.data(), 0, &total, &offsets, &mStats));
+        out.offsets.assign(offsets, offsets + packed.size() + 1);
+        detail::resizeUninitialized(out.hits, total);
+        check(c2d_gpu_raycast_fetch(mCtx, reinterpret_cast<c2d_hit_record*>(out.hits.data()), total, &mStats));
+    }
+    else
+    {
+        const c2d_hit_record* hits = nullptr;
+        const uint64_t* offsets = nullptr;
+        check(c2d_gpu_raycast(mCtx, static_cast<uint32_t>(packed.size()), packed.data(), &hits, &offsets, &mStats));
+        out.offsets.assign(offsets, offsets + packed.size() + 1);
+        out.hits.reserve(out.offsets.back());
+        for (uint64_t k = 0; k < out.offsets.back(); ++k)
+            out.hits.push_back(toRayHit(hits[k]));
+    }
     return out;
 }
 

@@ -1312,6 +1312,16 @@ uint64_t rn_get_collisions(rn_ctx* c, uint32_t id)
     }
     return c->npairs;
 }
+uint64_t rn_get_collisions_many(rn_ctx* c, uint32_t n, const uint32_t* ids, double* seconds)
+{
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    uint64_t total = 0;
+    for (uint32_t i = 0; i < n; ++i) total += rn_get_collisions(c, ids[i]);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+    return total;
+}
 
 /* ---- areColliding, Registry.hpp:748-864; boolSweepHelper Collision.hpp:126-149, 215-244 -------------------- */
 static int sweep_bool(const shape_t* a, const motion_t* ma, const shape_t* b, const motion_t* mb)

@@ -133,8 +133,9 @@ struct IRegistry
     virtual void rayCast(Ray r, uint64_t mask, std::vector<HitRec>& out) const = 0;
     virtual void rayCast(InfiniteRay r, uint64_t mask, std::vector<HitRec>& out) const = 0;
     // all rays in one call where the backend has a batched entry point; false -> the caller loops rayCast()
+    // *apiSeconds = the time of the Registry call alone (packing the queries and unpacking the result are test plumbing)
     virtual bool rayCastBatch(uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks,
-                              uint64_t* offsets, std::vector<HitRec>& out) const = 0;
+                              uint64_t* offsets, std::vector<HitRec>& out, double* apiSeconds) const = 0;
     virtual size_t size() const = 0;
     virtual void clear() = 0;
 };
@@ -243,17 +244,21 @@ struct RegistryHolder final : IRegistry
         return view.size();
     }
     bool rayCastBatch(uint32_t n, const float* ray4, const uint8_t* infinite, const uint64_t* masks, uint64_t* offsets,
-                      std::vector<HitRec>& out) const override
+                      std::vector<HitRec>& out, double* apiSeconds) const override
     {
         std::vector<typename Reg::RayQuery> q(n);
         for (uint32_t i = 0; i < n; ++i)
             q[i] = typename Reg::RayQuery{Vec2{ray4[4 * i], ray4[4 * i + 1]}, Vec2{ray4[4 * i + 2], ray4[4 * i + 3]},
                                           masks ? masks[i] : ~0ull, infinite && infinite[i]};
+        const auto t0 = std::chrono::steady_clock::now();
         const auto res = reg.rayCastBatch(std::span<const typename Reg::RayQuery>(q));
+        if (apiSeconds)
+            *apiSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         std::copy(res.offsets.begin(), res.offsets.end(), offsets);
-        out.reserve(res.hits.size());
-        for (const auto& h : res.hits)
-            out.push_back(HitRec{h.id.first, h.id.second, {h.entry.x, h.entry.y}, {h.exit.x, h.exit.y}, h.entryTime, h.exitTime});
+        static_assert(sizeof(typename Reg::RayHit) == sizeof(HitRec));
+        out.resize(res.hits.size());
+        if (!res.hits.empty())
+            std::memcpy(static_cast<void*>(out.data()), static_cast<const void*>(res.hits.data()), res.hits.size() * sizeof(HitRec));
         return true;
     }
     void* native() const override
@@ -307,7 +312,7 @@ struct RegistryHolder final : IRegistry
         *records = viewStorage.data();
         return viewStorage.size();
     }
-    bool rayCastBatch(uint32_t, const float*, const uint8_t*, const uint64_t*, uint64_t*, std::vector<HitRec>&) const override
+    bool rayCastBatch(uint32_t, const float*, const uint8_t*, const uint64_t*, uint64_t*, std::vector<HitRec>&, double*) const override
     {
         return false;
     }
@@ -616,6 +621,23 @@ uint64_t rn_count_colliding_pairs_device(rn_ctx* ctx, double* seconds)
     return 0;
 }
 
+uint64_t rn_get_collisions_many(rn_ctx* ctx, uint32_t n, const uint32_t* ids, double* seconds)
+{
+    RN_TRY(ctx)
+    uint64_t total = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ctx->reg->getCollisions(ids[i], ctx->pairs);
+        total += ctx->pairs.size();
+    }
+    if (seconds)
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return total;
+    RN_CATCH(ctx)
+    return 0;
+}
+
 uint64_t rn_get_collisions(rn_ctx* ctx, uint32_t id)
 {
     RN_TRY(ctx)
@@ -714,12 +736,8 @@ uint64_t rn_raycast(rn_ctx* ctx, uint32_t n, const float* ray4, const uint8_t* i
     ctx->hits.clear();
     const auto t0 = std::chrono::steady_clock::now();
     const bool single = std::getenv("RN_RAYCAST_SINGLE") != nullptr; // force the one-ray-per-call API
-    if (!single && ctx->reg->rayCastBatch(n, ray4, infinite, masks, offsets, ctx->hits))
-    {
-        if (seconds)
-            *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!single && ctx->reg->rayCastBatch(n, ray4, infinite, masks, offsets, ctx->hits, seconds))
         return ctx->hits.size();
-    }
     for (uint32_t i = 0; i < n; ++i)
     {
         offsets[i] = ctx->hits.size();

@@ -75,6 +75,8 @@ void rn_release_staged(rn_ctx*, int handle);
 
 /* getCollisions(id): keeps the result like rn_get_colliding_pairs; returns the count (copy with rn_copy_pairs). */
 uint64_t rn_get_collisions(rn_ctx*, uint32_t id);
+/* getCollisions(ids[i]) looped in native code; returns the summed result sizes, *seconds = time of the loop */
+uint64_t rn_get_collisions_many(rn_ctx*, uint32_t n, const uint32_t* ids, double* seconds);
 /* areColliding(idsA[i], idsB[i]) for i < n */
 void rn_are_colliding(rn_ctx*, uint32_t n, const uint32_t* idsA, const uint32_t* idsB, uint8_t* out);
 /* firstHitRayCast() looped over n rays: out_found[i] = has_value, out_hits32[i] = the hit (zeroed when none) */

@@ -130,6 +130,7 @@ def load(name: str) -> C.CDLL:
         "rn_set_ghost": (None, [vp, u32, pu32, pu8]),
         "rn_get_colliding_pairs_view": (u64, [vp, pd, C.POINTER(vp)]),
         "rn_get_collisions": (u64, [vp, u32]),
+        "rn_get_collisions_many": (u64, [vp, u32, pu32, pd]),
         "rn_are_colliding": (None, [vp, u32, pu32, pu32, pu8]),
         "rn_first_hit_raycast": (None, [vp, u32, pf, pu8, pu64, pu8, vp]),
         "rn_stage_translations": (i32, [vp, u32, pu32, pf]),
@@ -337,6 +338,14 @@ class Backend:
         if n:
             self.lib.rn_copy_pairs(self.ctx, out.ctypes.data_as(C.c_void_p))
         return out
+
+    def get_collisions_many(self, entity_ids):
+        """getCollisions() looped natively over the ids; returns (summed result size, seconds)."""
+        ids = _u32(entity_ids)
+        sec = C.c_double(0.0)
+        total = int(self.lib.rn_get_collisions_many(self.ctx, len(ids), _p(ids, C.c_uint32), C.byref(sec)))
+        self._check()
+        return total, sec.value
 
     def are_colliding(self, ids_a, ids_b) -> np.ndarray:
         a, b = _u32(ids_a), _u32(ids_b)
