@@ -87,6 +87,19 @@ def build_api_check(force: bool = False) -> str:
     return API_CHECK
 
 
+SNAPSHOT_CHECK = os.path.join(HERE, "libc2d_snapshot_check.so")
+
+
+def build_snapshot_check(force: bool = False) -> str:
+    """tests/cpp/snapshot_check.cpp: the host-only snapshot codec (no CUDA) behind a C interface, for the CPU tests."""
+    src = os.path.join(REPO, "tests", "cpp", "snapshot_check.cpp")
+    inc = os.path.join(REPO, "include")
+    deps = [src, os.path.join(inc, "colli2de", "internal", "utils", "Snapshot.hpp")]
+    if force or not _newer(SNAPSHOT_CHECK, deps):
+        _run(["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-I" + inc, src, "-o", SNAPSHOT_CHECK])
+    return SNAPSHOT_CHECK
+
+
 def build_oracles():
     targets = ["ref"] + (["oracle"] if os.path.exists(os.path.join(REPO, "oracle", "c2d_oracle.c")) else [])
     _run(["make", "-C", os.path.join(REPO, "oracle"), *targets])
@@ -96,6 +109,7 @@ def build_all(force: bool = False):
     build_gpu_lib(force)
     build_runner(force)
     build_api_check(force)
+    build_snapshot_check(force)
     build_oracles()
 
 

@@ -1175,6 +1175,60 @@ int c2d_gpu_read_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* 
     return 0;
 }
 
+int c2d_gpu_read_shapes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, uint8_t* out_type, uint8_t* out_vertex_count,
+                        uint8_t* out_flags, uint64_t* out_category, uint64_t* out_mask, float* out_geom32)
+{
+    cudaSetDevice(ctx->device);
+    if (int rc = flush(ctx))
+        return rc;
+    if (static_cast<uint64_t>(first) + count > ctx->capacity)
+        return fail(ctx, "c2d_gpu_read_shapes: range out of bounds");
+    cudaStream_t s = ctx->stream;
+    std::vector<uint32_t> meta(count);
+    if (count)
+        C2D_CUDA(ctx, cudaMemcpyAsync(meta.data(), ctx->d.meta + first, count * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (out_category && count)
+        C2D_CUDA(ctx, cudaMemcpyAsync(out_category, ctx->d.category + first, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (out_mask && count)
+        C2D_CUDA(ctx, cudaMemcpyAsync(out_mask, ctx->d.mask + first, count * sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (out_geom32 && count)
+        C2D_CUDA(ctx, cudaMemcpyAsync(out_geom32, ctx->d.geom + static_cast<size_t>(first) * 32,
+                                      static_cast<size_t>(count) * 32 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    C2D_CUDA(ctx, cudaStreamSynchronize(s));
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        if (out_type)
+            out_type[i] = static_cast<uint8_t>(meta_type(meta[i]));
+        if (out_vertex_count)
+            out_vertex_count[i] = static_cast<uint8_t>(meta_count(meta[i]));
+        if (out_flags)
+            out_flags[i] = static_cast<uint8_t>(((meta[i] & META_ALIVE) ? 1u : 0u) | ((meta[i] & META_ACTIVE) ? 2u : 0u) |
+                                                ((meta[i] & META_GHOST) ? 4u : 0u));
+    }
+    return 0;
+}
+
+int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const float* tight4, const float* fat4)
+{
+    cudaSetDevice(ctx->device);
+    if (int rc = flush(ctx))
+        return rc;
+    if (static_cast<uint64_t>(first) + count > ctx->capacity)
+        return fail(ctx, "c2d_gpu_write_boxes: range out of bounds");
+    cudaStream_t s = ctx->stream;
+    if (tight4 && count)
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->d.tight + first, tight4, count * sizeof(float4), cudaMemcpyHostToDevice, s));
+    if (fat4 && count)
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->d.fat + first, fat4, count * sizeof(float4), cudaMemcpyHostToDevice, s));
+    C2D_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int body = 0; body < 3; ++body)
+    {
+        ctx->treeDirty[body] = true; // every leaf box may have changed: rebuild, do not just refit
+        ctx->tree[body].membershipChanged = true;
+    }
+    return 0;
+}
+
 int c2d_gpu_read_candidates(c2d_gpu_ctx* ctx, uint64_t capacity, uint32_t* out_pairs2, uint64_t* out_count)
 {
     cudaSetDevice(ctx->device);

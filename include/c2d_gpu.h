@@ -232,6 +232,16 @@ int c2d_gpu_pairs_colliding(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapeA
 /* ---- introspection (secondary oracles) --------------------------- */
 /* Tight (ShapeInstance::mBoundingBox) and fat (leaf) AABBs as (minx, miny, maxx, maxy); flushes first. */
 int c2d_gpu_read_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* out_tight4, float* out_fat4);
+/* Per-shape state for snapshots (Registry::serialize, Registry.hpp:1205-1264 / ShapeInstance::serialize 1493-1570):
+ * shape type (0 circle, 1 capsule, 2 segment, 3 polygon), polygon vertex count, flags (bit 0 alive, bit 1 active,
+ * bit 2 ghost), category / mask bits and the 32-float geometry block; any output may be NULL.  Flushes first. */
+int c2d_gpu_read_shapes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, uint8_t* out_type, uint8_t* out_vertex_count,
+                        uint8_t* out_flags, uint64_t* out_category, uint64_t* out_mask, float* out_geom32);
+/* Restores the tight (ShapeInstance::mBoundingBox) and leaf (BVHNode::mBoundingBox) boxes of a shape range, e.g. after
+ * Registry::deserialize (Registry.hpp:1266-1344) re-added the shapes of a snapshot: both boxes are HISTORY (the tight
+ * box is shifted by translations, the leaf box follows the fat-leaf rule), so they cannot be recomputed.  Either
+ * pointer may be NULL.  Flushes first; the next query rebuilds the trees. */
+int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const float* tight4, const float* fat4);
 /* Broadphase candidate pairs of the last c2d_gpu_collide call (shapeA, shapeB), unsorted. */
 int c2d_gpu_read_candidates(c2d_gpu_ctx* ctx, uint64_t capacity, uint32_t* out_pairs2, uint64_t* out_count);
 

@@ -17,7 +17,9 @@
 //   * getCollidingPairs() returns the reference's SET of collisions in an unspecified order (the reference
 //     lists five body-type groups, each sorted by (shapeA, shapeB)); same-tree pairs always come out with
 //     shapeA < shapeB (the reference's A/B for those depends on its tree topology);
-//   * serialize / deserialize / operator== are not provided;
+//   * serialize / deserialize speak the reference's binary snapshot format for PartitioningMethod::None (the trees in a
+//     written snapshot are rebuilt, see internal/utils/Snapshot.hpp); Grid snapshots throw; operator== compares the
+//     logical state (entities, shapes, boxes), not tree topology;
 //   * extensions: moveEntities(), stageMoves() / applyStagedMoves(), rayCastBatch(), lastQueryStats().
 #pragma once
 
@@ -26,6 +28,7 @@
 #include <colli2de/Shapes.hpp>
 #include <colli2de/Transform.hpp>
 #include <colli2de/internal/utils/Debug.hpp>
+#include <colli2de/internal/utils/Snapshot.hpp>
 
 #include <c2d_gpu.h>
 
@@ -35,7 +38,9 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <istream>
 #include <optional>
+#include <ostream>
 #include <set>
 #include <span>
 #include <stdexcept>
@@ -252,6 +257,13 @@ class Registry
     std::set<RayHit> rayCast(Ray ray, BitMaskType maskBits = ~0ull) const;
     std::set<RayHit> rayCast(InfiniteRay ray, BitMaskType maskBits = ~0ull) const;
 
+    // Binary snapshots in the reference's wire format (reference Registry.hpp:1205-1344), PartitioningMethod::None only.
+    void serialize(std::ostream& out) const;
+    static Registry deserialize(std::istream& in);
+    // Same logical state: entities, transforms, shapes, category / mask bits, activity, tight and leaf boxes, free ids.
+    bool operator==(const Registry& other) const;
+    bool operator!=(const Registry& other) const { return !(*this == other); }
+
     size_t size() const { return mLiveEntities; }
     void clear();
 
@@ -333,6 +345,7 @@ class Registry
         if constexpr (Method == PartitioningMethod::Grid)
             check(c2d_gpu_set_broadphase(mCtx, C2D_BROADPHASE_GRID, cellSize));
     }
+    snapshot::RegistryState<EntityId> captureState() const;
     void check(int rc) const
     {
         if (rc != 0)
@@ -977,6 +990,189 @@ typename Registry<EntityId, Method>::RayBatchResult Registry<EntityId, Method>::
             out.hits.push_back(toRayHit(hits[k]));
     }
     return out;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// snapshots (reference Registry.hpp:1205-1344)
+// ---------------------------------------------------------------------------------------------------------
+template <typename EntityId, PartitioningMethod Method>
+snapshot::RegistryState<EntityId> Registry<EntityId, Method>::captureState() const
+{
+    syncHost();
+    snapshot::RegistryState<EntityId> state;
+    const uint32_t shapeCount = static_cast<uint32_t>(mShapes.size());
+    std::vector<uint8_t> type(shapeCount), vertexCount(shapeCount), flags(shapeCount);
+    std::vector<uint64_t> category(shapeCount), mask(shapeCount);
+    std::vector<float> geom(static_cast<size_t>(shapeCount) * C2D_GEOM_FLOATS), tight(static_cast<size_t>(shapeCount) * 4),
+        fat(static_cast<size_t>(shapeCount) * 4);
+    if (shapeCount)
+    {
+        check(c2d_gpu_read_shapes(mCtx, 0, shapeCount, type.data(), vertexCount.data(), flags.data(), category.data(), mask.data(),
+                                  geom.data()));
+        check(c2d_gpu_read_boxes(mCtx, 0, shapeCount, tight.data(), fat.data()));
+    }
+    state.shapes.resize(shapeCount);
+    state.shapeEntity.resize(shapeCount);
+    for (uint32_t s = 0; s < shapeCount; ++s)
+    {
+        snapshot::ShapeState& shape = state.shapes[s];
+        shape.alive = mShapes[s].entity != kNone;
+        if (!shape.alive)
+            continue;
+        const EntityInfo& owner = mEntities[mShapes[s].entity];
+        state.shapeEntity[s] = owner.id;
+        shape.type = type[s];
+        shape.vertexCount = vertexCount[s];
+        shape.body = static_cast<uint8_t>(owner.type);
+        shape.active = (flags[s] & 2u) != 0;
+        std::memcpy(shape.geom, geom.data() + static_cast<size_t>(s) * C2D_GEOM_FLOATS, sizeof(shape.geom));
+        std::memcpy(shape.tight, tight.data() + static_cast<size_t>(s) * 4, sizeof(shape.tight));
+        std::memcpy(shape.fat, fat.data() + static_cast<size_t>(s) * 4, sizeof(shape.fat));
+        shape.category = category[s];
+        shape.mask = mask[s];
+    }
+    state.entities.reserve(mLiveEntities);
+    for (const EntityInfo& e : mEntities)
+    {
+        if (!e.alive)
+            continue;
+        snapshot::EntityState<EntityId> out;
+        out.id = e.id;
+        out.body = static_cast<uint8_t>(e.type);
+        const auto store = [](const Transform& t, float* xf) {
+            xf[0] = t.translation.x, xf[1] = t.translation.y;
+            xf[2] = t.rotation.angleRadians, xf[3] = t.rotation.sin, xf[4] = t.rotation.cos;
+        };
+        store(e.transform, out.xf);
+        out.hasPrev = e.type == BodyType::Bullet;
+        store(e.previous, out.prev);
+        for (uint32_t s = e.firstShape; s != kNone; s = mShapes[s].next)
+            out.shapeIds.push_back(s);
+        state.entities.push_back(std::move(out));
+    }
+    state.freeShapeIds = mFreeShapeIds;
+    state.previousAllCollisionsCount = mPreviousAllCollisionsCount;
+    return state;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::serialize(std::ostream& out) const
+{
+    if constexpr (Method == PartitioningMethod::Grid)
+        throw std::runtime_error("colli2de-b200: snapshots of PartitioningMethod::Grid registries are not supported");
+    else
+        snapshot::write(out, captureState());
+}
+
+template <typename EntityId, PartitioningMethod Method>
+Registry<EntityId, Method> Registry<EntityId, Method>::deserialize(std::istream& in)
+{
+    if constexpr (Method == PartitioningMethod::Grid)
+        throw std::runtime_error("colli2de-b200: snapshots of PartitioningMethod::Grid registries are not supported");
+    const snapshot::RegistryState<EntityId> state = snapshot::read<EntityId>(in);
+    Registry registry;
+    const auto load = [](const float* xf) {
+        Transform t{};
+        t.translation = Vec2{xf[0], xf[1]};
+        t.rotation.angleRadians = xf[2];
+        t.rotation.sin = xf[3];
+        t.rotation.cos = xf[4];
+        return t;
+    };
+    const uint32_t shapeCount = static_cast<uint32_t>(state.shapes.size());
+    registry.mShapes.assign(shapeCount, ShapeLink{});
+    registry.mFreeShapeIds = state.freeShapeIds;
+    registry.mPreviousAllCollisionsCount = state.previousAllCollisionsCount;
+    std::vector<uint32_t> inactive;
+    for (const snapshot::EntityState<EntityId>& e : state.entities)
+    {
+        registry.createEntity(e.id, static_cast<BodyType>(e.body), load(e.xf));
+        const uint32_t idx = registry.indexOf(e.id);
+        EntityInfo& entity = registry.mEntities[idx];
+        if (e.hasPrev)
+            entity.previous = load(e.prev);
+        const bool bullet = entity.type == BodyType::Bullet;
+        const c2d_xf cur = pack(entity.transform, bullet);
+        const c2d_xf prev = pack(entity.previous, bullet);
+        for (const uint32_t shapeId : e.shapeIds)
+        {
+            const snapshot::ShapeState& shape = state.shapes[shapeId];
+            registry.check(c2d_gpu_shape_add(registry.mCtx, shapeId, registry.tagOf(idx), shape.type, e.body, shape.vertexCount,
+                                             shape.category, shape.mask, shape.geom, &cur, &prev));
+            ShapeLink& link = registry.mShapes[shapeId];
+            link.entity = idx;
+            link.prev = entity.lastShape;
+            link.next = kNone;
+            if (entity.lastShape != kNone)
+                registry.mShapes[entity.lastShape].next = shapeId;
+            else
+                entity.firstShape = shapeId;
+            entity.lastShape = shapeId;
+            if (!shape.active)
+                inactive.push_back(shapeId);
+        }
+    }
+    // the boxes are history (translations shift the tight box, the leaf box follows the fat-leaf rule): restore them
+    if (shapeCount)
+    {
+        std::vector<float> tight(static_cast<size_t>(shapeCount) * 4), fat(static_cast<size_t>(shapeCount) * 4);
+        for (uint32_t s = 0; s < shapeCount; ++s)
+        {
+            std::memcpy(tight.data() + static_cast<size_t>(s) * 4, state.shapes[s].tight, 4 * sizeof(float));
+            std::memcpy(fat.data() + static_cast<size_t>(s) * 4, state.shapes[s].fat, 4 * sizeof(float));
+        }
+        registry.check(c2d_gpu_write_boxes(registry.mCtx, 0, shapeCount, tight.data(), fat.data()));
+    }
+    for (const uint32_t shapeId : inactive)
+        registry.check(c2d_gpu_shape_set_active(registry.mCtx, shapeId, 0));
+    return registry;
+}
+
+template <typename EntityId, PartitioningMethod Method>
+bool Registry<EntityId, Method>::operator==(const Registry& other) const
+{
+    const snapshot::RegistryState<EntityId> a = captureState(), b = other.captureState();
+    if (a.entities.size() != b.entities.size() || a.shapes.size() != b.shapes.size() || a.freeShapeIds != b.freeShapeIds)
+        return false;
+    for (uint32_t s = 0; s < a.shapes.size(); ++s)
+    {
+        const snapshot::ShapeState &x = a.shapes[s], &y = b.shapes[s];
+        if (x.alive != y.alive)
+            return false;
+        if (!x.alive)
+            continue;
+        if (!(a.shapeEntity[s] == b.shapeEntity[s]) || x.type != y.type || x.vertexCount != y.vertexCount || x.body != y.body ||
+            x.active != y.active || x.category != y.category || x.mask != y.mask ||
+            std::memcmp(x.geom, y.geom, sizeof(x.geom)) != 0 || std::memcmp(x.tight, y.tight, sizeof(x.tight)) != 0 ||
+            std::memcmp(x.fat, y.fat, sizeof(x.fat)) != 0)
+            return false;
+    }
+    // entities may sit in different slots: match them through the other registry's index
+    for (const snapshot::EntityState<EntityId>& e : a.entities)
+    {
+        const uint32_t idx = other.indexOf(e.id);
+        if (idx == kNone)
+            return false;
+        const EntityInfo& o = other.mEntities[idx];
+        const float oxf[5] = {o.transform.translation.x, o.transform.translation.y, o.transform.rotation.angleRadians,
+                              o.transform.rotation.sin, o.transform.rotation.cos};
+        const float opv[5] = {o.previous.translation.x, o.previous.translation.y, o.previous.rotation.angleRadians,
+                              o.previous.rotation.sin, o.previous.rotation.cos};
+        if (e.body != static_cast<uint8_t>(o.type) || std::memcmp(e.xf, oxf, sizeof(oxf)) != 0)
+            return false;
+        if (e.hasPrev && std::memcmp(e.prev, opv, sizeof(opv)) != 0)
+            return false;
+        uint32_t s = o.firstShape;
+        for (const uint32_t shapeId : e.shapeIds)
+        {
+            if (s != shapeId)
+                return false;
+            s = other.mShapes[s].next;
+        }
+        if (s != kNone)
+            return false;
+    }
+    return true;
 }
 
 } // namespace c2d

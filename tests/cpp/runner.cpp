@@ -17,6 +17,7 @@
 #include <malloc.h>
 #include <memory>
 #include <span>
+#include <sstream>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -138,6 +139,8 @@ struct IRegistry
                               uint64_t* offsets, std::vector<HitRec>& out, double* apiSeconds) const = 0;
     virtual size_t size() const = 0;
     virtual void clear() = 0;
+    virtual void serialize(std::string& out) const = 0;
+    virtual bool equals(const IRegistry& other) const = 0;
 };
 
 template <PartitioningMethod Method>
@@ -148,6 +151,19 @@ struct RegistryHolder final : IRegistry
 
     RegistryHolder() requires(Method == PartitioningMethod::None) = default;
     explicit RegistryHolder(uint32_t cell) requires(Method == PartitioningMethod::Grid) : reg(cell) {}
+    explicit RegistryHolder(Reg&& loaded) : reg(std::move(loaded)) {}
+
+    void serialize(std::string& out) const override
+    {
+        std::stringstream ss(std::ios::in | std::ios::out | std::ios::binary);
+        reg.serialize(ss);
+        out = ss.str();
+    }
+    bool equals(const IRegistry& other) const override
+    {
+        const auto* o = dynamic_cast<const RegistryHolder*>(&other);
+        return o != nullptr && reg == o->reg;
+    }
 
     void createEntity(uint32_t id, BodyType type, const Transform& t) override
     {
@@ -386,6 +402,7 @@ struct rn_ctx
     std::unordered_map<uint32_t, Transform> prev; // bullets only (mirrors Registry.hpp:167 by observation)
     std::vector<PairRec> pairs;
     std::vector<HitRec> hits;
+    std::string blob; // last rn_serialize
     std::string error;
 
     void notePrev(uint32_t id)
@@ -679,6 +696,63 @@ uint64_t rn_get_colliding_pairs_view(rn_ctx* ctx, double* seconds, const void** 
     return ctx->reg->pairsView(seconds, records);
     RN_CATCH(ctx)
     return 0;
+}
+
+uint64_t rn_serialize(rn_ctx* ctx)
+{
+    RN_TRY(ctx)
+    ctx->reg->serialize(ctx->blob);
+    return ctx->blob.size();
+    RN_CATCH(ctx)
+    return 0;
+}
+
+void rn_copy_blob(rn_ctx* ctx, void* out)
+{
+    if (!ctx->blob.empty())
+        std::memcpy(out, ctx->blob.data(), ctx->blob.size());
+}
+
+rn_ctx* rn_deserialize(int method, const void* bytes, uint64_t size)
+{
+    auto* ctx = new rn_ctx();
+    try
+    {
+        std::stringstream ss(std::string(static_cast<const char*>(bytes), size), std::ios::in | std::ios::out | std::ios::binary);
+        if (method == 1)
+            ctx->reg = std::make_unique<RegistryHolder<PartitioningMethod::Grid>>(
+                Registry<uint32_t, PartitioningMethod::Grid>::deserialize(ss));
+        else
+            ctx->reg = std::make_unique<RegistryHolder<PartitioningMethod::None>>(
+                Registry<uint32_t, PartitioningMethod::None>::deserialize(ss));
+    }
+    catch (const std::exception& e)
+    {
+        ctx->error = e.what();
+    }
+    return ctx;
+}
+
+/* the harness mirrors body types and bullets' previous transforms by observation (rn_ctx::body / prev): after
+ * rn_deserialize they are re-seeded from the caller's knowledge of the scene */
+void rn_seed_entities(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const uint8_t* body, const float* prev_xf5)
+{
+    RN_TRY(ctx)
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        ctx->body[ids[i]] = body[i];
+        if (body[i] == 2)
+            ctx->prev[ids[i]] = makeRawTransform(prev_xf5 + 5 * i);
+    }
+    RN_CATCH(ctx)
+}
+
+int rn_equals(rn_ctx* a, rn_ctx* b)
+{
+    RN_TRY(a)
+    return a->reg->equals(*b->reg) ? 1 : 0;
+    RN_CATCH(a)
+    return -1;
 }
 
 void rn_set_ghost(rn_ctx* ctx, uint32_t n, const uint32_t* shape_ids, const uint8_t* ghost)

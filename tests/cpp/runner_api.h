@@ -88,6 +88,13 @@ void rn_first_hit_raycast(rn_ctx*, uint32_t n, const float* ray4, const uint8_t*
 uint64_t rn_get_colliding_pairs_view(rn_ctx*, double* seconds, const void** records);
 
 /* Multi-GPU halo copies (extension; B200 and the C oracle): see c2d_gpu_shape_set_ghost in include/c2d_gpu.h. */
+/* Registry::serialize into a context-owned blob (returns its size; rn_copy_blob copies it out), Registry::deserialize
+ * into a NEW context, Registry::operator== (1 equal, 0 different, -1 error). */
+uint64_t rn_serialize(rn_ctx*);
+void rn_copy_blob(rn_ctx*, void* out);
+rn_ctx* rn_deserialize(int method, const void* bytes, uint64_t size);
+void rn_seed_entities(rn_ctx*, uint32_t n, const uint32_t* ids, const uint8_t* body, const float* prev_xf5);
+int rn_equals(rn_ctx* a, rn_ctx* b);
 void rn_set_ghost(rn_ctx*, uint32_t n, const uint32_t* shape_ids, const uint8_t* ghost);
 
 /* B200 only: the c2d_gpu_ctx* behind the Registry (Registry::nativeContext); NULL elsewhere. */

@@ -131,6 +131,11 @@ def load(name: str) -> C.CDLL:
         "rn_get_colliding_pairs_view": (u64, [vp, pd, C.POINTER(vp)]),
         "rn_get_collisions": (u64, [vp, u32]),
         "rn_get_collisions_many": (u64, [vp, u32, pu32, pd]),
+        "rn_serialize": (u64, [vp]),
+        "rn_copy_blob": (None, [vp, vp]),
+        "rn_deserialize": (vp, [i32, vp, u64]),
+        "rn_seed_entities": (None, [vp, u32, pu32, pu8, pf]),
+        "rn_equals": (i32, [vp, vp]),
         "rn_are_colliding": (None, [vp, u32, pu32, pu32, pu8]),
         "rn_first_hit_raycast": (None, [vp, u32, pf, pu8, pu64, pu8, vp]),
         "rn_stage_translations": (i32, [vp, u32, pu32, pf]),
@@ -145,7 +150,10 @@ def load(name: str) -> C.CDLL:
         "rn_compute_aabb": (None, [u32, pu8, pf, pu8, pf, pf]),
         "rn_polygon_normals": (None, [u32, pf, pu8, pf]),
     }
+    optional = {"rn_serialize", "rn_copy_blob", "rn_deserialize", "rn_seed_entities", "rn_equals"}  # not in the C oracle
     for fn, (res, args) in sig.items():
+        if fn in optional and not hasattr(lib, fn):
+            continue
         f = getattr(lib, fn)
         f.restype = res
         f.argtypes = args
@@ -172,11 +180,39 @@ def xf5_from_xf3(xf3) -> np.ndarray:
 class Backend:
     """A Registry<uint32_t, Method> living behind one of the rn_* libraries."""
 
-    def __init__(self, name: str, method: int = 0, cell_size: int = 120):
+    def __init__(self, name: str, method: int = 0, cell_size: int = 120, _ctx=None):
         self.name = name
+        self.method = method
         self.lib = load(name)
-        self.ctx = self.lib.rn_create(method, cell_size)
+        self.ctx = _ctx if _ctx is not None else self.lib.rn_create(method, cell_size)
         self._check()
+
+    # -- snapshots ----------------------------------------------------------------------------
+    def serialize(self) -> bytes:
+        """Registry::serialize -> the snapshot bytes."""
+        n = int(self.lib.rn_serialize(self.ctx))
+        self._check()
+        buf = C.create_string_buffer(n)
+        self.lib.rn_copy_blob(self.ctx, buf)
+        return buf.raw
+
+    @classmethod
+    def deserialize(cls, name: str, blob: bytes, method: int = 0, entities=None):
+        """Registry::deserialize(blob) in backend `name`.  `entities` = (ids, body, prev_xf5) re-seeds the harness's own
+        mirror of body types / bullets' previous transforms (it is kept by observation, not read from the Registry)."""
+        lib = load(name)
+        ctx = lib.rn_deserialize(method, blob, len(blob))
+        b = cls(name, method, _ctx=ctx)
+        if entities is not None:
+            ids, body, prev = _u32(entities[0]), _u8(entities[1]), _f32(entities[2])
+            lib.rn_seed_entities(b.ctx, len(ids), _p(ids, C.c_uint32), _p(body, C.c_uint8), _p(prev, C.c_float))
+            b._check()
+        return b
+
+    def equals(self, other) -> bool:
+        r = int(self.lib.rn_equals(self.ctx, other.ctx))
+        self._check()
+        return r == 1
 
     def close(self):
         if self.ctx:
