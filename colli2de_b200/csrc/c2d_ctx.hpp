@@ -219,6 +219,7 @@ struct c2d_gpu_ctx
     uint32_t cellSize = 120;
     uint32_t shardRank = 0, shardWorld = 1;
     uint32_t rebuildPeriod = 4; // LBVH topology rebuilt every N-th dirty frame, refit in between
+    uint32_t smallSceneMax = 8192; // <= this many live shapes: all-pairs broadphase (c2d_gpu_set_small_scene_limit)
 
     // frame
     c2d_dev::FrameScratch* dScratch = nullptr;
@@ -232,6 +233,7 @@ struct c2d_gpu_ctx
     struct FrameState // one c2d_gpu_collide_begin .. c2d_gpu_collide_end bracket
     {
         bool open = false;
+        bool smallScene = false; // this frame runs k_small_pairs / k_small_narrow instead of the tree pipeline
         std::chrono::steady_clock::time_point wall0{};
         uint32_t retries = 0;
         uint64_t d2h = 0;

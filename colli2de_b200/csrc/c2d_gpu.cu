@@ -422,6 +422,24 @@ void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats);
 int pipeline_attempt(c2d_gpu_ctx* ctx)
 {
     cudaStream_t s = ctx->stream;
+    if (ctx->frame.smallScene)
+    {
+        const uint32_t nS = static_cast<uint32_t>(ctx->members[C2D_STATIC].size());
+        const uint32_t nD = static_cast<uint32_t>(ctx->members[C2D_DYNAMIC].size());
+        const uint32_t nB = static_cast<uint32_t>(ctx->members[C2D_BULLET].size());
+        if (nD + nB)
+            C2D_TIMED(ctx, "k_small_pairs", k_small_pairs<<<dim3(blocks_for(nD + nB, kSmallQueries), blocks_for(nS + nD + nB, kSmallTile)), kSmallQueries, 0, s>>>(
+                ctx->tree[C2D_STATIC].members.ptr, nS, ctx->tree[C2D_DYNAMIC].members.ptr, nD, ctx->tree[C2D_BULLET].members.ptr, nB,
+                ctx->d.fat, ctx->d.category, ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount));
+        C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+        C2D_TIMED(ctx, "k_small_narrow", k_small_narrow<<<148 * 2, 128, 0, s>>>(ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), ctx->d,
+                                                                             ctx->dScratch, ctx->out.ptr, static_cast<uint32_t>(ctx->out.capacity)));
+        ctx->launches += 2;
+        C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
+        ctx->frame.d2h += sizeof(FrameScratch);
+        return 0;
+    }
     if (ctx->broadphase == C2D_BROADPHASE_GRID)
     {
         ProfScope ps(ctx, "grid_broadphase(extent+count+scan+fill+sort+gather+pairs)");
@@ -476,7 +494,17 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
 
     C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
     ++ctx->launches;
-    if (ctx->broadphase != C2D_BROADPHASE_GRID) // the grid broadphase needs no tree; rays build them on demand (ensure_trees)
+    // small scenes: all-pairs box test + one narrowphase kernel instead of the tree pipeline (launch-latency bound);
+    // like the grid broadphase this needs no tree, rays build them on demand (ensure_trees)
+    const size_t alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
+    ctx->frame.smallScene = alive <= ctx->smallSceneMax && ctx->shardWorld == 1;
+    if (ctx->frame.smallScene)
+    {
+        for (int body = 0; body < 3; ++body)
+            if (int rc = upload_members(ctx, body))
+                return rc;
+    }
+    else if (ctx->broadphase != C2D_BROADPHASE_GRID)
         for (int body = 0; body < 3; ++body)
             if (ctx->treeDirty[body])
                 if (int rc = build_tree(ctx, body))
@@ -741,6 +769,12 @@ int c2d_gpu_kernel_profile(c2d_gpu_ctx* ctx, char* buffer, uint64_t capacity, in
 int c2d_gpu_set_rebuild_period(c2d_gpu_ctx* ctx, uint32_t frames)
 {
     ctx->rebuildPeriod = frames ? frames : 1;
+    return 0;
+}
+
+int c2d_gpu_set_small_scene_limit(c2d_gpu_ctx* ctx, uint32_t shapes)
+{
+    ctx->smallSceneMax = shapes;
     return 0;
 }
 

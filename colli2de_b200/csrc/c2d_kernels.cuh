@@ -913,6 +913,96 @@ __global__ void __launch_bounds__(128) k_narrow_manifold(const uint4* __restrict
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Small scenes (a few thousand shapes — the reference's own 1k / 10k benchmarks): the frame is bound by the ~30
+// dependent launches of the tree pipeline, not by work.  Two kernels replace sort + build + fit + 5 traversals and
+// the 8 narrowphase launches: an all-pairs box test over the member lists (tiles of targets staged in shared
+// memory; same predicate and same pair orientation as k_traverse) and a one-thread-per-candidate narrowphase.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kSmallQueries = 128; // queries per block (one per thread)
+constexpr int kSmallTile = 64;     // targets per block: grid = (query blocks, target tiles), 64 tests per thread
+
+__global__ void __launch_bounds__(kSmallQueries)
+    k_small_pairs(const uint32_t* __restrict__ membersS, uint32_t nS, const uint32_t* __restrict__ membersD, uint32_t nD,
+                  const uint32_t* __restrict__ membersB, uint32_t nB, const float4* __restrict__ fat,
+                  const uint64_t* __restrict__ category, uint2* __restrict__ out, uint32_t capacity, uint32_t* counter)
+{
+    __shared__ float4 tileBox[kSmallTile];
+    __shared__ uint64_t tileCat[kSmallTile];
+    __shared__ uint32_t tileShape[kSmallTile];
+    // targets: Static, Dynamic, Bullet lists back to back; this block sees the tile blockIdx.y of them
+    const uint32_t nT = nS + nD + nB;
+    const uint32_t t0 = blockIdx.y * kSmallTile;
+    if (threadIdx.x < kSmallTile && t0 + threadIdx.x < nT)
+    {
+        const uint32_t t = t0 + threadIdx.x;
+        const uint32_t ts = t < nS ? membersS[t] : (t < nS + nD ? membersD[t - nS] : membersB[t - nS - nD]);
+        tileShape[threadIdx.x] = ts;
+        tileBox[threadIdx.x] = fat[ts];
+        tileCat[threadIdx.x] = category[ts];
+    }
+    __syncthreads();
+    // queries: the Dynamic members, then the Bullet members (Static shapes never query, Registry.hpp:487-545)
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nD + nB)
+        return;
+    const bool bullet = q >= nD;
+    const uint32_t qs = bullet ? membersB[q - nD] : membersD[q];
+    const float4 qb = fat[qs];
+    const uint64_t qc = category[qs];
+    const uint32_t count = min(static_cast<uint32_t>(kSmallTile), nT - t0);
+    for (uint32_t k = 0; k < count; ++k)
+    {
+        const uint32_t ti = t0 + k; // position in the concatenated target list; nS + q is the query's own position
+        // Dynamic queries: all Static, Dynamic after itself.  Bullet queries: all Static, all Dynamic, Bullets after itself.
+        const bool wanted = ti < nS || (bullet ? (ti < nS + nD || ti > nS + q) : (ti > nS + q && ti < nS + nD));
+        if (wanted && (qc & tileCat[k]) != 0 && box_overlap(qb, tileBox[k]))
+        {
+            const uint32_t ts = tileShape[k];
+            const bool sameTree = bullet ? ti >= nS + nD : ti >= nS;
+            emit_pair(sameTree ? min(qs, ts) : qs, sameTree ? max(qs, ts) : ts, out, capacity, counter);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_small_narrow(const uint2* __restrict__ cand, uint32_t capacity, ShapeArrays s,
+                                                      FrameScratch* fs, PairOut* __restrict__ out, uint32_t outCapacity)
+{
+    const uint32_t n = min(fs->candCount, capacity);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const uint2 p = cand[i];
+        PairCtx c;
+        if (!load_pair(s, p, c))
+            continue;
+        Manifold m;
+        bool hit;
+        if (!c.bulletA && !c.bulletB)
+            hit = narrow_test<true>(c.A, c.xa, c.B, c.xb, m);
+        else
+        {
+            Motion moA, moB;
+            load_motions(s, p, c, moA, moB);
+            float fraction = 0.0f;
+            hit = !sweep_cannot_hit(c.A, moA, c.B, moB) && sweep_search(c.A, moA, c.B, moB, fraction);
+            if (hit)
+                sweep_manifold(c.A, moA, c.B, moB, fraction, m);
+        }
+        if (!hit)
+            continue;
+        const uint32_t j = atomicAdd(&fs->outCount, 1u);
+        if (j < outCapacity)
+        {
+            PairOut* o = out + j;
+            o->entityA = c.ea;
+            o->entityB = c.eb;
+            o->shapeA = p.x;
+            o->shapeB = p.y;
+            manifold_store(m, o->manifold);
+        }
+    }
+}
+
 // ---- polygon bin of mode 0 (polygon vs polygon | capsule | segment, no bullet): 8 lanes per pair --------------
 __device__ __forceinline__ bool pp_setup(const ShapeArrays& s, uint2 p, bool valid, PairCtx& c, bool& rev)
 {

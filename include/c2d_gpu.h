@@ -125,6 +125,10 @@ int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size);
  * rebuilt every `frames`-th dirty frame and only refit (exact boxes, bottom-up) in between.  1 = rebuild every
  * frame.  Default 4.  Results do not depend on it. */
 int c2d_gpu_set_rebuild_period(c2d_gpu_ctx* ctx, uint32_t frames);
+/* Scenes with at most `shapes` live shapes skip the tree pipeline: one all-pairs box-test kernel over the member
+ * lists and one narrowphase kernel (same candidate predicate, same results) - the ~30 dependent launches of the
+ * tree pipeline cost more than the work at that size.  Default 8192; 0 disables the shortcut. */
+int c2d_gpu_set_small_scene_limit(c2d_gpu_ctx* ctx, uint32_t shapes);
 /* Multi-GPU sharding of the query leaves: this context emits only the pairs whose
  * query leaf lies in Morton-rank slab `rank` of `world`.  Default 0 of 1. */
 int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world);
