@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(128) k_narrow_filter_pp(const uint2* __restric
     }
 }
 
-__global__ void __launch_bounds__(128, 4) k_narrow_manifold_pp(const uint4* __restrict__ hits, ShapeArrays s,
+__global__ void __launch_bounds__(128, 8) k_narrow_manifold_pp(const uint4* __restrict__ hits, ShapeArrays s,
                                                             FrameScratch* fs, PairOut* __restrict__ out,
                                                             uint32_t outCapacity)
 {

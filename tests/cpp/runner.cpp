@@ -120,6 +120,8 @@ struct IRegistry
     virtual Transform getEntityTransform(uint32_t id) const = 0;
     virtual void getCollidingPairs(std::vector<PairRec>& out, double* seconds) = 0;
     virtual void getCollisions(uint32_t id, std::vector<PairRec>& out) const = 0;
+    // all ids in one call where the backend has a batched entry point; false -> the caller loops getCollisions()
+    virtual bool getCollisionsBatch(uint32_t n, const uint32_t* ids, std::vector<PairRec>& out) const = 0;
     virtual bool areColliding(uint32_t a, uint32_t b) const = 0;
     virtual bool firstHit(Ray r, uint64_t mask, HitRec& out) const = 0;
     virtual bool firstHit(InfiniteRay r, uint64_t mask, HitRec& out) const = 0;
@@ -216,6 +218,19 @@ struct RegistryHolder final : IRegistry
         out.resize(pairs.size());
         if (!pairs.empty())
             std::memcpy(out.data(), pairs.data(), pairs.size() * sizeof(PairRec));
+    }
+    bool getCollisionsBatch(uint32_t n, const uint32_t* ids, std::vector<PairRec>& out) const override
+    {
+#if defined(RN_BACKEND_B200)
+        const auto pairs = reg.getCollisions(std::span<const uint32_t>(ids, n));
+        out.resize(pairs.size());
+        if (!pairs.empty())
+            std::memcpy(out.data(), pairs.data(), pairs.size() * sizeof(PairRec));
+        return true;
+#else
+        (void)n, (void)ids, (void)out;
+        return false;
+#endif
     }
     void getCollisions(uint32_t id, std::vector<PairRec>& out) const override
     {
@@ -643,11 +658,14 @@ uint64_t rn_get_collisions_many(rn_ctx* ctx, uint32_t n, const uint32_t* ids, do
     RN_TRY(ctx)
     uint64_t total = 0;
     const auto t0 = std::chrono::steady_clock::now();
-    for (uint32_t i = 0; i < n; ++i)
-    {
-        ctx->reg->getCollisions(ids[i], ctx->pairs);
-        total += ctx->pairs.size();
-    }
+    if (std::getenv("RN_COLLISIONS_BATCH") != nullptr && ctx->reg->getCollisionsBatch(n, ids, ctx->pairs))
+        total = ctx->pairs.size(); // the batched extension; the records stay available to rn_copy_pairs
+    else
+        for (uint32_t i = 0; i < n; ++i)
+        {
+            ctx->reg->getCollisions(ids[i], ctx->pairs);
+            total += ctx->pairs.size();
+        }
     if (seconds)
         *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return total;

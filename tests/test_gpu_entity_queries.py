@@ -73,3 +73,18 @@ def test_get_collisions_are_colliding_first_hit(oracle):
     else:  # exact (entry, exit) ties between leaf boxes are resolved by the reference's traversal order (D10)
         differing = int((rf != gf).sum()) + int(sum(x.tobytes() != y.tobytes() for x, y in zip(rh[rf & gf > 0], gh[rf & gf > 0])))
         assert differing <= 10, differing
+
+
+def test_get_collisions_batch_equals_the_single_calls(monkeypatch):
+    """Registry::getCollisions(span of ids) (extension): one device pass, the concatenation of the per-entity results."""
+    sc = _scene()
+    gpu = _prepare(SUBJECT, sc)
+    ids = np.arange(0, 6600, 7, dtype=np.uint32)
+    singles = np.concatenate([gpu.get_collisions(int(e)) for e in ids])
+    monkeypatch.setenv("RN_COLLISIONS_BATCH", "1")
+    total, _ = gpu.get_collisions_many(ids)
+    batch = np.zeros(total, H.PAIR_DTYPE)
+    if total:
+        gpu.lib.rn_copy_pairs(gpu.ctx, batch.ctypes.data_as(__import__("ctypes").c_void_p))
+    assert total == len(singles) > 100
+    assert P.sort_pairs(batch).tobytes() == P.sort_pairs(singles).tobytes()
