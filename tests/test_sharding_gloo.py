@@ -108,7 +108,7 @@ def test_slabs_with_ghosts_and_owner_rule(tmp_path, world):
     assert os.path.exists(tmp_path / "ok")
 
 
-def _exchange_worker(rank, world, port, out_dir):
+def _exchange_worker(rank, world, port, out_dir, use_plan=False):
     """Like _ghost_worker, but a rank only KNOWS the moves of the shapes it owns: the halo copies receive theirs through
     sharding.exchange_boundary_moves (the data-path collective of the decomposition)."""
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -124,6 +124,9 @@ def _exchange_worker(rank, world, port, out_dir):
     b.set_ghost(ids[ghost[local]], np.ones(int(ghost[local].sum()), np.uint8))
     movable = sc["ent_body"] != 0
     ghost_ids = np.sort(sc["ent_id"][ghost & movable])
+    plan = sharding.ExchangePlan(sc["ent_id"][exports & movable], ghost_ids) if use_plan else None
+    if plan is not None:
+        assert plan.found.all(), "a halo copy has no exporting owner"
     for frame in range(3):
         # moves of the OWNED shapes only (a private stream per rank would do; here a function of id and frame)
         mine = sc["ent_id"][owned & movable]
@@ -131,6 +134,12 @@ def _exchange_worker(rank, world, port, out_dir):
         d_all = r.uniform(-0.6, 0.6, (len(sc["ent_id"]), 2)).astype(np.float32)  # stands in for "what the owner decided"
         d_mine = d_all[mine]
         exp = sc["ent_id"][exports & movable]
+        if plan is not None:
+            # persistent plan: only the 8-byte moves travel, the ghosts' rows come back in ghost_ids order
+            d_ghost = plan.exchange(d_all[exp])
+            assert np.array_equal(d_ghost, d_all[ghost_ids])
+            b.move_translate(np.concatenate([mine, ghost_ids]), np.concatenate([d_mine, d_ghost]))
+            continue
         all_ids, all_d = sharding.exchange_boundary_moves(exp, d_all[exp])
         sel = np.isin(all_ids, ghost_ids)
         assert set(all_ids[sel].tolist()) == set(ghost_ids.tolist()), "a halo copy did not receive its move"
@@ -158,4 +167,12 @@ def _exchange_worker(rank, world, port, out_dir):
 def test_boundary_move_exchange_world2(tmp_path):
     port = _free_port()
     mp.spawn(_exchange_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert os.path.exists(tmp_path / "ok")
+
+
+@pytest.mark.skipif(not H.available("oracle"), reason="needs oracle/libc2d_oracle.so")
+def test_exchange_plan_world3(tmp_path):
+    """sharding.ExchangePlan: the halo-exchange plan built once, then one fixed-shape all-gather per frame."""
+    port = _free_port()
+    mp.spawn(_exchange_worker, args=(3, port, str(tmp_path), True), nprocs=3, join=True)
     assert os.path.exists(tmp_path / "ok")
