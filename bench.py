@@ -401,7 +401,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         rec = json.load(open(tpath)).get(ncu_name)
         if rec:
             traffic = rec["dram"]
-            traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_full_top_kernels_v2.csv "
+            traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_full_top_kernels_v3.csv "
                            f"(cold-cache, serialised replay; {rec['launches_profiled']} launches)")
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

@@ -1010,8 +1010,8 @@ c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
         if (const char* lws = std::getenv("LOCAL_WORLD_SIZE"))
         {
             const unsigned ranks = static_cast<unsigned>(std::strtoul(lws, nullptr, 10));
-            if (ranks > 1)
-                helpers = helpers / ranks > 0 ? helpers / ranks : 1;
+            if (ranks > 1) // all cores, split between the ranks (their main threads are blocked in this copy anyway)
+                helpers = std::thread::hardware_concurrency() / ranks > 0 ? std::thread::hardware_concurrency() / ranks : 1;
         }
         helpers = helpers > 8 ? 8 : helpers;
         if (const char* env = std::getenv("C2D_GPU_COPY_THREADS"))

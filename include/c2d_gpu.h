@@ -194,7 +194,8 @@ int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats*
  *   c2d_gpu_collide_end     waits (re-running on a pair-list overflow), joins the pre-fault, reports the count;
  *   c2d_gpu_collide_fetch   copies `count` (<= the frame's count) records into `dst`: chunked device-to-host copies
  *                           into pinned staging, moved on to `dst` by the helper threads as they land.
- * Helper threads: min(8, hardware threads / 2 / LOCAL_WORLD_SIZE) including the caller, C2D_GPU_COPY_THREADS overrides
+ * Helper threads: min(8, hardware threads / 2) including the caller (with torchrun's LOCAL_WORLD_SIZE = R > 1:
+ * min(8, hardware threads / R)), C2D_GPU_COPY_THREADS overrides
  * (1 = none);
  * results below 4 MB are copied by the calling thread alone.  Records are the same as c2d_gpu_collide's. */
 int c2d_gpu_collide_begin(c2d_gpu_ctx* ctx);
