@@ -7,7 +7,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <sstream>
 #include <string>
+#include <type_traits>
 
 using namespace c2d;
 
@@ -92,6 +94,21 @@ void scenario(MakeId id)
         threw = true;
     }
     CHECK(threw);
+    // snapshots (the reference's wire format stores the raw bytes of the id: trivially copyable ids only)
+    if constexpr (std::is_trivially_copyable_v<Id>)
+    {
+        std::stringstream blob(std::ios::in | std::ios::out | std::ios::binary);
+        reg.serialize(blob);
+        Registry<Id> loaded = Registry<Id>::deserialize(blob);
+        CHECK(loaded == reg && loaded.size() == reg.size());
+        CHECK(loaded.getCollidingPairs().size() == pairs.size());
+        loaded.moveEntity(id(3), Translation{0.25f, 0.0f});
+        CHECK(loaded != reg);
+        CHECK(loaded.getEntityTransform(id(4)).translation == reg.getEntityTransform(id(4)).translation);
+        // the bullet's previous transform travelled too: the sweep still hits entity 3
+        auto again = loaded.getCollidingPairs();
+        CHECK(std::any_of(again.begin(), again.end(), [&](const auto& c) { return c.entityA == id(4) && c.entityB == id(3); }));
+    }
     Registry<Id> moved = std::move(reg);
     CHECK(moved.size() == 3 && moved.getCollidingPairs().size() == pairs.size());
     moved.clear();
