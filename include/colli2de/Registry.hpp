@@ -17,9 +17,9 @@
 //   * getCollidingPairs() returns the reference's SET of collisions in an unspecified order (the reference
 //     lists five body-type groups, each sorted by (shapeA, shapeB)); same-tree pairs always come out with
 //     shapeA < shapeB (the reference's A/B for those depends on its tree topology);
-//   * serialize / deserialize speak the reference's binary snapshot format for PartitioningMethod::None (the trees in a
-//     written snapshot are rebuilt, see internal/utils/Snapshot.hpp); Grid snapshots throw; operator== compares the
-//     logical state (entities, shapes, boxes), not tree topology;
+//   * serialize / deserialize speak the reference's binary snapshot format (the trees in a written snapshot are
+//     rebuilt, see internal/utils/Snapshot.hpp); operator== compares the logical state (entities, shapes, boxes), not
+//     tree topology;
 //   * extensions: moveEntities(), stageMoves() / applyStagedMoves(), rayCastBatch(), lastQueryStats().
 #pragma once
 
@@ -230,6 +230,7 @@ class Registry
             mStructureEpoch = o.mStructureEpoch;
             mStats = o.mStats;
             mPreviousAllCollisionsCount = o.mPreviousAllCollisionsCount;
+            mCellSize = o.mCellSize;
         }
         return *this;
     }
@@ -257,7 +258,7 @@ class Registry
     std::set<RayHit> rayCast(Ray ray, BitMaskType maskBits = ~0ull) const;
     std::set<RayHit> rayCast(InfiniteRay ray, BitMaskType maskBits = ~0ull) const;
 
-    // Binary snapshots in the reference's wire format (reference Registry.hpp:1205-1344), PartitioningMethod::None only.
+    // Binary snapshots in the reference's wire format (reference Registry.hpp:1205-1344; Grid: BroadPhaseTree.hpp:539-733).
     void serialize(std::ostream& out) const;
     static Registry deserialize(std::istream& in);
     // Same logical state: entities, transforms, shapes, category / mask bits, activity, tight and leaf boxes, free ids.
@@ -346,7 +347,10 @@ class Registry
         if (c2d_gpu_create(-1, &mCtx) != 0)
             throw std::runtime_error(std::string("colli2de-b200: ") + c2d_gpu_last_error(nullptr));
         if constexpr (Method == PartitioningMethod::Grid)
-            check(c2d_gpu_set_broadphase(mCtx, C2D_BROADPHASE_GRID, cellSize));
+        {
+            mCellSize = cellSize ? cellSize : 120; // BroadPhaseTree's default (reference BroadPhaseTree.hpp:96)
+            check(c2d_gpu_set_broadphase(mCtx, C2D_BROADPHASE_GRID, mCellSize));
+        }
     }
     snapshot::RegistryState<EntityId> captureState() const;
     void check(int rc) const
@@ -502,6 +506,7 @@ class Registry
     mutable c2d_gpu_stats mStats{};
     std::vector<EntityCollision> mViewStorage;
     uint32_t mPreviousAllCollisionsCount = 1024; // reference Registry.hpp:168
+    uint32_t mCellSize = 0;                      // PartitioningMethod::Grid only
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -1073,25 +1078,26 @@ snapshot::RegistryState<EntityId> Registry<EntityId, Method>::captureState() con
     }
     state.freeShapeIds = mFreeShapeIds;
     state.previousAllCollisionsCount = mPreviousAllCollisionsCount;
+    state.gridCellSize = Method == PartitioningMethod::Grid ? static_cast<int32_t>(mCellSize) : 0;
     return state;
 }
 
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::serialize(std::ostream& out) const
 {
-    if constexpr (Method == PartitioningMethod::Grid)
-        throw std::runtime_error("colli2de-b200: snapshots of PartitioningMethod::Grid registries are not supported");
-    else
-        snapshot::write(out, captureState());
+    snapshot::write(out, captureState());
 }
 
 template <typename EntityId, PartitioningMethod Method>
 Registry<EntityId, Method> Registry<EntityId, Method>::deserialize(std::istream& in)
 {
-    if constexpr (Method == PartitioningMethod::Grid)
-        throw std::runtime_error("colli2de-b200: snapshots of PartitioningMethod::Grid registries are not supported");
-    const snapshot::RegistryState<EntityId> state = snapshot::read<EntityId>(in);
-    Registry registry;
+    const snapshot::RegistryState<EntityId> state = snapshot::read<EntityId>(in, Method == PartitioningMethod::Grid);
+    Registry registry = [&] {
+        if constexpr (Method == PartitioningMethod::Grid)
+            return Registry(static_cast<uint32_t>(state.gridCellSize));
+        else
+            return Registry();
+    }();
     const auto load = [](const float* xf) {
         Transform t{};
         t.translation = Vec2{xf[0], xf[1]};

@@ -19,7 +19,17 @@
 // (balanced median splits over the Morton-sorted leaves, exact heights / parents / unioned boxes and category bits, a
 // power-of-two node array whose tail is the free list) — the reference loads them and keeps inserting, moving and
 // removing proxies on top.  The per-shape state that IS history — the tight box and the leaf (fat) box — is carried
-// bit for bit in both directions.  PartitioningMethod::Grid snapshots are not supported yet.
+// bit for bit in both directions.
+//
+// PartitioningMethod::Grid (reference BroadPhaseTree.hpp:539-733): each of the three trees is
+//   i32 cellSize; size_t P; P x { ShapeId id; f32 box[4]; u64 category, mask; size_t H; H x { i32 cellX, cellY; i32 node } }
+//   size_t R; R x { i32 cellX, cellY; size_t bvhIndex };   size_t B; B x { i32 cellX, cellY; tree (as above) }
+//   size_t freeProxies; ... ; size_t freeBvhs; ...
+// A proxy is registered in every cell its box touches (getCellFor, BroadPhaseTree.hpp:71-79, quirks included) and owns
+// one leaf per cell.  In the reference those per-cell leaves have per-cell histories; the GPU library keeps ONE leaf box
+// per shape, so a snapshot written here gives every cell leaf that box (it contains the tight box, which is all the
+// reference's queries need), and a snapshot read here takes the union of the shape's cell leaves.  Query RESULTS are
+// unaffected either way — leaf boxes only decide which pairs reach the narrowphase.
 #pragma once
 
 #include <algorithm>
@@ -30,6 +40,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 namespace c2d::snapshot
@@ -70,6 +81,7 @@ struct RegistryState
     std::vector<ShapeState> shapes;
     std::vector<uint32_t> freeShapeIds;
     uint32_t previousAllCollisionsCount = 1024;
+    int32_t gridCellSize = 0; // > 0: a PartitioningMethod::Grid registry (BroadPhaseTree images instead of DynamicBVHs)
 };
 
 namespace detail
@@ -297,9 +309,187 @@ inline TreeImage buildTree(const std::vector<Leaf>& leaves)
     return t;
 }
 
+
+// ---- PartitioningMethod::Grid ------------------------------------------------------------------------------------
+struct Cell
+{
+    int32_t x, y;
+    bool operator<(const Cell& o) const { return x < o.x || (x == o.x && y < o.y); } // GridCell::operator<
+    bool operator==(const Cell& o) const { return x == o.x && y == o.y; }
+};
+
+// getCellFor (BroadPhaseTree.hpp:71-79), including its treatment of negative positions
+inline Cell cellFor(float px, float py, int32_t cellSize)
+{
+    const int32_t ix = static_cast<int32_t>(px), iy = static_cast<int32_t>(py);
+    return Cell{ix - (px >= 0 ? ix % cellSize : (ix % cellSize) + cellSize),
+                iy - (py >= 0 ? iy % cellSize : (iy % cellSize) + cellSize)};
+}
+
+struct GridEntry // one (cell, shape) registration
+{
+    Cell cell;
+    uint32_t leaf; // index into the tree's leaf list
+};
+
+// BroadPhaseTree<ShapeId>::serialize for the shapes in `leaves` (proxy handle = position in the list)
+inline void putGridTree(std::ostream& out, const std::vector<Leaf>& leaves, int32_t cellSize)
+{
+    std::vector<GridEntry> entries;
+    for (uint32_t i = 0; i < leaves.size(); ++i)
+    {
+        const float* b = leaves[i].state->tight; // the proxy's box is the last box handed to moveProxy: the tight box
+        const Cell lo = cellFor(b[0], b[1], cellSize), hi = cellFor(b[2], b[3], cellSize);
+        for (int32_t y = lo.y; y <= hi.y; y += cellSize) // forEachCell (BroadPhaseTree.hpp:81-90)
+            for (int32_t x = lo.x; x <= hi.x; x += cellSize)
+                entries.push_back(GridEntry{Cell{x, y}, i});
+    }
+    std::stable_sort(entries.begin(), entries.end(), [](const GridEntry& a, const GridEntry& b) { return a.cell < b.cell; });
+    // one DynamicBVH per occupied cell, in cell order; node index of (cell, leaf) = position inside the cell's list
+    std::vector<std::pair<Cell, TreeImage>> bvhs;
+    std::vector<std::vector<std::pair<Cell, int32_t>>> handles(leaves.size());
+    for (size_t first = 0; first < entries.size();)
+    {
+        size_t last = first;
+        std::vector<Leaf> cellLeaves;
+        while (last < entries.size() && entries[last].cell == entries[first].cell)
+        {
+            handles[entries[last].leaf].push_back({entries[first].cell, static_cast<int32_t>(cellLeaves.size())});
+            cellLeaves.push_back(leaves[entries[last].leaf]);
+            ++last;
+        }
+        bvhs.emplace_back(entries[first].cell, buildTree(cellLeaves));
+        first = last;
+    }
+    put(out, cellSize);
+    put(out, static_cast<size_t>(leaves.size()));
+    for (uint32_t i = 0; i < leaves.size(); ++i)
+    {
+        const ShapeState& s = *leaves[i].state;
+        put(out, leaves[i].shape);
+        for (float f : s.tight)
+            put(out, f);
+        put(out, s.category);
+        put(out, s.mask);
+        put(out, static_cast<size_t>(handles[i].size()));
+        for (const auto& [cell, node] : handles[i]) // already in std::map order: entries were sorted by cell
+        {
+            put(out, cell.x);
+            put(out, cell.y);
+            put(out, node);
+        }
+    }
+    put(out, static_cast<size_t>(bvhs.size()));
+    for (size_t i = 0; i < bvhs.size(); ++i)
+    {
+        put(out, bvhs[i].first.x);
+        put(out, bvhs[i].first.y);
+        put(out, i);
+    }
+    put(out, static_cast<size_t>(bvhs.size()));
+    for (const auto& [cell, tree] : bvhs)
+    {
+        put(out, cell.x);
+        put(out, cell.y);
+        putTree(out, tree);
+    }
+    put(out, static_cast<size_t>(0)); // proxies free list
+    put(out, static_cast<size_t>(0)); // BVH free list
+}
+
+struct GridProxy
+{
+    uint32_t id = 0;
+    float box[4] = {};
+    uint64_t category = 1, mask = ~0ull;
+    std::vector<std::pair<Cell, int32_t>> handles;
+};
+
+struct GridTreeImage
+{
+    int32_t cellSize = 0;
+    std::vector<GridProxy> proxies;
+    std::vector<std::pair<Cell, size_t>> regions; // sorted by cell
+    std::vector<std::pair<Cell, TreeImage>> bvhs;
+};
+
+inline GridTreeImage getGridTree(std::istream& in)
+{
+    GridTreeImage t;
+    get(in, t.cellSize);
+    if (t.cellSize <= 0)
+        throw std::runtime_error("colli2de snapshot: invalid grid cell size");
+    t.proxies.resize(getCount(in, 44));
+    for (GridProxy& p : t.proxies)
+    {
+        get(in, p.id);
+        for (float& f : p.box)
+            get(in, f);
+        get(in, p.category);
+        get(in, p.mask);
+        p.handles.resize(getCount(in, 12));
+        for (auto& [cell, node] : p.handles)
+        {
+            get(in, cell.x);
+            get(in, cell.y);
+            get(in, node);
+        }
+    }
+    t.regions.resize(getCount(in, 16));
+    for (auto& [cell, index] : t.regions)
+    {
+        get(in, cell.x);
+        get(in, cell.y);
+        get(in, index);
+    }
+    std::sort(t.regions.begin(), t.regions.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+    t.bvhs.resize(getCount(in, 36));
+    for (auto& [cell, tree] : t.bvhs)
+    {
+        get(in, cell.x);
+        get(in, cell.y);
+        tree = getTree(in);
+    }
+    size_t skip = getCount(in, sizeof(size_t));
+    for (size_t i = 0, v = 0; i < skip; ++i)
+        get(in, v);
+    skip = getCount(in, sizeof(size_t));
+    for (size_t i = 0, v = 0; i < skip; ++i)
+        get(in, v);
+    return t;
+}
+
+// Union of the leaves the proxy `handle` owns in its cells; false if the image is inconsistent.
+inline bool gridLeafBox(const GridTreeImage& t, size_t handle, uint32_t shape, float* box)
+{
+    if (handle >= t.proxies.size() || t.proxies[handle].id != shape || t.proxies[handle].handles.empty())
+        return false;
+    bool first = true;
+    for (const auto& [cell, node] : t.proxies[handle].handles)
+    {
+        const auto it = std::lower_bound(t.regions.begin(), t.regions.end(), cell,
+                                         [](const auto& r, const Cell& c) { return r.first < c; });
+        if (it == t.regions.end() || !(it->first == cell) || it->second >= t.bvhs.size())
+            return false;
+        const TreeImage& bvh = t.bvhs[it->second].second;
+        if (node < 0 || static_cast<size_t>(node) >= bvh.nodes.size() || bvh.nodes[node].child1 != -1 || bvh.nodes[node].id != shape)
+            return false;
+        const float* b = bvh.nodes[node].box;
+        if (first)
+            std::memcpy(box, b, 4 * sizeof(float));
+        else
+        {
+            box[0] = std::min(box[0], b[0]), box[1] = std::min(box[1], b[1]);
+            box[2] = std::max(box[2], b[2]), box[3] = std::max(box[3], b[3]);
+        }
+        first = false;
+    }
+    return true;
+}
+
 } // namespace detail
 
-// Registry<EntityId, None>::serialize (reference Registry.hpp:1205-1264).
+// Registry<EntityId, Method>::serialize (reference Registry.hpp:1205-1264); state.gridCellSize selects the tree format.
 template <typename EntityId>
 void write(std::ostream& out, const RegistryState<EntityId>& state)
 {
@@ -380,7 +570,10 @@ void write(std::ostream& out, const RegistryState<EntityId>& state)
         put(out, s);
 
     for (int body = 0; body < 3; ++body)
-        putTree(out, buildTree(leaves[body]));
+        if (state.gridCellSize > 0)
+            putGridTree(out, leaves[body], state.gridCellSize);
+        else
+            putTree(out, buildTree(leaves[body]));
 
     size_t bullets = 0;
     for (const EntityState<EntityId>& e : state.entities)
@@ -398,9 +591,9 @@ void write(std::ostream& out, const RegistryState<EntityId>& state)
         throw std::runtime_error("colli2de snapshot: write failed");
 }
 
-// Registry<EntityId, None>::deserialize (reference Registry.hpp:1266-1344).
+// Registry<EntityId, Method>::deserialize (reference Registry.hpp:1266-1344); grid = PartitioningMethod::Grid.
 template <typename EntityId>
-RegistryState<EntityId> read(std::istream& in)
+RegistryState<EntityId> read(std::istream& in, bool grid = false)
 {
     using namespace detail;
     static_assert(std::is_trivially_copyable_v<EntityId>, "snapshots store the raw bytes of the entity id");
@@ -470,8 +663,14 @@ RegistryState<EntityId> read(std::istream& in)
     for (uint32_t& s : state.freeShapeIds)
         get(in, s);
     TreeImage trees[3];
-    for (TreeImage& t : trees)
-        t = getTree(in);
+    GridTreeImage gridTrees[3];
+    for (int body = 0; body < 3; ++body)
+        if (grid)
+            gridTrees[body] = getGridTree(in);
+        else
+            trees[body] = getTree(in);
+    if (grid)
+        state.gridCellSize = gridTrees[0].cellSize;
     const size_t bullets = getCount(in, sizeof(EntityId) + 20);
     std::vector<std::pair<EntityId, std::vector<float>>> previous(bullets);
     for (auto& [id, xf] : previous)
@@ -494,8 +693,14 @@ RegistryState<EntityId> read(std::istream& in)
             ShapeState& s = state.shapes[shape];
             s.alive = true;
             s.body = e.body;
-            const TreeImage& t = trees[e.body];
             const size_t h = handles[shape];
+            if (grid)
+            {
+                if (!gridLeafBox(gridTrees[e.body], h, shape, s.fat))
+                    throw std::runtime_error("colli2de snapshot: shape handle does not name its grid proxy");
+                continue;
+            }
+            const TreeImage& t = trees[e.body];
             if (h >= t.nodes.size() || t.nodes[h].child1 != -1 || t.nodes[h].id != shape)
                 throw std::runtime_error("colli2de snapshot: shape handle does not name its leaf");
             std::memcpy(s.fat, t.nodes[h].box, sizeof(s.fat));

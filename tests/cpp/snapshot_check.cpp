@@ -19,14 +19,14 @@ const char* snap_last_error(void)
     return g_error.c_str();
 }
 
-// Decodes a Registry<uint32_t, None> snapshot and encodes it again (the trees are rebuilt).  Returns 0 on success;
+// Decodes a Registry<uint32_t, None | Grid> snapshot and encodes it again (the trees are rebuilt).  Returns 0 on success;
 // *out is malloc'ed, release it with snap_free.
-int snap_reencode(const void* bytes, uint64_t size, void** out, uint64_t* out_size)
+int snap_reencode(const void* bytes, uint64_t size, int grid, void** out, uint64_t* out_size)
 {
     try
     {
         std::stringstream in(std::string(static_cast<const char*>(bytes), size), std::ios::in | std::ios::binary);
-        const auto state = c2d::snapshot::read<uint32_t>(in);
+        const auto state = c2d::snapshot::read<uint32_t>(in, grid != 0);
         std::stringstream ss(std::ios::in | std::ios::out | std::ios::binary);
         c2d::snapshot::write(ss, state);
         const std::string blob = ss.str();
@@ -45,12 +45,12 @@ int snap_reencode(const void* bytes, uint64_t size, void** out, uint64_t* out_si
 
 // Summary of a decoded snapshot: counts[0] entities, [1] shape slots, [2] live shapes, [3] free ids, [4] bullets with a
 // previous transform, [5] inactive live shapes.
-int snap_summary(const void* bytes, uint64_t size, uint64_t* counts6)
+int snap_summary(const void* bytes, uint64_t size, int grid, uint64_t* counts6)
 {
     try
     {
         std::stringstream in(std::string(static_cast<const char*>(bytes), size), std::ios::in | std::ios::binary);
-        const auto state = c2d::snapshot::read<uint32_t>(in);
+        const auto state = c2d::snapshot::read<uint32_t>(in, grid != 0);
         counts6[0] = state.entities.size();
         counts6[1] = state.shapes.size();
         counts6[2] = counts6[4] = counts6[5] = 0;
