@@ -103,17 +103,15 @@ struct Round
 struct RayBuffers
 {
     DevBuf<c2d_ray> dRays;
-    DevBuf<uint32_t> counts, finalCounts, sums, totals;
-    DevBuf<unsigned char> segs;
-    DevBuf<c2d_hit_record> out;
-    PinnedVec<c2d_hit_record> hostHits;
+    DevBuf<uint32_t> counts, sums, totals;   // per-ray hit counts -> exclusive offsets (scan)
+    DevBuf<unsigned char> smallHeaders;      // 16-byte control block + one SmallHeader per ray
+    DevBuf<c2d_hit_record> packed;           // hits in block-completion order, before the gather into ray order
+    DevBuf<unsigned char> segs;              // global scratch of the heavy tier (2 x leaf-hit entries)
+    PinnedVec<c2d_hit_record> hostHits;      // results of the pointer-returning entry points / the latency path
     PinnedVec<uint64_t> hostOffsets;
     PinnedVec<uint32_t> hostOffsets32;
-    // small-batch (block-per-ray) path
-    DevBuf<unsigned char> smallHeaders;
-    PinnedVec<unsigned char> hostSmall;
-    PinnedVec<c2d_hit_record> hostReorder;
-    DevBuf<c2d_hit_record> packed; // hits in block-completion order, before the gather into ray order
+    PinnedVec<unsigned char> hostSmall;      // latency path: headers downloaded in one copy
+    PinnedVec<c2d_hit_record> hostReorder;   // latency path: completion order -> ray order on the host
     // rays with more leaf-box hits than the shared-memory kernel holds (global-scratch path)
     DevBuf<unsigned char> heavy;
     DevBuf<uint32_t> heavyIndex;

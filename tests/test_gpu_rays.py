@@ -192,3 +192,22 @@ def test_heavy_rays_all_tiers(oracle):
     assert np.array_equal(ef, gf)
     differ = sum(1 for k in range(m) if ef[k] and eh[k].tobytes() != gh[k].tobytes())
     assert differ <= (0 if oracle == "oracle" else 3), differ
+
+
+def test_batches_larger_than_one_chunk_are_consistent():
+    """More than 2^20 rays in one call (the throughput path works in chunks of 2^20): per-ray results must equal those of
+    the same rays cast in smaller calls, and the offsets must be a proper prefix sum across the chunk boundary."""
+    sc = scenes.mixed_scene(4000, 400, 300.0, seed=3)
+    gpu = H.Backend(SUBJECT)
+    scenes.populate(gpu, sc)
+    n = (1 << 20) + 70_000
+    ray4, inf = scenes.rays(n, 300.0, seed=21, finite_len=6.0)
+    inf[:] = 0  # short finite rays: a handful of hits each, so 1.1 M rays stay cheap
+    off, hits = gpu.raycast(ray4, inf)
+    assert len(off) == n + 1 and off[0] == 0 and off[-1] == len(hits) > n // 4
+    assert (np.diff(off.astype(np.int64)) >= 0).all()
+    lo = (1 << 20) - 5000
+    sub_off, sub_hits = gpu.raycast(ray4[lo:lo + 12_000], inf[lo:lo + 12_000])  # straddles the chunk boundary
+    a = hits[int(off[lo]):int(off[lo + 12_000])]
+    assert np.array_equal(np.diff(off[lo:lo + 12_001].astype(np.int64)), np.diff(sub_off.astype(np.int64)))
+    assert a.tobytes() == sub_hits.tobytes()
