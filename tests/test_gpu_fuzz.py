@@ -197,9 +197,19 @@ def test_random_api_sequences(seed):
     w = World()
     add_entities(rng, w, backends, int(rng.integers(150, 500)))
     total = 0
+    twin = None
     for step in range(7):
         random_step(rng, w, backends, teleports=method == 0)
         total += check_queries(rng, w, ref, gpu, ref_grid)
+        if step == 2:
+            # snapshot mid-script: the reloaded registry joins the script and must stay indistinguishable
+            twin = H.Backend.deserialize("b200", gpu.serialize(), method=method)
+            assert twin.equals(gpu)
+            backends = backends + (twin,)
+        elif twin is not None:
+            a, b = P.sort_pairs(gpu.get_colliding_pairs()), P.sort_pairs(twin.get_colliding_pairs())
+            assert a.tobytes() == b.tobytes(), f"reloaded registry diverged at step {step}"
+    assert twin.equals(gpu)
     assert total > 100, "the scripts should produce collisions"
     if method == 0:  # rays (grid rays are covered by tests/test_gpu_grid.py with the reference's cell-walk bug in mind)
         n = 48
