@@ -21,6 +21,10 @@
 #include <string>
 #include <vector>
 
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
 using namespace c2d_dev;
 
 namespace
@@ -999,7 +1003,22 @@ namespace
 {
 constexpr uint64_t kPoolThresholdBytes = 4ull << 20; // smaller results: one copy on the calling thread
 constexpr uint64_t kFetchChunkBytes = 1ull << 20;
-constexpr uint32_t kFetchWaveChunks = 64; // pinned staging = 64 MB, refilled wave by wave
+constexpr uint32_t kFetchWaveChunks = 64; // 64 MB per wave; two staging halves alternate
+
+// Destination buffers are usually freshly allocated (a new std::vector per call): ask for transparent huge pages so
+// that filling a GB-sized result costs thousands of page faults instead of hundreds of thousands.  A hint only.
+void advise_huge_pages(void* dst, uint64_t bytes)
+{
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    constexpr uintptr_t kHuge = 2u << 20;
+    const uintptr_t lo = (reinterpret_cast<uintptr_t>(dst) + kHuge - 1) & ~(kHuge - 1);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(dst) + bytes) & ~(kHuge - 1);
+    if (hi > lo)
+        madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+#else
+    (void)dst, (void)bytes;
+#endif
+}
 
 c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
 {
@@ -1043,32 +1062,48 @@ int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, u
     }
     c2d_host::CopyPool* pool = copy_pool(ctx);
     pool->wait();
+    advise_huge_pages(dstHost, total);
+    // two staging halves: while the workers drain wave w, the device-to-host copies of wave w + 1 are already in flight
     const uint64_t waveBytes = kFetchWaveChunks * kFetchChunkBytes;
-    if (!ctx->copyStage.reserve(waveBytes))
+    const uint64_t waves = (total + waveBytes - 1) / waveBytes;
+    if (!ctx->copyStage.reserve(waves > 1 ? 2 * waveBytes : waveBytes))
         return fail(ctx, "pinned host allocation failed");
-    while (ctx->copyEvents.size() < kFetchWaveChunks)
+    while (ctx->copyEvents.size() < 2 * kFetchWaveChunks)
     {
         cudaEvent_t ev = nullptr;
         C2D_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         ctx->copyEvents.push_back(ev);
     }
-    char* stage = reinterpret_cast<char*>(ctx->copyStage.data);
+    char* stageBase = reinterpret_cast<char*>(ctx->copyStage.data);
     const int device = ctx->device;
-    const cudaEvent_t* events = ctx->copyEvents.data();
-    for (uint64_t wave = 0; wave < total; wave += waveBytes)
-    {
-        const uint64_t bytes = wave + waveBytes < total ? waveBytes : total - wave;
+    const auto wave_bytes = [&](uint64_t w) { return (w + 1) * waveBytes <= total ? waveBytes : total - w * waveBytes; };
+    const auto issue = [&](uint64_t w) -> int {
+        const uint64_t bytes = wave_bytes(w);
         const uint32_t chunks = static_cast<uint32_t>((bytes + kFetchChunkBytes - 1) / kFetchChunkBytes);
+        char* stage = stageBase + (w & 1) * waveBytes;
         for (uint32_t k = 0; k < chunks; ++k)
         {
             const uint64_t off = k * kFetchChunkBytes, len = off + kFetchChunkBytes < bytes ? kFetchChunkBytes : bytes - off;
-            C2D_CUDA(ctx, cudaMemcpyAsync(stage + off, src + wave + off, len, cudaMemcpyDeviceToHost, s));
-            C2D_CUDA(ctx, cudaEventRecord(ctx->copyEvents[k], s));
+            C2D_CUDA(ctx, cudaMemcpyAsync(stage + off, src + w * waveBytes + off, len, cudaMemcpyDeviceToHost, s));
+            C2D_CUDA(ctx, cudaEventRecord(ctx->copyEvents[(w & 1) * kFetchWaveChunks + k], s));
         }
+        return 0;
+    };
+    if (int rc = issue(0))
+        return rc;
+    for (uint64_t w = 0; w < waves; ++w)
+    {
+        if (w + 1 < waves)
+            if (int rc = issue(w + 1))
+                return rc;
+        const uint64_t bytes = wave_bytes(w);
+        const uint32_t chunks = static_cast<uint32_t>((bytes + kFetchChunkBytes - 1) / kFetchChunkBytes);
         // every worker (helpers + this thread) takes the next chunk whose device-to-host copy has landed
         std::atomic<uint32_t> next{0};
         std::atomic<int> cudaErr{0};
-        char* dst = out + wave;
+        const char* stage = stageBase + (w & 1) * waveBytes;
+        char* dst = out + w * waveBytes;
+        const cudaEvent_t* events = ctx->copyEvents.data() + (w & 1) * kFetchWaveChunks;
         auto work = [&next, &cudaErr, device, events, chunks, bytes, stage, dst](unsigned) {
             cudaSetDevice(device);
             for (uint32_t k = next.fetch_add(1); k < chunks; k = next.fetch_add(1))
@@ -1103,6 +1138,7 @@ int c2d_host::copy_host(c2d_gpu_ctx* ctx, const void* srcHost, void* dstHost, ui
     }
     c2d_host::CopyPool* pool = copy_pool(ctx);
     pool->wait();
+    advise_huge_pages(dstHost, total);
     const uint32_t chunks = static_cast<uint32_t>((total + kFetchChunkBytes - 1) / kFetchChunkBytes);
     std::atomic<uint32_t> next{0};
     const char* src = static_cast<const char*>(srcHost);
@@ -1140,6 +1176,7 @@ int c2d_gpu_prefault(c2d_gpu_ctx* ctx, void* dst, uint64_t bytes)
     if (!dst || bytes < kPoolThresholdBytes)
         return 0;
     c2d_host::CopyPool* pool = copy_pool(ctx);
+    advise_huge_pages(dst, bytes);
     const unsigned workers = pool->helpers();
     if (workers == 0)
         return 0;
