@@ -1298,6 +1298,8 @@ int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const 
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->d.tight + first, tight4, count * sizeof(float4), cudaMemcpyHostToDevice, s));
     if (fat4 && count)
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->d.fat + first, fat4, count * sizeof(float4), cudaMemcpyHostToDevice, s));
+    if (tight4 && count)
+        k_clear_meta_bits<<<blocks_for(count, 256), 256, 0, s>>>(ctx->d.meta + first, count, META_TIGHT_EXACT);
     C2D_CUDA(ctx, cudaStreamSynchronize(s));
     for (int body = 0; body < 3; ++body)
     {

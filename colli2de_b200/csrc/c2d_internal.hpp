@@ -16,6 +16,8 @@ constexpr uint32_t META_BODY_SHIFT = 2;
 constexpr uint32_t META_ACTIVE = 1u << 4;
 constexpr uint32_t META_ALIVE = 1u << 5;
 constexpr uint32_t META_GHOST = 1u << 6; // halo copy of a shape owned by another rank (multi-GPU slabs)
+constexpr uint32_t META_TIGHT_EXACT = 1u << 7; // tight box == computeAABB(shape, current transform): set by add / Transform
+                                               // moves, cleared by translations (which shift the box) and restores
 constexpr uint32_t META_COUNT_SHIFT = 8;
 
 __host__ __device__ inline uint32_t meta_type(uint32_t m) { return m & META_TYPE_MASK; }

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(128) k_apply_adds(const AddRec* __restrict__ l
     s.geom[static_cast<size_t>(shape) * 32 + lane] = r->geom[lane];
     if (lane == 0)
     {
-        const uint32_t meta = r->meta;
+        const uint32_t meta = r->meta | META_TIGHT_EXACT;
         s.meta[shape] = meta;
         s.entity[shape] = r->entity;
         s.category[shape] = r->category;
@@ -111,7 +111,10 @@ __global__ void __launch_bounds__(256) k_apply_translates(const TransRec* __rest
     const float4 raw = reinterpret_cast<const float4*>(log)[i];
     const uint32_t shape = __float_as_uint(raw.x);
     const float dx = raw.y, dy = raw.z;
-    const bool bullet = meta_body(s.meta[shape]) == 2u;
+    const uint32_t meta = s.meta[shape];
+    const bool bullet = meta_body(meta) == 2u;
+    if (meta & META_TIGHT_EXACT)
+        s.meta[shape] = meta & ~META_TIGHT_EXACT; // the box is shifted from now on, not recomputed (rounding drift)
 
     const Box old = box_from(s.tight[shape]);
     Box nt; // AABB::translate: min += d; max += d (AABB.cpp:248-252)
@@ -149,6 +152,8 @@ __global__ void __launch_bounds__(256) k_apply_moves(const MoveRec* __restrict__
     t.c = r1.y;
     const uint32_t meta = s.meta[shape];
     const bool bullet = meta_body(meta) == 2u;
+    if (!(meta & META_TIGHT_EXACT))
+        s.meta[shape] = meta | META_TIGHT_EXACT;
 
     const Box old = box_from(s.tight[shape]);
     const Box nt = compute_aabb(meta_type(meta), meta_count(meta), s.geom + static_cast<size_t>(shape) * 32, t);
@@ -161,6 +166,14 @@ __global__ void __launch_bounds__(256) k_apply_moves(const MoveRec* __restrict__
     }
     s.xf[shape] = make_float4(t.tx, t.ty, t.s, t.c);
     s.xa[shape] = make_float4(r0.w, r1.z, r1.w, 0.0f);
+}
+
+// c2d_gpu_write_boxes: restored boxes are history, not computeAABB of the current transform
+__global__ void __launch_bounds__(256) k_clear_meta_bits(uint32_t* __restrict__ meta, uint32_t n, uint32_t bits)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        meta[i] &= ~bits;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -709,6 +722,7 @@ struct PairCtx
     XF xa, xb;
     uint32_t ea, eb;
     bool bulletA, bulletB;
+    bool exactTightB; // s.tight[shapeB] is the exact world AABB of B (B never translated since its box was computed)
 };
 
 __device__ __forceinline__ bool load_pair(const ShapeArrays& s, uint2 p, PairCtx& c)
@@ -740,6 +754,7 @@ __device__ __forceinline__ bool load_pair(const ShapeArrays& s, uint2 p, PairCtx
     c.xb = xf_from(s.xf[p.y]);
     c.bulletA = meta_body(ma) == 2u;
     c.bulletB = meta_body(mb) == 2u;
+    c.exactTightB = (mb & META_TIGHT_EXACT) != 0;
     return true;
 }
 
@@ -764,31 +779,68 @@ __device__ __forceinline__ void load_motions(const ShapeArrays& s, uint2 p, cons
 // start transform, used by the t = 0 test).  If that union and the other body's are further apart than a margin that
 // dwarfs the narrowphase slack (1e-6) and float rounding, none of the <= 19 boolean tests can succeed: skipping them
 // cannot change the result.
-__device__ __forceinline__ Box swept_extent(const ShapeRef& S, const Motion& mo)
+struct SweptBounds
 {
-    Box b = compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, mo.start);
+    Box start; // the shape at the start of the sweep: stored transform (t = 0 test) and libm sin/cos (later samples)
+    Box all;   // ... united with the shape at the end of the sweep
+};
+
+__device__ __forceinline__ SweptBounds swept_extent(const ShapeRef& S, const Motion& mo)
+{
+    SweptBounds r;
+    r.start = compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, mo.start);
+    r.all = r.start;
     if (mo.moving)
     {
         XF t = mo.start;
         t.s = mo.csin;
         t.c = mo.ccos;
-        b = box_combine(b, compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, t));
+        r.start = box_combine(r.start, compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, t));
         t.tx = mo.start.tx + mo.dx;
         t.ty = mo.start.ty + mo.dy;
-        b = box_combine(b, compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, t));
+        r.all = box_combine(r.start, compute_aabb(static_cast<uint32_t>(S.type), static_cast<uint32_t>(S.count), S.g, t));
     }
-    return b;
+    return r;
 }
 
-__device__ __forceinline__ bool sweep_cannot_hit(const ShapeRef& A, const Motion& ma, const ShapeRef& B, const Motion& mb)
+// exactB: the stored tight box of B when B does not move and that box is known to be computeAABB(B, its transform) —
+// then B's 128-byte geometry block need not be touched for the (vast majority of) candidates rejected here.
+__device__ __forceinline__ bool sweep_cannot_hit(const ShapeRef& A, const Motion& ma, const ShapeRef& B, const Motion& mb,
+                                                 const float4* exactB = nullptr)
 {
     if ((ma.moving && ma.da != 0.0f) || (mb.moving && mb.da != 0.0f))
         return false; // rotating sweep: no cheap bound
-    const Box a = swept_extent(A, ma), b = swept_extent(B, mb);
+    const SweptBounds sa = swept_extent(A, ma);
+    SweptBounds sb;
+    if (exactB != nullptr && !mb.moving)
+        sb.start = sb.all = box_from(*exactB);
+    else
+        sb = swept_extent(B, mb);
+    const Box &a = sa.all, &b = sb.all;
     const float scale = fmaxf(fmaxf(fmaxf(fabsf(a.minx), fabsf(a.maxx)), fmaxf(fabsf(a.miny), fabsf(a.maxy))),
                               fmaxf(fmaxf(fabsf(b.minx), fabsf(b.maxx)), fmaxf(fabsf(b.miny), fabsf(b.maxy))));
     const float margin = 1e-3f + 1e-5f * scale;
-    return a.minx > b.maxx + margin || b.minx > a.maxx + margin || a.miny > b.maxy + margin || b.miny > a.maxy + margin;
+    if (a.minx > b.maxx + margin || b.minx > a.maxx + margin || a.miny > b.maxy + margin || b.miny > a.maxy + margin)
+        return true;
+    // The union boxes of a long diagonal move are mostly empty.  Tighter: during a translation-only sweep each shape
+    // stays inside the disc that circumscribes its start box, carried along its motion; the discs' centres move
+    // relative to each other along one segment.  If the smallest centre distance over t in [0, 1] exceeds the two
+    // radii (plus the same generous margin), no sample of sweepHelper can find the shapes in contact.
+    const float ax = 0.5f * (sa.start.minx + sa.start.maxx), ay = 0.5f * (sa.start.miny + sa.start.maxy);
+    const float bx = 0.5f * (sb.start.minx + sb.start.maxx), by = 0.5f * (sb.start.miny + sb.start.maxy);
+    const float ra = 0.5f * sqrtf((sa.start.maxx - sa.start.minx) * (sa.start.maxx - sa.start.minx) +
+                                  (sa.start.maxy - sa.start.miny) * (sa.start.maxy - sa.start.miny));
+    const float rb = 0.5f * sqrtf((sb.start.maxx - sb.start.minx) * (sb.start.maxx - sb.start.minx) +
+                                  (sb.start.maxy - sb.start.miny) * (sb.start.maxy - sb.start.miny));
+    const float rx = ax - bx, ry = ay - by;
+    const float dx = (ma.moving ? ma.dx : 0.0f) - (mb.moving ? mb.dx : 0.0f);
+    const float dy = (ma.moving ? ma.dy : 0.0f) - (mb.moving ? mb.dy : 0.0f);
+    const float dd = dx * dx + dy * dy;
+    float t = dd > 0.0f ? -(rx * dx + ry * dy) / dd : 0.0f;
+    t = fminf(fmaxf(t, 0.0f), 1.0f);
+    const float cx = rx + t * dx, cy = ry + t * dy;
+    const float reach = (ra + rb) * 1.0001f + 2.0f * margin;
+    return cx * cx + cy * cy > reach * reach; // NaN compares false: keep the pair
 }
 
 // Phase 1: boolean test (areColliding / sweepHelper) of every binned candidate; hits are compacted per bin
@@ -827,7 +879,8 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
                 {
                     Motion moA, moB;
                     load_motions(s, p, c, moA, moB);
-                    hit = !sweep_cannot_hit(c.A, moA, c.B, moB) && sweep_search(c.A, moA, c.B, moB, fraction);
+                    hit = !sweep_cannot_hit(c.A, moA, c.B, moB, c.exactTightB ? &s.tight[p.y] : nullptr) &&
+                          sweep_search(c.A, moA, c.B, moB, fraction);
                 }
             }
         }
