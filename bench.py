@@ -450,7 +450,16 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     return out
 
 
+JSON_OUT = sys.stdout
+
+
 def main():
+    # stdout carries exactly ONE line, the JSON result: everything else that writes to fd 1 during the run (NCCL prints its
+    # version banner there, libraries may print warnings) is sent to stderr
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -484,7 +493,7 @@ def main():
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        print(json.dumps(line), file=JSON_OUT, flush=True)
         return 0
 
     weak = world > 1 and args.scaling in ("auto", "weak")
@@ -495,7 +504,7 @@ def main():
             r = run_reference(args, scene, n_dyn, as_baseline=True)
             out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")}
             out["cpu_baseline"]["ms_per_step"] = r["ms_per_step"]
-        print(json.dumps(out))
+        print(json.dumps(out), file=JSON_OUT, flush=True)
     if world > 1:
         import torch.distributed as dist
 
