@@ -846,9 +846,67 @@ __device__ __forceinline__ bool sweep_cannot_hit(const ShapeRef& A, const Motion
 // Phase 1: boolean test (areColliding / sweepHelper) of every binned candidate; hits are compacted per bin
 // into hits[binOffset[bin] + k] = (shapeA, shapeB, fraction bits, 0).  Most candidates are rejected here by
 // the cheap early-out paths, so the expensive manifold code of phase 2 runs on full warps of real hits.
+// All lanes of the warp call this; lanes with `hit` append (shapeA, shapeB, fraction) to the hit list of entry i's bin.
+__device__ __forceinline__ void append_hits(bool hit, uint32_t i, uint2 p, float fraction, FrameScratch* fs,
+                                            uint4* __restrict__ hits, int lane)
+{
+    // the bin of entry i: the binned array is the concatenation of the bins
+    int bin = 31;
+    if (hit)
+    {
+        bin = 0;
+#pragma unroll
+        for (int b = 1; b < 15; ++b)
+            bin += (i >= fs->binOffset[b]) ? 1 : 0;
+    }
+    const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (hit && lane == leader)
+        base = atomicAdd(&fs->hitCount[bin], __popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (hit)
+        hits[fs->binOffset[bin] + base + __popc(peers & ((1u << lane) - 1u))] =
+            make_uint4(p.x, p.y, __float_as_uint(fraction), 0u);
+}
+
+struct SweepTodo // a bullet candidate that survived the conservative bound and needs the real sweep search
+{
+    uint2 p;
+    uint32_t i;
+};
+
+// The sweep searches (<= 19 boolean tests each) of `count` queued candidates, one per lane.
+__device__ __forceinline__ void run_sweeps(const SweepTodo* queue, int count, const ShapeArrays& s, FrameScratch* fs,
+                                           uint4* __restrict__ hits, int lane)
+{
+    uint2 p = make_uint2(0, 0);
+    uint32_t i = 0;
+    float fraction = 0.0f;
+    bool hit = false;
+    if (lane < count)
+    {
+        p = queue[lane].p;
+        i = queue[lane].i;
+        PairCtx c;
+        load_pair(s, p, c); // accepted once already
+        Motion moA, moB;
+        load_motions(s, p, c, moA, moB);
+        hit = sweep_search(c.A, moA, c.B, moB, fraction);
+    }
+    __syncwarp();
+    append_hits(hit, i, p, fraction, fs, hits, lane);
+}
+
 __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__ binned, uint32_t capacity,
                                                        ShapeArrays s, FrameScratch* fs, uint4* __restrict__ hits)
 {
+    // Bullet candidates: the conservative bound rejects nearly all of them (98 % among 1 M static polygons), and the few
+    // survivors would each run their 19-test sweep search alone in a warp.  They are queued per warp instead and searched
+    // 32 at a time.
+    __shared__ SweepTodo queues[4][64];
+    SweepTodo* queue = queues[threadIdx.x >> 5];
+    int queued = 0; // warp-uniform
     const uint32_t n = min(fs->candCount, capacity);
     // the polygon bin of mode 0 is handled by k_narrow_filter_pp (8 lanes per pair)
     const uint32_t ppOff = fs->binOffset[CORE_PP], ppCnt = fs->binCount[CORE_PP];
@@ -862,8 +920,7 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
         const bool valid = i0 < total;
         const uint32_t i = i0 < ppOff ? i0 : i0 + ppCnt;
         uint2 p = make_uint2(0, 0);
-        float fraction = 0.0f;
-        bool hit = false;
+        bool hit = false, sweep = false;
         if (valid)
         {
             p = binned[i];
@@ -879,31 +936,29 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
                 {
                     Motion moA, moB;
                     load_motions(s, p, c, moA, moB);
-                    hit = !sweep_cannot_hit(c.A, moA, c.B, moB, c.exactTightB ? &s.tight[p.y] : nullptr) &&
-                          sweep_search(c.A, moA, c.B, moB, fraction);
+                    sweep = !sweep_cannot_hit(c.A, moA, c.B, moB, c.exactTightB ? &s.tight[p.y] : nullptr);
                 }
             }
         }
         __syncwarp();
-        // the bin of entry i: the binned array is the concatenation of the bins
-        int bin = 31;
-        if (hit)
+        append_hits(hit, i, p, 0.0f, fs, hits, lane);
+        const uint32_t todo = __ballot_sync(0xffffffffu, sweep);
+        if (todo)
         {
-            bin = 0;
-#pragma unroll
-            for (int b = 1; b < 15; ++b)
-                bin += (i >= fs->binOffset[b]) ? 1 : 0;
+            if (sweep)
+                queue[queued + __popc(todo & ((1u << lane) - 1u))] = SweepTodo{p, i};
+            queued += __popc(todo);
+            __syncwarp();
+            if (queued >= 32)
+            {
+                queued -= 32;
+                run_sweeps(queue + queued, 32, s, fs, hits, lane);
+                __syncwarp();
+            }
         }
-        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (hit && lane == leader)
-            base = atomicAdd(&fs->hitCount[bin], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (hit)
-            hits[fs->binOffset[bin] + base + __popc(peers & ((1u << lane) - 1u))] =
-                make_uint4(p.x, p.y, __float_as_uint(fraction), 0u);
     }
+    if (queued > 0)
+        run_sweeps(queue, queued, s, fs, hits, lane);
 }
 
 __global__ void k_hit_scan(FrameScratch* fs)
