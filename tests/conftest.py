@@ -11,6 +11,13 @@ if REPO not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+    # a fresh checkout has no built artefacts (they are git-ignored): build them once, in-tree, like __graft_entry__.build()
+    built = [os.path.join(REPO, "colli2de_b200", "libc2d_gpu.so"), os.path.join(REPO, "colli2de_b200", "libc2d_b200_runner.so"),
+             os.path.join(REPO, "colli2de_b200", "libc2d_snapshot_check.so"), os.path.join(REPO, "oracle", "libc2d_oracle.so")]
+    if not all(os.path.exists(p) for p in built):
+        from colli2de_b200 import build
+
+        build.build_all(force=False)
 
 
 def _have_cuda() -> bool:
