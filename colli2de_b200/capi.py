@@ -12,7 +12,7 @@ GPU_LIB = os.path.join(HERE, "libc2d_gpu.so")
 
 EXPORTS = [
     "c2d_gpu_create", "c2d_gpu_destroy", "c2d_gpu_last_error", "c2d_gpu_clear", "c2d_gpu_set_broadphase",
-    "c2d_gpu_set_shard", "c2d_gpu_set_small_scene_limit", "c2d_gpu_set_rebuild_period", "c2d_gpu_set_profiling", "c2d_gpu_kernel_profile", "c2d_gpu_shape_add",
+    "c2d_gpu_set_shard", "c2d_gpu_mutation_epoch", "c2d_gpu_set_small_scene_limit", "c2d_gpu_set_rebuild_period", "c2d_gpu_set_profiling", "c2d_gpu_kernel_profile", "c2d_gpu_shape_add",
     "c2d_gpu_shape_remove", "c2d_gpu_shape_set_active", "c2d_gpu_shape_set_ghost", "c2d_gpu_shape_translate", "c2d_gpu_shapes_translate",
     "c2d_gpu_shape_move", "c2d_gpu_stage_translations", "c2d_gpu_apply_staged", "c2d_gpu_release_staged",
     "c2d_gpu_flush", "c2d_gpu_collide", "c2d_gpu_collide_device", "c2d_gpu_collide_begin", "c2d_gpu_prefault", "c2d_gpu_collide_end",

@@ -217,6 +217,7 @@ struct c2d_gpu_ctx
     uint32_t cellSize = 120;
     uint32_t shardRank = 0, shardWorld = 1;
     uint32_t rebuildPeriod = 4; // LBVH topology rebuilt every N-th dirty frame, refit in between
+    uint64_t mutationEpoch = 0;    // bumped by every entry point that changes what a query would answer
     uint32_t smallSceneMax = 8192; // <= this many live shapes: all-pairs broadphase (c2d_gpu_set_small_scene_limit)
 
     // frame

@@ -717,6 +717,7 @@ const char* c2d_gpu_last_error(c2d_gpu_ctx* ctx)
 
 int c2d_gpu_clear(c2d_gpu_ctx* ctx)
 {
+    ++ctx->mutationEpoch;
     cudaSetDevice(ctx->device);
     C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->flagLog->size = ctx->addLog->size = ctx->transLog->size = ctx->moveLog->size = 0;
@@ -776,6 +777,13 @@ int c2d_gpu_set_rebuild_period(c2d_gpu_ctx* ctx, uint32_t frames)
     return 0;
 }
 
+int c2d_gpu_mutation_epoch(c2d_gpu_ctx* ctx, uint64_t* out_epoch)
+{
+    if (out_epoch)
+        *out_epoch = ctx->mutationEpoch;
+    return 0;
+}
+
 int c2d_gpu_set_small_scene_limit(c2d_gpu_ctx* ctx, uint32_t shapes)
 {
     ctx->smallSceneMax = shapes;
@@ -795,6 +803,7 @@ int c2d_gpu_shape_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t entity_tag, uin
                       uint32_t vertex_count, uint64_t category, uint64_t mask, const float* geom32, const c2d_xf* xf,
                       const c2d_xf* prev)
 {
+    ++ctx->mutationEpoch;
     if (type > 3 || body > 2 || vertex_count > 8 || !geom32 || !xf)
         return fail(ctx, "c2d_gpu_shape_add: bad argument");
     claim(ctx, shape, PH_ADD);
@@ -822,6 +831,7 @@ int c2d_gpu_shape_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t entity_tag, uin
 
 int c2d_gpu_shape_remove(c2d_gpu_ctx* ctx, uint32_t shape)
 {
+    ++ctx->mutationEpoch;
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
         return fail(ctx, "c2d_gpu_shape_remove: unknown shape");
     claim(ctx, shape, PH_FLAG);
@@ -837,6 +847,7 @@ int c2d_gpu_shape_remove(c2d_gpu_ctx* ctx, uint32_t shape)
 
 int c2d_gpu_shape_set_active(c2d_gpu_ctx* ctx, uint32_t shape, int active)
 {
+    ++ctx->mutationEpoch;
     // like the reference (Registry.hpp:353-358) this also works on a removed shape's stale slot
     if (shape >= ctx->hostMeta.size())
         return fail(ctx, "c2d_gpu_shape_set_active: unknown shape");
@@ -851,6 +862,7 @@ int c2d_gpu_shape_set_active(c2d_gpu_ctx* ctx, uint32_t shape, int active)
 
 int c2d_gpu_shape_set_ghost(c2d_gpu_ctx* ctx, uint32_t shape, int ghost)
 {
+    ++ctx->mutationEpoch;
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
         return fail(ctx, "c2d_gpu_shape_set_ghost: unknown shape");
     claim(ctx, shape, PH_FLAG);
@@ -864,6 +876,7 @@ int c2d_gpu_shape_set_ghost(c2d_gpu_ctx* ctx, uint32_t shape, int ghost)
 
 int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy)
 {
+    ++ctx->mutationEpoch;
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
         return fail(ctx, "c2d_gpu_shape_translate: unknown shape");
     claim(ctx, shape, PH_TRANS);
@@ -880,6 +893,7 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
 
 int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy)
 {
+    ++ctx->mutationEpoch;
     if (!ctx->transLog->reserve(ctx->transLog->size + n))
         return fail(ctx, "pinned host allocation failed");
     for (uint32_t i = 0; i < n; ++i)
@@ -890,6 +904,7 @@ int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shape
 
 int c2d_gpu_shape_move(c2d_gpu_ctx* ctx, uint32_t shape, const c2d_xf* xf)
 {
+    ++ctx->mutationEpoch;
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE) || !xf)
         return fail(ctx, "c2d_gpu_shape_move: unknown shape");
     claim(ctx, shape, PH_MOVE);
@@ -952,6 +967,7 @@ int c2d_gpu_stage_translations(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* sha
 
 int c2d_gpu_apply_staged(c2d_gpu_ctx* ctx, uint32_t handle)
 {
+    ++ctx->mutationEpoch;
     if (handle >= ctx->staged.size() || !ctx->staged[handle])
         return fail(ctx, "c2d_gpu_apply_staged: unknown handle");
     const StagedBatch* sb = ctx->staged[handle];
@@ -1288,6 +1304,7 @@ int c2d_gpu_read_shapes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, uint8_
 
 int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const float* tight4, const float* fat4)
 {
+    ++ctx->mutationEpoch;
     cudaSetDevice(ctx->device);
     if (int rc = flush(ctx))
         return rc;

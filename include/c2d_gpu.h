@@ -125,6 +125,10 @@ int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size);
  * rebuilt every `frames`-th dirty frame and only refit (exact boxes, bottom-up) in between.  1 = rebuild every
  * frame.  Default 4.  Results do not depend on it. */
 int c2d_gpu_set_rebuild_period(c2d_gpu_ctx* ctx, uint32_t frames);
+/* A counter bumped by every call that changes what a query would answer (add / remove / activate / ghost / translate /
+ * move / apply_staged / clear / write_boxes).  Equal epochs = identical answers: lets a host layer memoise query results
+ * (c2d::Registry caches the per-entity results of getCollisions() between mutations). */
+int c2d_gpu_mutation_epoch(c2d_gpu_ctx* ctx, uint64_t* out_epoch);
 /* Scenes with at most `shapes` live shapes skip the tree pipeline: one all-pairs box-test kernel over the member
  * lists and one narrowphase kernel (same candidate predicate, same results) - the ~30 dependent launches of the
  * tree pipeline cost more than the work at that size.  Default 8192; 0 disables the shortcut. */

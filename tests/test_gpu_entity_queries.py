@@ -88,3 +88,40 @@ def test_get_collisions_batch_equals_the_single_calls(monkeypatch):
         gpu.lib.rn_copy_pairs(gpu.ctx, batch.ctypes.data_as(__import__("ctypes").c_void_p))
     assert total == len(singles) > 100
     assert P.sort_pairs(batch).tobytes() == P.sort_pairs(singles).tobytes()
+
+
+@pytest.mark.parametrize("oracle", ORACLES)
+def test_get_collisions_memoised_between_mutations(oracle):
+    """After a few single getCollisions() calls without a mutation the Registry fetches the collisions of ALL entities in
+    one device pass and serves further calls from that table (c2d_gpu_mutation_epoch); any mutation invalidates it."""
+    sc = _scene()
+    ref, gpu = _prepare(oracle, sc), _prepare(SUBJECT, sc)
+    ids = np.arange(0, 6600, 11, dtype=np.uint32)
+
+    def check(entities):
+        for e in entities.tolist():
+            a, b = P.sort_pairs(ref.get_collisions(e)), P.sort_pairs(gpu.get_collisions(e))
+            assert np.array_equal(P.pair_keys(a), P.pair_keys(b)), e
+            assert P.manifold_close(a, b).all(), e
+
+    check(ids[:40])  # calls 5.. come out of the table
+    total, sec = gpu.get_collisions_many(ids)  # 600 more calls, all table lookups now
+    assert total > 100 and sec < 0.02, (total, sec)  # 600 device round trips would take ~18 ms
+    # a move invalidates the table: the mover's neighbours see it at once
+    mover = int(ids[3])
+    target = ref.get_transforms(np.uint32([int(ids[5])]))[0, :2]
+    for b in (ref, gpu):
+        b.teleport_translation(np.uint32([mover]), target[None, :])
+    check(np.uint32([mover, int(ids[5])]))
+    check(ids[:12])
+    # an entity created after the table was built, with and without shapes
+    for b in (ref, gpu):
+        b.create_entities(np.uint32([777001]), np.uint8([1]), np.float32([[5.0, 5.0, 0.0]]))
+    check(ids[:8])
+    assert len(gpu.get_collisions(777001)) == 0
+    g = np.zeros((1, 16), np.float32)
+    g[0, 2] = 30.0
+    for b in (ref, gpu):
+        b.add_shapes(np.uint32([777001]), np.uint8([0]), g)
+    check(np.uint32([777001]))
+    assert len(gpu.get_collisions(777001)) > 3

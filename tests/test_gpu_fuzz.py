@@ -173,7 +173,8 @@ def check_queries(rng, w, ref, gpu, ref_grid=None):
     ents = np.asarray(sorted(w.live_entities), np.uint32)
     assert np.array_equal(ref.get_transforms(ents).view(np.uint32), gpu.get_transforms(ents).view(np.uint32))
     # per-entity queries on a few entities (records are (queried shape, other): compare as sorted records)
-    for e in some(rng, w.live_entities, 0.0, 4).tolist():
+    # nine single calls without a mutation in between: the drop-in Registry answers the last ones from its memoised table
+    for e in some(rng, w.live_entities, 0.0, 9).tolist():
         a, _ = drop_ghost_pairs(w, ref.get_collisions(e))
         a, b = np.unique(P.pair_keys(a)), np.unique(P.pair_keys(gpu.get_collisions(e)))  # Grid: once per shared cell
         assert np.array_equal(a, b), e
