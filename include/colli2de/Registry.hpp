@@ -32,6 +32,7 @@
 
 #include <c2d_gpu.h>
 
+#include <algorithm>
 #include <bit>
 #include <cmath>
 #include <cstddef>
@@ -444,6 +445,18 @@ class Registry
             id = mEntities[h.entity].id;
         return RayHit{{id, h.shape}, Vec2{h.entry[0], h.entry[1]}, Vec2{h.exit[0], h.exit[1]}, h.entryTime, h.exitTime};
     }
+    EntityCollision toCollision(const c2d_pair_record& r) const
+    {
+        EntityId a, b;
+        if constexpr (kDirectTag)
+            a = std::bit_cast<EntityId>(r.entityA), b = std::bit_cast<EntityId>(r.entityB);
+        else
+            a = mEntities[r.entityA].id, b = mEntities[r.entityB].id;
+        EntityCollision c{a, b, r.shapeA, r.shapeB, Manifold{}};
+        static_assert(sizeof(Manifold) == sizeof(c2d_manifold));
+        std::memcpy(static_cast<void*>(&c.manifold), &r.manifold, sizeof(Manifold));
+        return c;
+    }
     std::vector<EntityCollision> toCollisions(const c2d_pair_record* records, uint64_t count) const
     {
         if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
@@ -515,7 +528,6 @@ class Registry
         uint32_t singleCalls = 0;
         bool built = false;
         std::vector<uint64_t> offsets; // per dense entity index
-        std::vector<uint32_t> order;
         std::vector<EntityCollision> records;
     };
     mutable CollisionCache mCollisionCache;
@@ -844,10 +856,10 @@ std::span<const typename Registry<EntityId, Method>::EntityCollision> Registry<E
 //
 // A single call is a device round trip (~30 us whatever the scene size), three orders of magnitude above the
 // reference's pointer walk on a small scene.  Applications (and the reference's own benchmark) call it in loops over
-// many entities between mutations, so the results are memoised: after kCollisionCacheWarmup single calls without an
-// intervening mutation (c2d_gpu_mutation_epoch) the next call asks the device for the collisions of ALL entities in
-// one pass, keeps them grouped by entity on the host, and every further call until the next mutation is a copy out of
-// that table.
+// many entities between mutations, so the results are memoised: once the single calls of an epoch (no intervening
+// mutation, c2d_gpu_mutation_epoch) have cost about what one pass over ALL entities costs, the next call asks the
+// device for everybody's collisions, keeps them grouped by entity on the host, and every further call until the next
+// mutation is a copy out of that table.
 template <typename EntityId, PartitioningMethod Method>
 std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<EntityId, Method>::getCollisions(
     EntityId id) const
@@ -863,7 +875,9 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
         cache.singleCalls = 0;
         cache.built = false;
     }
-    if (!cache.built && ++cache.singleCalls > kCollisionCacheWarmup)
+    // ski rental: a single call costs one device round trip, the table roughly one per 64 live shapes — switch once the
+    // calls of this epoch have cost about as much as the table would (never more than twice the best strategy)
+    if (!cache.built && ++cache.singleCalls > std::max<uint64_t>(kCollisionCacheWarmup, mShapes.size() / 64))
     {
         // all live shapes in one device pass; records are (queried shape, other shape): group by the queried entity
         std::vector<uint32_t> shapes;
@@ -880,14 +894,9 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
         for (size_t e = 0; e < mEntities.size(); ++e)
             cache.offsets[e + 1] += cache.offsets[e];
         std::vector<uint64_t> cursor(cache.offsets.begin(), cache.offsets.end() - 1);
-        cache.order.resize(count);
+        cache.records.resize(count);
         for (uint64_t i = 0; i < count; ++i)
-            cache.order[cursor[mShapes[records[i].shapeA].entity]++] = static_cast<uint32_t>(i);
-        const std::vector<EntityCollision> all = toCollisions(records, count);
-        cache.records.clear();
-        cache.records.reserve(count);
-        for (uint64_t i = 0; i < count; ++i)
-            cache.records.push_back(all[cache.order[i]]);
+            cache.records[cursor[mShapes[records[i].shapeA].entity]++] = toCollision(records[i]);
         cache.built = true;
     }
     if (cache.built && idx + 1 >= cache.offsets.size())

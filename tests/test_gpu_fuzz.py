@@ -165,16 +165,23 @@ def check_queries(rng, w, ref, gpu, ref_grid=None):
     assert ghosts == 0, "the reference's None registry never reports removed shapes"
     got_pairs = gpu.get_colliding_pairs()
     res = P.compare_pairs(ORACLE, ref, idx, ref_pairs, got_pairs)
-    if ref_grid is not None:
-        grid_pairs, _ = drop_ghost_pairs(w, ref_grid.get_colliding_pairs())
-        assert pair_set(grid_pairs) <= pair_set(got_pairs), "the reference's Grid registry reports a pair we do not"
+    if ref_grid is not None and not getattr(ref_grid, "broken", False):
+        try:
+            grid_pairs, _ = drop_ghost_pairs(w, ref_grid.get_colliding_pairs())
+        except RuntimeError:
+            # the leaked cell leaves (see drop_ghost_pairs) now name an entity that is gone: the reference throws from
+            # its entity map.  Its Grid registry is not consulted any further; the comparison with the None registry goes on.
+            ref_grid.broken = True
+        else:
+            assert pair_set(grid_pairs) <= pair_set(got_pairs), "the reference's Grid registry reports a pair we do not"
     assert res["not_bit_identical"] == 0, res
     assert ref.size() == gpu.size() == len(w.live_entities)
     ents = np.asarray(sorted(w.live_entities), np.uint32)
     assert np.array_equal(ref.get_transforms(ents).view(np.uint32), gpu.get_transforms(ents).view(np.uint32))
     # per-entity queries on a few entities (records are (queried shape, other): compare as sorted records)
-    # nine single calls without a mutation in between: the drop-in Registry answers the last ones from its memoised table
-    for e in some(rng, w.live_entities, 0.0, 9).tolist():
+    # two dozen single calls without a mutation in between: the drop-in Registry answers the later ones from its memoised
+    # table (it switches after max(4, live shapes / 64) calls)
+    for e in some(rng, w.live_entities, 0.0, 24).tolist():
         a, _ = drop_ghost_pairs(w, ref.get_collisions(e))
         a, b = np.unique(P.pair_keys(a)), np.unique(P.pair_keys(gpu.get_collisions(e)))  # Grid: once per shared cell
         assert np.array_equal(a, b), e
@@ -202,6 +209,7 @@ def test_random_api_sequences(seed):
     for step in range(7):
         random_step(rng, w, backends, teleports=method == 0)
         total += check_queries(rng, w, ref, gpu, ref_grid)
+        backends = tuple(b for b in backends if not getattr(b, "broken", False))  # a thrown reference Grid registry is out
         if step == 2:
             # snapshot mid-script: the reloaded registry joins the script and must stay indistinguishable
             twin = H.Backend.deserialize("b200", gpu.serialize(), method=method)

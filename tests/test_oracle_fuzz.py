@@ -11,7 +11,7 @@ needs = pytest.mark.skipif(not (H.available("reference") and H.available("oracle
 
 
 @needs
-@pytest.mark.parametrize("seed", range(8))
+@pytest.mark.parametrize("seed", range(12))
 def test_oracle_follows_reference_through_random_scripts(seed, monkeypatch):
     monkeypatch.setenv("C2D_DRYRUN_CANON", "1")  # the oracle reports same-tree pairs in its own orientation
     rng = np.random.default_rng(1000 + seed)
@@ -25,4 +25,5 @@ def test_oracle_follows_reference_through_random_scripts(seed, monkeypatch):
     for _ in range(7):
         F.random_step(rng, w, backends, teleports=method == 0)
         total += F.check_queries(rng, w, ref, sub, ref_grid)
+        backends = tuple(b for b in backends if not getattr(b, "broken", False))  # a thrown reference Grid registry is out
     assert total > 100
