@@ -875,9 +875,9 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
         cache.singleCalls = 0;
         cache.built = false;
     }
-    // ski rental: a single call costs one device round trip, the table roughly one per 64 live shapes — switch once the
+    // ski rental: a single call costs one device round trip, the table roughly one per 128 live shapes — switch once the
     // calls of this epoch have cost about as much as the table would (never more than twice the best strategy)
-    if (!cache.built && ++cache.singleCalls > std::max<uint64_t>(kCollisionCacheWarmup, mShapes.size() / 64))
+    if (!cache.built && ++cache.singleCalls > std::max<uint64_t>(kCollisionCacheWarmup, mShapes.size() / 128))
     {
         // all live shapes in one device pass; records are (queried shape, other shape): group by the queried entity
         std::vector<uint32_t> shapes;

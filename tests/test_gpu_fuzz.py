@@ -180,7 +180,7 @@ def check_queries(rng, w, ref, gpu, ref_grid=None):
     assert np.array_equal(ref.get_transforms(ents).view(np.uint32), gpu.get_transforms(ents).view(np.uint32))
     # per-entity queries on a few entities (records are (queried shape, other): compare as sorted records)
     # two dozen single calls without a mutation in between: the drop-in Registry answers the later ones from its memoised
-    # table (it switches after max(4, live shapes / 64) calls)
+    # table (it switches after max(4, live shapes / 128) calls)
     for e in some(rng, w.live_entities, 0.0, 24).tolist():
         a, _ = drop_ghost_pairs(w, ref.get_collisions(e))
         a, b = np.unique(P.pair_keys(a)), np.unique(P.pair_keys(gpu.get_collisions(e)))  # Grid: once per shared cell
