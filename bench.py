@@ -370,7 +370,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                           np.where(scene["shp_type"] == 0, 12, np.where(scene["shp_type"] == 1, 20, 16))).mean())
     alg = {
         # per-launch algorithmic bytes of each kernel (DESIGN.md "Roofline")
-        "k_apply_translates": n_dyn * (16 + 4 + 16 + 16 + 16 + 16 + 16 + 16),
+        "k_apply_translates": n_dyn * (12 + 4 + 16 + 16 + 16 + 16 + 16 + 16),
         "k_traverse<self>": n_dyn * (4 + 16 + 8) + (n_dyn - 1) * 64 + 0.8 * cand_per_frame * 8,
         "k_traverse<cross>": n_dyn * (4 + 16 + 8) + (n_sta - 1) * 64 + 0.2 * cand_per_frame * 8,
         # narrowphase: the polygon bin (polygon vs polygon|capsule|segment) holds ~45 % of the candidates of this mix
@@ -424,7 +424,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
                                    f"loop exchanges the boundary moves with one NCCL all-gather per frame "
                                    f"(rank 0 slab: {n_dyn} dynamic + {n_sta} static incl. halo)" if weak else
                                    f"strong: fixed workload mirrored on {world} GPUs, query leaves sharded by Morton-rank slab"),
-                   "l2": "inputs larger than L2 (fresh 16 MB move batch per frame; ~255 MB shape state + ~100 MB "
+                   "l2": "inputs larger than L2 (fresh 12 MB move batch per frame; ~255 MB shape state + ~100 MB "
                          "sort/tree buffers rewritten every frame vs 126 MB L2), no explicit flush",
                    "lbvh_rebuild_period": args.rebuild_period,
                    "broadphase": f"uniform grid, cell {args.grid_cell}" if args.grid_cell > 0 else "LBVH",

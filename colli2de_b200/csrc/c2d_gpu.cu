@@ -886,7 +886,6 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
     r->shape = shape;
     r->dx = dx;
     r->dy = dy;
-    r->_pad = 0;
     ctx->treeDirty[meta_body(ctx->hostMeta[shape])] = true;
     return 0;
 }
@@ -942,7 +941,7 @@ int c2d_gpu_stage_translations(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* sha
         }
         seen[s] = 1;
         sb->touches[meta_body(ctx->hostMeta[s])] = true;
-        host[i] = TransRec{s, dxy[2 * i], dxy[2 * i + 1], 0u};
+        host[i] = TransRec{s, dxy[2 * i], dxy[2 * i + 1]};
     }
     sb->n = n;
     sb->live = true;

@@ -30,11 +30,10 @@ struct FlagRec // 8 B: remove / activate / deactivate
     uint32_t shape;
     uint32_t op; // 0 remove, 1 activate, 2 deactivate, 3 mark ghost, 4 clear ghost
 };
-struct TransRec // 16 B: moveEntity(id, Translation) for one shape
+struct TransRec // 12 B: moveEntity(id, Translation) for one shape (the bulk of a frame's upload: no padding)
 {
     uint32_t shape;
     float dx, dy;
-    uint32_t _pad;
 };
 struct MoveRec // 32 B: moveEntity(id, Transform) / teleportEntity(id, Transform) for one shape
 {
@@ -49,7 +48,7 @@ struct AddRec // 224 B: addShape
     float prev[8]; // previous transform (bullets)
     float geom[32];
 };
-static_assert(sizeof(FlagRec) == 8 && sizeof(TransRec) == 16 && sizeof(MoveRec) == 32 && sizeof(AddRec) == 224,
+static_assert(sizeof(FlagRec) == 8 && sizeof(TransRec) == 12 && sizeof(MoveRec) == 32 && sizeof(AddRec) == 224,
               "log record layout");
 
 // ---- per-shape state in HBM (SoA) ---------------------------------------------------------------------

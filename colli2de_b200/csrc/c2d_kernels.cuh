@@ -108,9 +108,9 @@ __global__ void __launch_bounds__(256) k_apply_translates(const TransRec* __rest
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
-    const float4 raw = reinterpret_cast<const float4*>(log)[i];
-    const uint32_t shape = __float_as_uint(raw.x);
-    const float dx = raw.y, dy = raw.z;
+    const TransRec rec = log[i]; // 12-byte records: three coalesced 4-byte loads per thread
+    const uint32_t shape = rec.shape;
+    const float dx = rec.dx, dy = rec.dy;
     const uint32_t meta = s.meta[shape];
     const bool bullet = meta_body(meta) == 2u;
     if (meta & META_TIGHT_EXACT)
