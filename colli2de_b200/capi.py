@@ -18,7 +18,7 @@ EXPORTS = [
     "c2d_gpu_flush", "c2d_gpu_collide", "c2d_gpu_collide_device", "c2d_gpu_collide_begin", "c2d_gpu_prefault", "c2d_gpu_collide_end",
     "c2d_gpu_collide_fetch", "c2d_gpu_device_records", "c2d_gpu_raycast", "c2d_gpu_raycast_first", "c2d_gpu_raycast_begin", "c2d_gpu_raycast_fetch",
     "c2d_gpu_query_shapes", "c2d_gpu_pairs_colliding", "c2d_gpu_read_boxes", "c2d_gpu_read_shapes", "c2d_gpu_write_boxes",
-    "c2d_gpu_read_candidates", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
+    "c2d_gpu_read_candidates", "c2d_gpu_shape_slots", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
     "c2d_gpu_compute_aabb_batch",
 ]
 

@@ -204,7 +204,8 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
     if (ctx->rounds.empty())
         return 0;
     cudaStream_t s = ctx->stream;
-    if (int rc = ensure_shape_capacity(ctx, ctx->shapeSlots))
+    // every id the host tables accept (c2d_gpu_shape_set_active on a stale slot, Registry.hpp:353-358) must be addressable
+    if (int rc = ensure_shape_capacity(ctx, std::max<uint32_t>(ctx->shapeSlots, static_cast<uint32_t>(ctx->hostMeta.size()))))
         return rc;
     const size_t nf = ctx->flagLog->size, na = ctx->addLog->size, nt = ctx->transLog->size, nm = ctx->moveLog->size;
     if (nf)
@@ -1258,8 +1259,12 @@ int c2d_gpu_read_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* 
     cudaSetDevice(ctx->device);
     if (int rc = flush(ctx))
         return rc;
-    if (static_cast<uint64_t>(first) + count > ctx->capacity)
+    // a snapshot's shape table may end in freed ids the device never saw (all shapes removed, or trailing free ids
+    // past a capacity step): the arrays grow to the requested range (zero-filled = dead shapes)
+    if (static_cast<uint64_t>(first) + count > 0xffffffffull)
         return fail(ctx, "c2d_gpu_read_boxes: range out of bounds");
+    if (int rc = ensure_shape_capacity(ctx, first + count))
+        return rc;
     if (out_tight4)
         C2D_CUDA(ctx, cudaMemcpyAsync(out_tight4, ctx->d.tight + first, count * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     if (out_fat4)
@@ -1274,8 +1279,12 @@ int c2d_gpu_read_shapes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, uint8_
     cudaSetDevice(ctx->device);
     if (int rc = flush(ctx))
         return rc;
-    if (static_cast<uint64_t>(first) + count > ctx->capacity)
+    // a snapshot's shape table may end in freed ids the device never saw (all shapes removed, or trailing free ids
+    // past a capacity step): the arrays grow to the requested range (zero-filled = dead shapes)
+    if (static_cast<uint64_t>(first) + count > 0xffffffffull)
         return fail(ctx, "c2d_gpu_read_shapes: range out of bounds");
+    if (int rc = ensure_shape_capacity(ctx, first + count))
+        return rc;
     cudaStream_t s = ctx->stream;
     std::vector<uint32_t> meta(count);
     if (count)
@@ -1307,8 +1316,12 @@ int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const 
     cudaSetDevice(ctx->device);
     if (int rc = flush(ctx))
         return rc;
-    if (static_cast<uint64_t>(first) + count > ctx->capacity)
+    // a snapshot's shape table may end in freed ids the device never saw (all shapes removed, or trailing free ids
+    // past a capacity step): the arrays grow to the requested range (zero-filled = dead shapes)
+    if (static_cast<uint64_t>(first) + count > 0xffffffffull)
         return fail(ctx, "c2d_gpu_write_boxes: range out of bounds");
+    if (int rc = ensure_shape_capacity(ctx, first + count))
+        return rc;
     cudaStream_t s = ctx->stream;
     if (tight4 && count)
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->d.tight + first, tight4, count * sizeof(float4), cudaMemcpyHostToDevice, s));
@@ -1322,6 +1335,13 @@ int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const 
         ctx->treeDirty[body] = true; // every leaf box may have changed: rebuild, do not just refit
         ctx->tree[body].membershipChanged = true;
     }
+    return 0;
+}
+
+int c2d_gpu_shape_slots(c2d_gpu_ctx* ctx, uint32_t* out_slots)
+{
+    if (out_slots)
+        *out_slots = ctx->shapeSlots;
     return 0;
 }
 

@@ -252,6 +252,8 @@ int c2d_gpu_read_shapes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, uint8_
  * box is shifted by translations, the leaf box follows the fat-leaf rule), so they cannot be recomputed.  Either
  * pointer may be NULL.  Flushes first; the next query rebuilds the trees. */
 int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const float* tight4, const float* fat4);
+/* 1 + the highest ShapeId ever added (the size of the reference's mShapes table, Registry.hpp:159). */
+int c2d_gpu_shape_slots(c2d_gpu_ctx* ctx, uint32_t* out_slots);
 /* Broadphase candidate pairs of the last c2d_gpu_collide call (shapeA, shapeB), unsorted. */
 int c2d_gpu_read_candidates(c2d_gpu_ctx* ctx, uint64_t capacity, uint32_t* out_pairs2, uint64_t* out_count);
 

@@ -309,7 +309,13 @@ class Registry
     std::span<const EntityCollision> getCollidingPairsView();
     // Multi-GPU slabs: marks a shape as the halo copy of a shape owned by another rank's Registry (see
     // c2d_gpu_shape_set_ghost in c2d_gpu.h for the owner rule that keeps the union of the ranks' results duplicate free).
-    void setShapeGhost(ShapeId shapeId, bool isGhost = true) { check(c2d_gpu_shape_set_ghost(mCtx, shapeId, isGhost ? 1 : 0)); }
+    // The owner rule compares entity tags across ranks, so the tags must be global: only EntityIds that travel as their
+    // own 32-bit pattern qualify (any other id type is a rank-local dense index on the device).
+    void setShapeGhost(ShapeId shapeId, bool isGhost = true)
+    {
+        static_assert(kDirectTag, "setShapeGhost needs a 4-byte trivially copyable EntityId (global entity tags)");
+        check(c2d_gpu_shape_set_ghost(mCtx, shapeId, isGhost ? 1 : 0));
+    }
     // Counters and CUDA-event timings of the last getCollidingPairs() / rayCast().
     const c2d_gpu_stats& lastQueryStats() const { return mStats; }
     // Runs the pipeline but leaves the records on the device; returns the number of colliding pairs.
@@ -578,6 +584,8 @@ ShapeId Registry<EntityId, Method>::addShape(EntityId entityId, const Shape& sha
                                              uint64_t maskBits)
 {
     syncHost();
+    // a live staged batch captured the entity's shape list: a new shape would be left behind by applyStagedMoves()
+    ++mStructureEpoch;
     const uint32_t idx = indexOf(entityId);
     C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
     EntityInfo& entity = mEntities[idx];
@@ -618,7 +626,8 @@ ShapeId Registry<EntityId, Method>::addShape(EntityId entityId, const Shape& sha
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::removeShape(ShapeId shapeId)
 {
-    C2D_DEBUG_ASSERT(shapeId < mShapes.size(), "Shape ID out of bounds");
+    if (shapeId >= mShapes.size()) // the reference indexes with .at() (Registry.hpp:334)
+        throw std::out_of_range("colli2de-b200: removeShape: shape id out of range");
     syncHost();
     ++mStructureEpoch;
     ShapeLink& link = mShapes[shapeId];
@@ -640,7 +649,8 @@ void Registry<EntityId, Method>::removeShape(ShapeId shapeId)
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::setShapeActive(ShapeId shapeId, bool isActive)
 {
-    C2D_DEBUG_ASSERT(shapeId < mShapes.size(), "Shape ID out of bounds");
+    if (shapeId >= mShapes.size())
+        throw std::out_of_range("colli2de-b200: setShapeActive: shape id out of range");
     check(c2d_gpu_shape_set_active(mCtx, shapeId, isActive ? 1 : 0));
 }
 
@@ -762,7 +772,7 @@ void Registry<EntityId, Method>::applyStagedMoves(MoveBatch batch)
     if (batch >= mStaged.size() || !mStaged[batch].live)
         throw std::runtime_error("colli2de-b200: applyStagedMoves: unknown batch");
     if (mStaged[batch].epoch != mStructureEpoch)
-        throw std::runtime_error("colli2de-b200: applyStagedMoves: shapes were removed since the batch was staged");
+        throw std::runtime_error("colli2de-b200: applyStagedMoves: shapes were added or removed since the batch was staged");
     check(c2d_gpu_apply_staged(mCtx, mStaged[batch].handle));
     mPendingApplies.push_back(batch);
 }
@@ -773,9 +783,9 @@ void Registry<EntityId, Method>::releaseStagedMoves(MoveBatch batch)
     if (batch >= mStaged.size() || !mStaged[batch].live)
         return;
     syncHost();
-    if (mStaged[batch].epoch == mStructureEpoch || true)
-        c2d_gpu_release_staged(mCtx, mStaged[batch].handle);
+    const uint32_t handle = mStaged[batch].handle;
     mStaged[batch] = StagedMoves{};
+    check(c2d_gpu_release_staged(mCtx, handle));
 }
 
 template <typename EntityId, PartitioningMethod Method>
@@ -831,6 +841,7 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
         const c2d_pair_record* records = nullptr;
         uint64_t count = 0;
         check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
+        mPreviousAllCollisionsCount = static_cast<uint32_t>(count);
         return toCollisions(records, count);
     }
 }
@@ -841,6 +852,7 @@ std::span<const typename Registry<EntityId, Method>::EntityCollision> Registry<E
     const c2d_pair_record* records = nullptr;
     uint64_t count = 0;
     check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
+    mPreviousAllCollisionsCount = static_cast<uint32_t>(count);
     if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
                   std::is_trivially_copyable_v<EntityCollision>)
         return std::span<const EntityCollision>(reinterpret_cast<const EntityCollision*>(records), count);

@@ -780,6 +780,7 @@ struct rn_ctx
     pairrec_t* pairs; uint64_t npairs, cappairs;
     hitrec_t* hits; uint64_t nhits, caphits;
     staged_t* staged; uint32_t nstaged;
+    uint32_t* cands; uint64_t ncands; /* last rn_candidates */
     char error[256];
 };
 
@@ -838,7 +839,7 @@ void rn_destroy(rn_ctx* c)
     if (!c) return;
     rn_clear(c);
     for (uint32_t i = 0; i < c->nstaged; ++i) { free(c->staged[i].ids); free(c->staged[i].dxy); }
-    free(c->staged); free(c->pairs); free(c->hits); free(c);
+    free(c->staged); free(c->pairs); free(c->hits); free(c->cands); free(c);
 }
 const char* rn_last_error(rn_ctx* c) { return c->error; }
 uint64_t rn_size(rn_ctx* c) { return c->live; }
@@ -1112,20 +1113,17 @@ static void narrow_phase(rn_ctx* c, uint32_t sa, uint32_t sb)
     r->eA = ea->id; r->eB = eb->id; r->sA = sa; r->sB = sb; r->m = m;
 }
 
-uint64_t rn_get_colliding_pairs(rn_ctx* c, double* seconds)
+/* broadphase: sort-and-sweep on the leaf boxes; candidate iff boxes intersect (non-strict) and
+ * (categoryA & categoryB) != 0 (DynamicBVH.hpp:944-964).  Fills the five groups of Registry.hpp:487-545, each sorted. */
+static void broadphase_groups(rn_ctx* c, cand_t* cand[5], uint64_t ncand[5])
 {
-    struct timespec t0, t1;
-    clock_gettime(CLOCK_MONOTONIC, &t0);
-    c->npairs = 0;
-    /* broadphase: sort-and-sweep on the leaf boxes; candidate iff boxes intersect (non-strict) and
-     * (categoryA & categoryB) != 0 (DynamicBVH.hpp:944-964) */
     uint32_t n = 0;
     sweepitem_t* items = (sweepitem_t*)malloc(sizeof(sweepitem_t) * (c->nshapes ? c->nshapes : 1));
     for (uint32_t s = 0; s < c->nshapes; ++s)
         if (c->shapes[s].alive) { items[n].minx = c->shapes[s].fat.minx; items[n].shape = s; ++n; }
     qsort(items, n, sizeof(sweepitem_t), cmp_sweep);
-    cand_t* cand[5] = {0, 0, 0, 0, 0};
-    uint64_t ncand[5] = {0, 0, 0, 0, 0}, capcand[5] = {0, 0, 0, 0, 0};
+    uint64_t capcand[5] = {0, 0, 0, 0, 0};
+    for (int g = 0; g < 5; ++g) { cand[g] = NULL; ncand[g] = 0; }
     for (uint32_t i = 0; i < n; ++i)
     {
         const uint32_t si = items[i].shape;
@@ -1148,8 +1146,19 @@ uint64_t rn_get_colliding_pairs(rn_ctx* c, double* seconds)
     }
     free(items);
     for (int g = 0; g < 5; ++g)
-    {
         qsort(cand[g], ncand[g], sizeof(cand_t), cmp_cand); /* std::sort of each group, Registry.hpp:495-533 */
+}
+
+uint64_t rn_get_colliding_pairs(rn_ctx* c, double* seconds)
+{
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    c->npairs = 0;
+    cand_t* cand[5];
+    uint64_t ncand[5];
+    broadphase_groups(c, cand, ncand);
+    for (int g = 0; g < 5; ++g)
+    {
         for (uint64_t k = 0; k < ncand[g]; ++k) narrow_phase(c, cand[g][k].a, cand[g][k].b);
         free(cand[g]);
     }
@@ -1157,6 +1166,37 @@ uint64_t rn_get_colliding_pairs(rn_ctx* c, double* seconds)
     if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
     return c->npairs;
 }
+
+/* ---- secondary oracles ---------------------------------------------- */
+uint32_t rn_shape_slots(rn_ctx* c) { return c->nshapes; }
+void rn_read_boxes(rn_ctx* c, uint32_t first, uint32_t count, float* tight4, float* fat4, uint8_t* alive)
+{
+    for (uint32_t i = 0; i < count; ++i)
+    {
+        if (first + i >= c->nshapes) { snprintf(c->error, sizeof(c->error), "rn_read_boxes: shape id out of range"); return; }
+        const inst_t* I = &c->shapes[first + i];
+        if (tight4) { tight4[4 * i] = I->tight.minx; tight4[4 * i + 1] = I->tight.miny; tight4[4 * i + 2] = I->tight.maxx; tight4[4 * i + 3] = I->tight.maxy; }
+        if (fat4) { fat4[4 * i] = I->fat.minx; fat4[4 * i + 1] = I->fat.miny; fat4[4 * i + 2] = I->fat.maxx; fat4[4 * i + 3] = I->fat.maxy; }
+        if (alive) alive[i] = I->alive ? 1 : 0;
+    }
+}
+uint64_t rn_candidates(rn_ctx* c)
+{
+    cand_t* cand[5];
+    uint64_t ncand[5], total = 0;
+    broadphase_groups(c, cand, ncand);
+    for (int g = 0; g < 5; ++g) total += ncand[g];
+    free(c->cands);
+    c->cands = (uint32_t*)malloc(sizeof(uint32_t) * 2 * (total ? total : 1));
+    c->ncands = 0;
+    for (int g = 0; g < 5; ++g)
+    {
+        for (uint64_t k = 0; k < ncand[g]; ++k) { c->cands[2 * c->ncands] = cand[g][k].a; c->cands[2 * c->ncands + 1] = cand[g][k].b; ++c->ncands; }
+        free(cand[g]);
+    }
+    return c->ncands;
+}
+void rn_copy_candidates(rn_ctx* c, uint32_t* out) { if (c->ncands) memcpy(out, c->cands, c->ncands * 2 * sizeof(uint32_t)); }
 uint64_t rn_count_colliding_pairs_device(rn_ctx* c, double* seconds) { return rn_get_colliding_pairs(c, seconds); }
 uint64_t rn_get_colliding_pairs_view(rn_ctx* c, double* seconds, const void** records)
 {

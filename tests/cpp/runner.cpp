@@ -8,8 +8,7 @@
 // C-ABI (c2d_gpu_*_batch), i.e. to the CUDA narrowphase.
 #include "runner_api.h"
 
-#include <colli2de/Registry.hpp>
-
+#include <algorithm>
 #include <array>
 #include <chrono>
 #include <cstdlib>
@@ -21,6 +20,39 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+
+#if defined(RN_BACKEND_REF)
+// The secondary oracles of SURVEY.md section 8(c) item 5 (tight boxes, leaf boxes, broadphase candidates) live in
+// private members of the reference's Registry (mShapes / mShapeTreeHandles / mTrees).  The reference sources stay
+// untouched: its headers are read with `private` spelled `public` (access does not change layout or mangling), after
+// every standard header they use has been included normally.
+#include <cassert>
+#include <cmath>
+#include <cstddef>
+#include <cstdint>
+#include <execution>
+#include <format>
+#include <functional>
+#include <iostream>
+#include <istream>
+#include <limits>
+#include <map>
+#include <memory_resource>
+#include <optional>
+#include <ostream>
+#include <print>
+#include <ranges>
+#include <set>
+#include <thread>
+#include <tsl/robin_map.h>
+#include <utility>
+#include <variant>
+#define private public
+#include <colli2de/Registry.hpp>
+#undef private
+#else
+#include <colli2de/Registry.hpp>
+#endif
 
 #if defined(RN_BACKEND_B200)
 #include <c2d_gpu.h>
@@ -141,6 +173,10 @@ struct IRegistry
                               uint64_t* offsets, std::vector<HitRec>& out, double* apiSeconds) const = 0;
     virtual size_t size() const = 0;
     virtual void clear() = 0;
+    // secondary oracles: shape table size, per-shape tight / leaf boxes + alive flag, broadphase candidate pairs
+    virtual uint32_t shapeSlots() = 0;
+    virtual void readBoxes(uint32_t first, uint32_t count, float* tight4, float* fat4, uint8_t* alive) = 0;
+    virtual void candidates(std::vector<std::pair<uint32_t, uint32_t>>& out) = 0;
     virtual void serialize(std::string& out) const = 0;
     virtual bool equals(const IRegistry& other) const = 0;
 };
@@ -327,7 +363,103 @@ struct RegistryHolder final : IRegistry
     {
         reg.releaseStagedMoves(static_cast<uint32_t>(handle));
     }
+    static void gpuCheck(c2d_gpu_ctx* g, int rc)
+    {
+        if (rc != 0)
+            throw std::runtime_error(c2d_gpu_last_error(g));
+    }
+    uint32_t shapeSlots() override
+    {
+        uint32_t n = 0;
+        gpuCheck(reg.nativeContext(), c2d_gpu_shape_slots(reg.nativeContext(), &n));
+        return n;
+    }
+    void readBoxes(uint32_t first, uint32_t count, float* tight4, float* fat4, uint8_t* alive) override
+    {
+        c2d_gpu_ctx* g = reg.nativeContext();
+        gpuCheck(g, c2d_gpu_read_boxes(g, first, count, tight4, fat4));
+        if (alive)
+        {
+            gpuCheck(g, c2d_gpu_read_shapes(g, first, count, nullptr, nullptr, alive, nullptr, nullptr, nullptr));
+            for (uint32_t i = 0; i < count; ++i)
+                alive[i] &= 1u;
+        }
+    }
+    void candidates(std::vector<std::pair<uint32_t, uint32_t>>& out) override
+    {
+        c2d_gpu_ctx* g = reg.nativeContext();
+        reg.countCollidingPairsOnDevice();
+        uint64_t n = 0;
+        gpuCheck(g, c2d_gpu_read_candidates(g, 0, nullptr, &n));
+        out.resize(n);
+        static_assert(sizeof(std::pair<uint32_t, uint32_t>) == 8);
+        if (n)
+            gpuCheck(g, c2d_gpu_read_candidates(g, n, reinterpret_cast<uint32_t*>(out.data()), &n));
+    }
 #else
+    uint32_t shapeSlots() override
+    {
+        return static_cast<uint32_t>(reg.mShapes.size());
+    }
+    void readBoxes(uint32_t first, uint32_t count, float* tight4, float* fat4, uint8_t* alive) override
+    {
+        if constexpr (Method == PartitioningMethod::None)
+        {
+            std::vector<uint8_t> isFree(reg.mShapes.size(), 0);
+            for (const ShapeId f : reg.mFreeShapeIds)
+                isFree[f] = 1;
+            for (uint32_t i = 0; i < count; ++i)
+            {
+                const uint32_t s = first + i;
+                if (s >= reg.mShapes.size())
+                    throw std::runtime_error("rn_read_boxes: shape id out of range");
+                const AABB tight = reg.mShapes[s].mBoundingBox; // ShapeInstance::mBoundingBox (Registry.hpp:117)
+                AABB fat = tight;
+                if (!isFree[s])
+                {
+                    // the leaf of the shape's proxy (DynamicBVH.hpp:119-122, 352-365, 386-417)
+                    const BodyType body = reg.mEntities.at(reg.mShapeEntity[s]).mType;
+                    fat = reg.treeFor(body).getNode(static_cast<NodeIndex>(reg.mShapeTreeHandles[s])).mBoundingBox;
+                }
+                if (tight4)
+                    tight4[4 * i] = tight.min.x, tight4[4 * i + 1] = tight.min.y, tight4[4 * i + 2] = tight.max.x,
+                              tight4[4 * i + 3] = tight.max.y;
+                if (fat4)
+                    fat4[4 * i] = fat.min.x, fat4[4 * i + 1] = fat.min.y, fat4[4 * i + 2] = fat.max.x, fat4[4 * i + 3] = fat.max.y;
+                if (alive)
+                    alive[i] = isFree[s] ? 0 : 1;
+            }
+        }
+        else
+            throw std::runtime_error("rn_read_boxes: the reference's Grid registry keeps one leaf per touched cell");
+    }
+    void candidates(std::vector<std::pair<uint32_t, uint32_t>>& out) override
+    {
+        out.clear();
+        if constexpr (Method == PartitioningMethod::None)
+        {
+            // the five broadphase groups of getCollidingPairs (Registry.hpp:487-545), each sorted like there
+            const auto cross = [&](BodyType a, BodyType b)
+            {
+                const size_t first = out.size();
+                reg.treeFor(a).findAllCollisions(reg.treeFor(b), [&](ShapeId x, ShapeId y) { out.emplace_back(x, y); });
+                std::sort(out.begin() + first, out.end());
+            };
+            const auto self = [&](BodyType a)
+            {
+                const size_t first = out.size();
+                reg.treeFor(a).findAllCollisions([&](ShapeId x, ShapeId y) { out.emplace_back(std::min(x, y), std::max(x, y)); });
+                std::sort(out.begin() + first, out.end());
+            };
+            cross(BodyType::Dynamic, BodyType::Static);
+            self(BodyType::Dynamic);
+            cross(BodyType::Bullet, BodyType::Static);
+            cross(BodyType::Bullet, BodyType::Dynamic);
+            self(BodyType::Bullet);
+        }
+        else
+            throw std::runtime_error("rn_candidates: PartitioningMethod::None only");
+    }
     std::vector<std::pair<std::vector<uint32_t>, std::vector<Translation>>> staged;
     std::vector<typename Reg::EntityCollision> viewStorage;
     void setGhost(ShapeId, bool) override
@@ -417,6 +549,7 @@ struct rn_ctx
     std::unordered_map<uint32_t, Transform> prev; // bullets only (mirrors Registry.hpp:167 by observation)
     std::vector<PairRec> pairs;
     std::vector<HitRec> hits;
+    std::vector<std::pair<uint32_t, uint32_t>> cands; // last rn_candidates
     std::string blob; // last rn_serialize
     std::string error;
 
@@ -784,6 +917,36 @@ void rn_set_ghost(rn_ctx* ctx, uint32_t n, const uint32_t* shape_ids, const uint
 void* rn_native_context(rn_ctx* ctx)
 {
     return ctx->reg->native();
+}
+
+uint32_t rn_shape_slots(rn_ctx* ctx)
+{
+    RN_TRY(ctx)
+    return ctx->reg->shapeSlots();
+    RN_CATCH(ctx)
+    return 0;
+}
+
+void rn_read_boxes(rn_ctx* ctx, uint32_t first, uint32_t count, float* out_tight4, float* out_fat4, uint8_t* out_alive)
+{
+    RN_TRY(ctx)
+    ctx->reg->readBoxes(first, count, out_tight4, out_fat4, out_alive);
+    RN_CATCH(ctx)
+}
+
+uint64_t rn_candidates(rn_ctx* ctx)
+{
+    RN_TRY(ctx)
+    ctx->reg->candidates(ctx->cands);
+    return ctx->cands.size();
+    RN_CATCH(ctx)
+    return 0;
+}
+
+void rn_copy_candidates(rn_ctx* ctx, uint32_t* out_pairs2)
+{
+    if (!ctx->cands.empty())
+        std::memcpy(out_pairs2, ctx->cands.data(), ctx->cands.size() * sizeof(ctx->cands[0]));
 }
 
 void rn_query_stats(rn_ctx* ctx, double* out16)

@@ -97,6 +97,15 @@ void rn_seed_entities(rn_ctx*, uint32_t n, const uint32_t* ids, const uint8_t* b
 int rn_equals(rn_ctx* a, rn_ctx* b);
 void rn_set_ghost(rn_ctx*, uint32_t n, const uint32_t* shape_ids, const uint8_t* ghost);
 
+/* Secondary oracles.  Reference: read from the Registry's private members
+ * (mShapes[i].mBoundingBox; the leaf box mTrees[body].getNode(mShapeTreeHandles[i]).mBoundingBox; the five
+ * mTrees[..].findAllCollisions groups of Registry.hpp:487-545) - PartitioningMethod::None only.  B200: c2d_gpu_read_boxes /
+ * c2d_gpu_read_shapes / c2d_gpu_read_candidates after a device-resident query.  Same-tree candidates are (min, max). */
+uint32_t rn_shape_slots(rn_ctx*);
+void rn_read_boxes(rn_ctx*, uint32_t first, uint32_t count, float* out_tight4, float* out_fat4, uint8_t* out_alive);
+uint64_t rn_candidates(rn_ctx*); /* runs the broadphase, keeps the pairs; copy with rn_copy_candidates */
+void rn_copy_candidates(rn_ctx*, uint32_t* out_pairs2);
+
 /* B200 only: the c2d_gpu_ctx* behind the Registry (Registry::nativeContext); NULL elsewhere. */
 void* rn_native_context(rn_ctx*);
 

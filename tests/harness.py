@@ -127,6 +127,10 @@ def load(name: str) -> C.CDLL:
         "rn_count_colliding_pairs_device": (u64, [vp, pd]),
         "rn_query_stats": (None, [vp, pd]),
         "rn_native_context": (vp, [vp]),
+        "rn_shape_slots": (u32, [vp]),
+        "rn_read_boxes": (None, [vp, u32, u32, pf, pf, pu8]),
+        "rn_candidates": (u64, [vp]),
+        "rn_copy_candidates": (None, [vp, pu32]),
         "rn_set_ghost": (None, [vp, u32, pu32, pu8]),
         "rn_get_colliding_pairs_view": (u64, [vp, pd, C.POINTER(vp)]),
         "rn_get_collisions": (u64, [vp, u32]),
@@ -337,6 +341,31 @@ class Backend:
 
     def native_context(self):
         return self.lib.rn_native_context(self.ctx)
+
+    # -- secondary oracles ----------------------------------------
+    def shape_slots(self) -> int:
+        n = int(self.lib.rn_shape_slots(self.ctx))
+        self._check()
+        return n
+
+    def read_boxes(self, first: int = 0, count: int | None = None):
+        """(tight (n,4), leaf (n,4), alive (n,)): ShapeInstance::mBoundingBox, the shape's leaf box in its tree, liveness."""
+        if count is None:
+            count = self.shape_slots() - first
+        tight, fat = np.zeros((count, 4), np.float32), np.zeros((count, 4), np.float32)
+        alive = np.zeros(count, np.uint8)
+        self.lib.rn_read_boxes(self.ctx, first, count, _p(tight, C.c_float), _p(fat, C.c_float), _p(alive, C.c_uint8))
+        self._check()
+        return tight, fat, alive
+
+    def candidates(self) -> np.ndarray:
+        """Broadphase candidate pairs (shapeA, shapeB) of the five groups; same-tree pairs as (min, max)."""
+        n = int(self.lib.rn_candidates(self.ctx))
+        self._check()
+        out = np.zeros((n, 2), np.uint32)
+        if n:
+            self.lib.rn_copy_candidates(self.ctx, _p(out, C.c_uint32))
+        return out
 
     def stats(self) -> dict:
         out = np.zeros(16, np.float64)

@@ -44,3 +44,14 @@ def test_registry_scenes():
     R.test_mixed_with_bullets_translate_frames()
     R.test_transform_moves_teleports_removal_activation()
     R.test_category_filter_and_same_entity()
+
+
+def test_secondary_oracles(monkeypatch):
+    """tight boxes, leaf boxes (fat-leaf rule) and the candidate set of the C oracle against the reference's private
+    state, bit for bit over the scripted scene of tests/test_gpu_secondary_oracles.py."""
+    from tests import test_gpu_secondary_oracles as S
+
+    monkeypatch.setattr(S, "SUBJECT", "oracle")
+    totals = S.run_scripted_scene(n_dyn=3000, n_static=800, side=160.0, frames=5)
+    assert all(c > 4000 for _, c in totals), totals
+    S.test_boxes_and_candidates_cfg1b_frames()
