@@ -561,7 +561,7 @@ struct rn_ctx
     }
 };
 
-#define RN_TRY(ctx) try {
+#define RN_TRY(ctx) (ctx)->error.clear(); try {
 #define RN_CATCH(ctx)                                                                                                  \
     }                                                                                                                  \
     catch (const std::exception& e)                                                                                    \

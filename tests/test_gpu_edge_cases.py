@@ -149,3 +149,61 @@ def test_shape_id_recycling_under_churn():
         assert len(ka) > 300
         # removing the shapes above broke "entity i owns shape i": from now on only remove what we just added
         break
+
+
+def test_staged_moves_equal_moves_and_are_invalidated_by_structure_changes():
+    """N2: a device-resident move batch does what the same moveEntity(Translation) calls do (bit-identical boxes, leaf
+    rule and results); addShape / removeShape on ANY entity after staging invalidates the batch instead of silently
+    leaving the new shape behind (host and device would disagree about where the entity's shapes are)."""
+    sc = scenes.mixed_scene(3000, 300, 150.0, seed=5)
+    a, b = H.Backend(SUBJECT), H.Backend(SUBJECT)
+    for reg in (a, b):
+        scenes.populate(reg, sc)
+    mov = np.nonzero(sc["ent_body"] != 0)[0].astype(np.uint32)
+    d = scenes.jitter(scenes.LCG(3), len(mov), 0.7)
+    h = b.stage_translations(mov, d)
+    for _ in range(3):
+        a.move_translate(mov, d)
+        b.apply_staged(h)
+        ta, fa, _ = a.read_boxes()
+        tb, fb, _ = b.read_boxes()
+        assert ta.tobytes() == tb.tobytes() and fa.tobytes() == fb.tobytes()
+        assert P.sort_pairs(a.get_colliding_pairs()).tobytes() == P.sort_pairs(b.get_colliding_pairs()).tobytes()
+        assert np.array_equal(a.get_transforms(mov).view(np.uint32), b.get_transforms(mov).view(np.uint32))
+    b.add_shapes(mov[:1], [H.CIRCLE], G.UNIT)
+    with pytest.raises(RuntimeError, match="added or removed"):
+        b.apply_staged(h)
+    b.release_staged(h)
+    h2 = b.stage_translations(mov, d)  # a fresh batch sees the new shape
+    a.add_shapes(mov[:1], [H.CIRCLE], G.UNIT)
+    a.move_translate(mov, d)
+    b.apply_staged(h2)
+    assert P.sort_pairs(a.get_colliding_pairs()).tobytes() == P.sort_pairs(b.get_colliding_pairs()).tobytes()
+
+
+def test_out_of_range_shape_ids_throw():
+    b = H.Backend(SUBJECT)
+    b.create_entities([1], [H.DYNAMIC], [[0, 0, 0]])
+    s = b.add_shapes([1], [H.CIRCLE], G.UNIT)
+    with pytest.raises(RuntimeError, match="out of range"):
+        b.set_active([int(s[0]) + 100000], [0])
+
+
+def test_sparse_shape_ids_stay_inside_the_device_arrays():
+    """host tables grow by doubling and can exceed the device capacity (ids 10000, 10001 -> host 20002 slots,
+    capacity 16384); setShapeActive on a stale slot past the capacity must not write out of bounds."""
+    b, r = H.Backend(SUBJECT), H.Backend(ORACLE)
+    n = 10002
+    ids = np.arange(n, dtype=np.uint32)
+    xf3 = np.zeros((n, 3), np.float32)
+    xf3[:, 0] = np.arange(n) * 0.75
+    g = np.zeros((n, 16), np.float32)
+    g[:, 2] = 0.5
+    for reg in (b, r):
+        reg.create_entities(ids, np.full(n, H.DYNAMIC, np.uint8), xf3)
+        reg.add_shapes(ids, np.zeros(n, np.uint8), g)
+        reg.remove_entities(ids[:10000])  # frees ids 0..9999; live ids 10000, 10001
+        reg.set_active([10001], [0])
+        reg.set_active([10001], [1])
+    assert P.sort_pairs(b.get_colliding_pairs()).tobytes() == P.sort_pairs(r.get_colliding_pairs()).tobytes()
+    assert len(b.get_colliding_pairs()) == 1

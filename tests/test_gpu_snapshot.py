@@ -117,3 +117,44 @@ def test_grid_snapshots_travel_too():
             reg.move_translate(movable, d)
     twin = H.Backend.deserialize("b200", gpu.serialize(), method=1)
     assert gpu.equals(twin)
+
+
+@needs_ref
+def test_snapshots_whose_shape_table_ends_in_freed_ids():
+    """the snapshot's shape table includes freed ids; the device arrays only ever grew to the highest LIVE id
+    re-added.  (a) every shape removed: the device capacity is still 0 when the boxes are restored; (b) 5000 slots with
+    all live ids below 4096 (the first capacity step).  Both round trips work in both directions."""
+    # (a)
+    for name in ("reference", "b200"):
+        reg = H.Backend(name)
+        reg.create_entities([1, 2], [H.DYNAMIC, H.STATIC], np.zeros((2, 3), np.float32))
+        g = np.zeros((2, 16), np.float32)
+        g[:, 2] = 1.0
+        s = reg.add_shapes([1, 2], [0, 0], g)
+        reg.remove_shapes(s)
+        blob = reg.serialize()
+        for target in ("reference", "b200"):
+            back = H.Backend.deserialize(target, blob)
+            assert back.size() == 2 and len(back.get_colliding_pairs()) == 0
+            # the freed ids are handed out again, LIFO
+            assert list(back.add_shapes([1, 2], [0, 0], g)) == list(reg.add_shapes([1, 2], [0, 0], g))
+            reg.remove_shapes(s)
+    # (b)
+    n = 5000
+    ids = np.arange(n, dtype=np.uint32)
+    xf3 = np.zeros((n, 3), np.float32)
+    xf3[:, 0] = np.arange(n) * 0.8
+    g = np.zeros((n, 16), np.float32)
+    g[:, 2] = 0.5
+    results = {}
+    for name in ("reference", "b200"):
+        reg = H.Backend(name)
+        reg.create_entities(ids, np.full(n, H.DYNAMIC, np.uint8), xf3)
+        reg.add_shapes(ids, np.zeros(n, np.uint8), g)
+        reg.remove_entities(ids[4000:])
+        blob = reg.serialize()
+        for target in ("reference", "b200"):
+            back = H.Backend.deserialize(target, blob)
+            results[(name, target)] = P.sort_pairs(back.get_colliding_pairs()).tobytes()
+            assert back.size() == 4000
+    assert len(set(results.values())) == 1 and len(next(iter(results.values()))) == 3999 * 84
