@@ -155,6 +155,9 @@ def test_snapshots_whose_shape_table_ends_in_freed_ids():
         blob = reg.serialize()
         for target in ("reference", "b200"):
             back = H.Backend.deserialize(target, blob)
-            results[(name, target)] = P.sort_pairs(back.get_colliding_pairs()).tobytes()
+            p = back.get_colliding_pairs()  # same-tree orientation is the backend's own: unordered keys
+            results[(name, target)] = sorted(zip(np.minimum(p["shapeA"], p["shapeB"]).tolist(),
+                                                 np.maximum(p["shapeA"], p["shapeB"]).tolist()))
             assert back.size() == 4000
-    assert len(set(results.values())) == 1 and len(next(iter(results.values()))) == 3999 * 84
+    first = results[("reference", "reference")]
+    assert len(first) == 3999 and all(v == first for v in results.values())
