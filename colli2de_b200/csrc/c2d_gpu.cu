@@ -362,7 +362,7 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     if (n > 1)
     {
         C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
-        C2D_TIMED(ctx, "k_karras_build", k_karras_build<<<blocks_for(n - 1, 256), 256, 0, s>>>(t.keys.ptr, static_cast<int>(n), t.nodes.ptr,
+        C2D_TIMED(ctx, "k_karras_build", k_karras_build<<<blocks_for(n - 1, 256), 256, 0, s>>>(t.keys.ptr, t.vals.ptr, static_cast<int>(n), t.nodes.ptr,
                                                              t.nodeParent.ptr, t.leafParent.ptr));
         C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
                                                  t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
@@ -395,29 +395,40 @@ int c2d_host::ensure_trees(c2d_gpu_ctx* ctx)
 namespace
 {
 
+// Traversal of the query leaves [lo, hi) of tree `q` against tree `t`.  rejectLeaf: leaf links carrying any of these
+// bits are skipped (halo leaves of a slab tree, see c2d_comm.cu).
+template <bool SELF>
+void launch_traverse_trees(c2d_gpu_ctx* ctx, const TreeBuf& q, const TreeBuf& t, uint32_t lo, uint32_t hi, uint32_t rejectLeaf)
+{
+    if (q.n == 0 || t.n == 0 || (SELF && q.n < 2) || hi <= lo)
+        return;
+    uint32_t* overflow = &ctx->dScratch->stackOverflow;
+    // few queries (bullets, whose swept leaves overlap hundreds of boxes): one WARP per query leaf
+    if (static_cast<uint64_t>(hi - lo) * 32 <= 148ull * 2048 * 4)
+        C2D_TIMED(ctx, SELF ? "k_traverse_warp<self>" : "k_traverse_warp<cross>",
+                  k_traverse_warp<SELF><<<blocks_for(static_cast<size_t>(hi - lo) * 32, 128), 128, 0, ctx->stream>>>(
+                      q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, rejectLeaf,
+                      ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
+    else if (ctx->traverseVariant == 0 || t.n < 2)
+        C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+        q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
+        static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
+    else
+        C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse_sync<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+        q.vals.ptr, q.n, lo, hi, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, rejectLeaf, ctx->cand.ptr,
+        static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
+    ++ctx->launches;
+}
+
 template <bool SELF>
 void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)
 {
     const TreeBuf& q = ctx->tree[qBody];
     const TreeBuf& t = ctx->tree[tBody];
-    if (q.n == 0 || t.n == 0 || (SELF && q.n < 2))
-        return;
     // multi-GPU: this context owns the query leaves of Morton-rank slab [lo, hi)
     const uint32_t lo = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * ctx->shardRank / ctx->shardWorld);
     const uint32_t hi = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * (ctx->shardRank + 1) / ctx->shardWorld);
-    if (hi <= lo)
-        return;
-    // few queries (bullets, whose swept leaves overlap hundreds of boxes): one WARP per query leaf
-    if (static_cast<uint64_t>(hi - lo) * 32 <= 148ull * 2048 * 4)
-        C2D_TIMED(ctx, SELF ? "k_traverse_warp<self>" : "k_traverse_warp<cross>",
-                  k_traverse_warp<SELF><<<blocks_for(static_cast<size_t>(hi - lo) * 32, 128), 128, 0, ctx->stream>>>(
-                      q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
-                      static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount));
-    else
-        C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
-        q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
-        static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount));
-    ++ctx->launches;
+    launch_traverse_trees<SELF>(ctx, q, t, lo, hi, 0u);
 }
 
 void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats);
@@ -547,6 +558,8 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
         pairCount = ctx->hScratch->outCount;
         if (ctx->hScratch->clipOverflow)
             return fail(ctx, "polygon clip scratch overflow (non-convex polygon input?)");
+        if (ctx->hScratch->stackOverflow)
+            return fail(ctx, "LBVH traversal stack overflow (tree deeper than 64 levels)");
         const bool candOverflow = candCount > ctx->cand.capacity;
         const bool outOverflow = pairCount > ctx->out.capacity;
         if (!candOverflow && !outOverflow)
@@ -671,6 +684,8 @@ int c2d_gpu_create(int device, c2d_gpu_ctx** out_ctx)
         delete ctx;
         return 1;
     }
+    if (const char* env = std::getenv("C2D_GPU_TRAVERSE")) // A/B switch for measurements (see c2d_ctx.hpp)
+        ctx->traverseVariant = std::atoi(env);
     *out_ctx = ctx;
     return 0;
 }

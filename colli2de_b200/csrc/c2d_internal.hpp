@@ -68,11 +68,18 @@ struct ShapeArrays
 };
 
 // ---- LBVH node: both children's boxes live in the parent so one 64 B read serves both tests -------------
+// child link of a node: >= 0 internal node index; < 0 (bit 31) a leaf that carries its ShapeId in the low 30 bits, so
+// emitting a candidate needs no dependent load of the sorted id array; bit 30 marks a halo leaf of a multi-GPU slab tree
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kLeafGhost = 0x40000000u; // also carried by the sorted value array of a slab tree
+constexpr uint32_t kLeafIdMask = 0x3fffffffu;
+__host__ __device__ inline uint32_t leaf_shape(int link) { return static_cast<uint32_t>(link) & kLeafIdMask; }
+
 struct __align__(16) BvhNode
 {
     float4 boxL;
     float4 boxR;
-    int left;  // >= 0: internal node index; < 0: leaf, sorted position = ~left
+    int left;  // >= 0: internal node index; < 0: leaf (kLeafBit | ghost bit | ShapeId)
     int right;
     int lastL; // last sorted leaf position covered by the left / right subtree
     int lastR;
@@ -89,7 +96,7 @@ struct FrameScratch
     uint32_t candCount;
     uint32_t outCount;
     uint32_t clipOverflow;
-    uint32_t _pad;
+    uint32_t stackOverflow; // a traversal stack ran out (cannot happen with the depth bound of the Karras tree; never silent)
     uint32_t binCount[16];
     uint32_t binOffset[16];
     uint32_t binCursor[16];

@@ -199,7 +199,10 @@ __global__ void k_frame_init(FrameScratch* fs)
     if (t == 13)
         fs->outCount = 0;
     if (t == 14)
+    {
         fs->clipOverflow = 0;
+        fs->stackOverflow = 0;
+    }
     if (t >= 16 && t < 32)
     {
         fs->binCount[t - 16] = 0;
@@ -287,7 +290,8 @@ __device__ __forceinline__ int karras_delta(const uint32_t* __restrict__ keys, i
 }
 
 // parent code: (parent index << 1) | (1 if right child)
-__global__ void __launch_bounds__(256) k_karras_build(const uint32_t* __restrict__ keys, int n, BvhNode* nodes,
+__global__ void __launch_bounds__(256) k_karras_build(const uint32_t* __restrict__ keys,
+                                                      const uint32_t* __restrict__ sorted, int n, BvhNode* nodes,
                                                       int* __restrict__ nodeParent, int* __restrict__ leafParent)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -319,7 +323,7 @@ __global__ void __launch_bounds__(256) k_karras_build(const uint32_t* __restrict
     int left, right;
     if (lo == gamma)
     {
-        left = ~gamma;
+        left = static_cast<int>(kLeafBit | sorted[gamma]);
         leafParent[gamma] = (i << 1);
     }
     else
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(256) k_karras_build(const uint32_t* __restrict
     }
     if (hi == gamma + 1)
     {
-        right = ~(gamma + 1);
+        right = static_cast<int>(kLeafBit | sorted[gamma + 1]);
         leafParent[gamma + 1] = (i << 1) | 1;
     }
     else
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(256) k_fit(int n, const uint32_t* __restrict__
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n)
         return;
-    const uint32_t shape = sorted[p];
+    const uint32_t shape = sorted[p] & kLeafIdMask;
     float4 box = fat[shape];
     uint64_t cat = category[shape];
     int code = leafParent[p];
@@ -414,12 +418,12 @@ __global__ void __launch_bounds__(128)
     k_traverse(const uint32_t* __restrict__ qSorted, uint32_t qn, uint32_t qLo, uint32_t qHi,
                const uint32_t* __restrict__ tSorted, uint32_t tn, const BvhNode* __restrict__ nodes,
                const float4* __restrict__ fat, const uint64_t* __restrict__ category, uint2* __restrict__ out,
-               uint32_t capacity, uint32_t* counter)
+               uint32_t capacity, uint32_t* counter, uint32_t* stackOverflow)
 {
     const uint32_t i = qLo + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= qHi || i >= qn || tn == 0)
         return;
-    const uint32_t qs = qSorted[i];
+    const uint32_t qs = qSorted[i] & kLeafIdMask;
     const float4 qb = fat[qs];
     const uint64_t qc = category[qs];
 
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(128)
     {
         if (!SELF)
         {
-            const uint32_t ts = tSorted[0];
+            const uint32_t ts = tSorted[0] & kLeafIdMask;
             if ((qc & category[ts]) != 0 && box_overlap(qb, fat[ts]))
                 emit_pair(qs, ts, out, capacity, counter);
         }
@@ -448,7 +452,7 @@ __global__ void __launch_bounds__(128)
         bool hitR = box_overlap(qb, boxR) && (qc & cats.y) != 0 && (!SELF || links.w > static_cast<int>(i));
         if (hitL && links.x < 0)
         {
-            const uint32_t ts = tSorted[~links.x];
+            const uint32_t ts = leaf_shape(links.x);
             if (SELF)
                 emit_pair(min(qs, ts), max(qs, ts), out, capacity, counter);
             else
@@ -457,7 +461,7 @@ __global__ void __launch_bounds__(128)
         }
         if (hitR && links.y < 0)
         {
-            const uint32_t ts = tSorted[~links.y];
+            const uint32_t ts = leaf_shape(links.y);
             if (SELF)
                 emit_pair(min(qs, ts), max(qs, ts), out, capacity, counter);
             else
@@ -466,8 +470,13 @@ __global__ void __launch_bounds__(128)
         }
         if (hitL)
         {
-            if (hitR && sp < 64)
-                stack[sp++] = links.y;
+            if (hitR)
+            {
+                if (sp < 64)
+                    stack[sp++] = links.y;
+                else
+                    *stackOverflow = 1; // cannot happen (Karras depth <= 64 with the index tie-break); never silent
+            }
             node = links.x;
         }
         else if (hitR)
@@ -483,6 +492,129 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// k_traverse_sync: the same traversal with a warp-CONVERGENT loop.  Every iteration each live lane visits one node; the
+// warp reconverges before the candidates of the iteration are appended, so
+//   * the two emit sites of k_traverse (each a divergent region with its own coalesced-group election and global atomic)
+//     become two full-mask ballots,
+//   * candidates are staged in a per-warp shared-memory buffer and flushed 32 at a time: one global atomic and one
+//     coalesced 256-byte store per 32 candidates instead of one contended same-address atomic per (partial) warp emit.
+// rejectLeaf: leaf links with any of these bits are skipped (kLeafGhost: halo leaves of a multi-GPU slab tree when the
+// query side is replicated on every rank, i.e. Bullet x Dynamic).
+constexpr int kStageCap = 96; // < 32 staged + <= 64 new entries per iteration
+
+__device__ __forceinline__ void stage_flush32(uint2* stage, int& staged, uint2* __restrict__ out, uint32_t capacity,
+                                              uint32_t* counter, int lane)
+{
+    // warp-convergent; staged >= 32: the OLDEST 32 entries go out, the rest slides down
+    uint32_t base = 0;
+    if (lane == 0)
+        base = atomicAdd(counter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    const uint2 mine = stage[lane];
+    if (base + lane < capacity)
+        out[base + lane] = mine;
+    const int rest = staged - 32;
+    // slide: rest < 64 entries, two per lane
+    const uint2 a = lane < rest ? stage[32 + lane] : make_uint2(0, 0);
+    const uint2 b = 32 + lane < rest ? stage[64 + lane] : make_uint2(0, 0);
+    __syncwarp();
+    if (lane < rest)
+        stage[lane] = a;
+    if (32 + lane < rest)
+        stage[32 + lane] = b;
+    __syncwarp();
+    staged = rest;
+}
+
+template <bool SELF>
+__global__ void __launch_bounds__(128)
+    k_traverse_sync(const uint32_t* __restrict__ qSorted, uint32_t qn, uint32_t qLo, uint32_t qHi, uint32_t tn,
+                    const BvhNode* __restrict__ nodes, const float4* __restrict__ fat,
+                    const uint64_t* __restrict__ category, uint32_t rejectLeaf, uint2* __restrict__ out,
+                    uint32_t capacity, uint32_t* counter, uint32_t* stackOverflow)
+{
+    __shared__ uint2 stages[4][kStageCap];
+    uint2* stage = stages[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t i = qLo + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < qHi && i < qn && tn >= 2;
+    uint32_t qs = 0;
+    float4 qb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    uint64_t qc = 0;
+    if (live)
+    {
+        qs = qSorted[i] & kLeafIdMask;
+        qb = fat[qs];
+        qc = category[qs];
+    }
+    int stack[64];
+    int sp = 0;
+    int node = live ? 0 : -1;
+    int staged = 0; // warp-uniform
+    while (__any_sync(0xffffffffu, node >= 0))
+    {
+        bool emitL = false, emitR = false;
+        int4 links = make_int4(0, 0, 0, 0);
+        if (node >= 0)
+        {
+            const float4* np = reinterpret_cast<const float4*>(nodes + node);
+            const float4 boxL = __ldg(np);
+            const float4 boxR = __ldg(np + 1);
+            links = __ldg(reinterpret_cast<const int4*>(np + 2));
+            const ulonglong2 cats = __ldg(reinterpret_cast<const ulonglong2*>(np + 3));
+            const bool hitL = box_overlap(qb, boxL) && (qc & cats.x) != 0 && (!SELF || links.z > static_cast<int>(i));
+            const bool hitR = box_overlap(qb, boxR) && (qc & cats.y) != 0 && (!SELF || links.w > static_cast<int>(i));
+            emitL = hitL && links.x < 0 && (static_cast<uint32_t>(links.x) & rejectLeaf) == 0;
+            emitR = hitR && links.y < 0 && (static_cast<uint32_t>(links.y) & rejectLeaf) == 0;
+            const bool goL = hitL && links.x >= 0, goR = hitR && links.y >= 0;
+            if (goL)
+            {
+                if (goR)
+                {
+                    if (sp < 64)
+                        stack[sp++] = links.y;
+                    else
+                        *stackOverflow = 1;
+                }
+                node = links.x;
+            }
+            else if (goR)
+                node = links.y;
+            else
+                node = sp > 0 ? stack[--sp] : -1;
+        }
+        const uint32_t eL = __ballot_sync(0xffffffffu, emitL), eR = __ballot_sync(0xffffffffu, emitR);
+        if (eL | eR)
+        {
+            if (emitL)
+            {
+                const uint32_t ts = leaf_shape(links.x);
+                stage[staged + __popc(eL & ltMask)] = make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
+            }
+            if (emitR)
+            {
+                const uint32_t ts = leaf_shape(links.y);
+                stage[staged + __popc(eL) + __popc(eR & ltMask)] =
+                    make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
+            }
+            staged += __popc(eL) + __popc(eR);
+            __syncwarp();
+            while (staged >= 32)
+                stage_flush32(stage, staged, out, capacity, counter, lane);
+        }
+    }
+    if (staged > 0)
+    {
+        uint32_t base = 0;
+        if (lane == 0)
+            base = atomicAdd(counter, static_cast<uint32_t>(staged));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (lane < staged && base + lane < capacity)
+            out[base + lane] = stage[lane];
+    }
+}
+
 // Warp-per-query variant for SMALL query sets with large boxes (bullets: the leaf is a swept, displacement-fattened
 // box that overlaps hundreds of leaves).  One thread per query would leave the GPU idle (10 k threads) and serialise
 // each long traversal; here the 32 lanes of a warp pop up to 32 nodes of a shared stack per step and push / emit
@@ -490,9 +622,9 @@ __global__ void __launch_bounds__(128)
 constexpr int kWarpStack = 1024;
 
 template <bool SELF>
-__device__ void lane_dfs(int root, uint32_t i, uint32_t qs, const float4& qb, uint64_t qc,
-                         const uint32_t* __restrict__ tSorted, const BvhNode* __restrict__ nodes,
-                         uint2* __restrict__ out, uint32_t capacity, uint32_t* counter)
+__device__ void lane_dfs(int root, uint32_t i, uint32_t qs, const float4& qb, uint64_t qc, uint32_t rejectLeaf,
+                         const BvhNode* __restrict__ nodes, uint2* __restrict__ out, uint32_t capacity,
+                         uint32_t* counter, uint32_t* stackOverflow)
 {
     // overflow fallback of k_traverse_warp: a plain per-lane stack traversal of one subtree
     int stack[64];
@@ -505,20 +637,27 @@ __device__ void lane_dfs(int root, uint32_t i, uint32_t qs, const float4& qb, ui
         bool hitR = box_overlap(qb, N.boxR) && (qc & N.catR) != 0 && (!SELF || N.lastR > static_cast<int>(i));
         if (hitL && N.left < 0)
         {
-            const uint32_t ts = tSorted[~N.left];
-            emit_pair(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts, out, capacity, counter);
+            const uint32_t ts = leaf_shape(N.left);
+            if ((static_cast<uint32_t>(N.left) & rejectLeaf) == 0)
+                emit_pair(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts, out, capacity, counter);
             hitL = false;
         }
         if (hitR && N.right < 0)
         {
-            const uint32_t ts = tSorted[~N.right];
-            emit_pair(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts, out, capacity, counter);
+            const uint32_t ts = leaf_shape(N.right);
+            if ((static_cast<uint32_t>(N.right) & rejectLeaf) == 0)
+                emit_pair(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts, out, capacity, counter);
             hitR = false;
         }
         if (hitL)
         {
-            if (hitR && sp < 64)
-                stack[sp++] = N.right;
+            if (hitR)
+            {
+                if (sp < 64)
+                    stack[sp++] = N.right;
+                else
+                    *stackOverflow = 1;
+            }
             node = N.left;
         }
         else if (hitR)
@@ -536,8 +675,8 @@ template <bool SELF>
 __global__ void __launch_bounds__(128)
     k_traverse_warp(const uint32_t* __restrict__ qSorted, uint32_t qn, uint32_t qLo, uint32_t qHi,
                     const uint32_t* __restrict__ tSorted, uint32_t tn, const BvhNode* __restrict__ nodes,
-                    const float4* __restrict__ fat, const uint64_t* __restrict__ category, uint2* __restrict__ out,
-                    uint32_t capacity, uint32_t* counter)
+                    const float4* __restrict__ fat, const uint64_t* __restrict__ category, uint32_t rejectLeaf,
+                    uint2* __restrict__ out, uint32_t capacity, uint32_t* counter, uint32_t* stackOverflow)
 {
     __shared__ int stacks[4][kWarpStack];
     const int lane = threadIdx.x & 31;
@@ -545,15 +684,15 @@ __global__ void __launch_bounds__(128)
     const uint32_t i = qLo + ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (i >= qHi || i >= qn || tn == 0)
         return; // warp-uniform
-    const uint32_t qs = qSorted[i];
+    const uint32_t qs = qSorted[i] & kLeafIdMask;
     const float4 qb = fat[qs];
     const uint64_t qc = category[qs];
     if (tn == 1)
     {
         if (!SELF && lane == 0)
         {
-            const uint32_t ts = tSorted[0];
-            if ((qc & category[ts]) != 0 && box_overlap(qb, fat[ts]))
+            const uint32_t ts = tSorted[0] & kLeafIdMask;
+            if ((tSorted[0] & rejectLeaf) == 0 && (qc & category[ts]) != 0 && box_overlap(qb, fat[ts]))
                 emit_pair(qs, ts, out, capacity, counter);
         }
         return;
@@ -580,8 +719,8 @@ __global__ void __launch_bounds__(128)
             const ulonglong2 cats = __ldg(reinterpret_cast<const ulonglong2*>(np + 3));
             const bool hitL = box_overlap(qb, boxL) && (qc & cats.x) != 0 && (!SELF || links.z > static_cast<int>(i));
             const bool hitR = box_overlap(qb, boxR) && (qc & cats.y) != 0 && (!SELF || links.w > static_cast<int>(i));
-            emitL = hitL && links.x < 0;
-            emitR = hitR && links.y < 0;
+            emitL = hitL && links.x < 0 && (static_cast<uint32_t>(links.x) & rejectLeaf) == 0;
+            emitR = hitR && links.y < 0 && (static_cast<uint32_t>(links.y) & rejectLeaf) == 0;
             pushL = hitL && links.x >= 0;
             pushR = hitR && links.y >= 0;
         }
@@ -594,14 +733,14 @@ __global__ void __launch_bounds__(128)
             if (posL < kWarpStack)
                 stack[posL] = links.x;
             else
-                lane_dfs<SELF>(links.x, i, qs, qb, qc, tSorted, nodes, out, capacity, counter);
+                lane_dfs<SELF>(links.x, i, qs, qb, qc, rejectLeaf, nodes, out, capacity, counter, stackOverflow);
         }
         if (pushR)
         {
             if (posR < kWarpStack)
                 stack[posR] = links.y;
             else
-                lane_dfs<SELF>(links.y, i, qs, qb, qc, tSorted, nodes, out, capacity, counter);
+                lane_dfs<SELF>(links.y, i, qs, qb, qc, rejectLeaf, nodes, out, capacity, counter, stackOverflow);
         }
         size = min(size + __popc(bL) + __popc(bR), kWarpStack);
         // emits: one atomic per step
@@ -616,14 +755,14 @@ __global__ void __launch_bounds__(128)
             if (emitL)
             {
                 const uint32_t idx = base + __popc(eL & ltMask);
-                const uint32_t ts = tSorted[~links.x];
+                const uint32_t ts = leaf_shape(links.x);
                 if (idx < capacity)
                     out[idx] = make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
             }
             if (emitR)
             {
                 const uint32_t idx = base + __popc(eL) + __popc(eR & ltMask);
-                const uint32_t ts = tSorted[~links.y];
+                const uint32_t ts = leaf_shape(links.y);
                 if (idx < capacity)
                     out[idx] = make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
             }

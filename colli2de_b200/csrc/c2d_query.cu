@@ -110,12 +110,12 @@ __device__ void query_tree(const ShapeArrays& s, const TreeView& tree, uint32_t 
         bool hitR = (N.catR & mask) != 0 && box_overlap(N.boxR, qb);
         if (hitL && N.left < 0)
         {
-            query_narrow(s, a, ma, tree.sorted[~N.left], out, capacity, counter);
+            query_narrow(s, a, ma, leaf_shape(N.left), out, capacity, counter);
             hitL = false;
         }
         if (hitR && N.right < 0)
         {
-            query_narrow(s, a, ma, tree.sorted[~N.right], out, capacity, counter);
+            query_narrow(s, a, ma, leaf_shape(N.right), out, capacity, counter);
             hitR = false;
         }
         if (hitL)

@@ -345,7 +345,7 @@ __global__ void __launch_bounds__(THREADS)
                 {
                     const int at = atomicAdd(&hitCount, 1);
                     if (at < CAP)
-                        hits[at] = LeafHit{a0, a1, trees[tree].sorted[~N.left], tree};
+                        hits[at] = LeafHit{a0, a1, leaf_shape(N.left), tree};
                     else
                         overflow = 1;
                 }
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(THREADS)
                 {
                     const int at = atomicAdd(&hitCount, 1);
                     if (at < CAP)
-                        hits[at] = LeafHit{a0, a1, trees[tree].sorted[~N.right], tree};
+                        hits[at] = LeafHit{a0, a1, leaf_shape(N.right), tree};
                     else
                         overflow = 1;
                 }
