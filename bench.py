@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py — Colli2De per-frame collision query path on B200: getCollidingPairs ms/frame and pairs/s.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload cfg3-clustered|cfg3-uniform|cfg2]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+                    [--workload cfg3-clustered|cfg3-uniform|cfg2|cfg5-rays] [--scaling strong|weak]
 
 Own arm (default): the BASELINE.json workload quoted by the metric — cfg 3, 1 M dynamic mixed shapes
 (circle / capsule / segment / convex polygon) + 100 k static polygons, clustered density — driven through the
@@ -16,15 +17,21 @@ is moved by a jitter in U(-0.5, 0.5)^2, then getCollidingPairs runs.
     downloaded (D2H) and returned as std::vector inside the timed call.  Like the reference's metric
      the per-entity moveEntity host calls are outside the timed call; their cost is
     reported as e2e.moves_host_ms.
+  * `parity`: before the timed regions two frames are compared with the UNMODIFIED reference (oracle/_ref) on rank 0 —
+    sorted tuple set, manifolds, orientation-ambiguous pairs classified (tests/parity.py).  At N > 1 the records of all
+    ranks are gathered to rank 0 by the library (C2D_RESULTS_ROOT) for it.
   * `roofline`: the dominant kernel by live CUDA-event time (c2d_gpu_set_profiling), algorithmic bytes per
     launch as defined in DESIGN.md section "Roofline", against MEASURED_PEAKS.json hbm_gbs.
   * `cpu_baseline`: the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by oracle/Makefile)
     timed on this host on a bounded sample (same scene, a few frames).
 Reference arm (--impl reference): the reference's own CPU getCollidingPairs on the same scene, K steps.
 
-Multi-GPU (torchrun, one rank per GPU): every rank mirrors the scene and owns one Morton-rank slab of the query
-leaves (c2d_gpu_set_shard) — traversal and narrowphase are sharded, the pair count is all-reduced over NCCL;
-`scaling` is "strong" (the scene is fixed).
+Multi-GPU (torchrun, one rank per GPU): the decomposition lives in the library (include/c2d_gpu.h "multi-GPU").  Every
+rank holds a Registry of the whole scene joined to one NCCL group (c2d_gpu_comm_init); each frame a rank sorts, builds
+and traverses only its Morton-key slab of the Dynamic tree (+ halo) and returns its share of the pairs.  Default
+`scaling` is "strong": the metric's fixed 1 M-shape scene on N GPUs.  `--scaling weak` runs an N-times larger world.
+In the e2e loop every rank logs the moves of 1/N of the entities and the library all-gathers the 12-byte records over
+NVLink (c2d_gpu_comm_set_move_exchange) before it replays them.
 """
 from __future__ import annotations
 
@@ -113,20 +120,6 @@ def build_scene(name: str, scale: int = 1):
     n_dyn, n_sta, box, clustered = WORKLOADS[name]
     return (scenes.mixed_scene(n_dyn * scale, n_sta * scale, box * scale ** 0.5, clustered=clustered),
             n_dyn * scale, n_sta * scale)
-
-
-HALO_MARGIN = 32.0  # > largest fat-box interaction distance (~10) + the random-walk drift of a bench run
-
-
-def local_slab(scene, rank: int, world: int):
-    """Sub-scene of spatial slab `rank` (owned shapes + halo copies) and the mask of the halo copies in it."""
-    from colli2de_b200 import sharding
-
-    x = scene["ent_xf3"][:, 0]
-    owned, ghost = sharding.slab_selection(x, rank, world, HALO_MARGIN)
-    exports = sharding.slab_exports(x, rank, world, HALO_MARGIN)
-    local = np.nonzero(owned | ghost)[0]
-    return {k: v[local] for k, v in scene.items()}, ghost[local], local, owned, exports
 
 
 def measured_peak_gbs():

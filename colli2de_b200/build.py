@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, "csrc")
 GPU_LIB = os.path.join(HERE, "libc2d_gpu.so")
 RUNNER_LIB = os.path.join(HERE, "libc2d_b200_runner.so")
 
-CU_SOURCES = ["c2d_sort.cu", "c2d_gpu.cu", "c2d_batch.cu", "c2d_rays.cu", "c2d_grid.cu", "c2d_query.cu"]
+CU_SOURCES = ["c2d_sort.cu", "c2d_gpu.cu", "c2d_batch.cu", "c2d_rays.cu", "c2d_grid.cu", "c2d_query.cu", "c2d_comm.cu"]
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
     "-fmad=false", "-Xcompiler", "-fPIC",
@@ -45,18 +45,23 @@ def build_gpu_lib(force: bool = False) -> str:
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".hpp"))]
     headers.append(os.path.join(REPO, "include", "c2d_gpu.h"))
     objs = []
-    rebuilt = False
+    jobs = []
     for src in CU_SOURCES:
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
         obj = os.path.join(CSRC, src.replace(".cu", ".o"))
         if force or not _newer(obj, [path] + headers):
-            _run(["nvcc", *NVCC_FLAGS, "-c", path, "-o", obj])
-            rebuilt = True
+            jobs.append(["nvcc", *NVCC_FLAGS, "-c", path, "-o", obj])
         objs.append(obj)
+    rebuilt = bool(jobs)
+    if jobs:  # the translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            list(pool.map(_run, jobs))
     if rebuilt or not os.path.exists(GPU_LIB):
-        _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", GPU_LIB, *objs])
+        _run(["nvcc", "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", GPU_LIB, *objs, "-ldl"])
     return GPU_LIB
 
 

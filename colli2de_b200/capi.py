@@ -20,6 +20,8 @@ EXPORTS = [
     "c2d_gpu_query_shapes", "c2d_gpu_pairs_colliding", "c2d_gpu_read_boxes", "c2d_gpu_read_shapes", "c2d_gpu_write_boxes",
     "c2d_gpu_read_candidates", "c2d_gpu_shape_slots", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
     "c2d_gpu_compute_aabb_batch",
+    "c2d_gpu_set_slab_mode", "c2d_gpu_comm_unique_id", "c2d_gpu_comm_init", "c2d_gpu_comm_destroy",
+    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats",
 ]
 
 _lib = None
@@ -64,6 +66,68 @@ def set_small_scene_limit(ctx, shapes: int):
 
 def set_shard(ctx, rank: int, world: int):
     _check(ctx, lib().c2d_gpu_set_shard(ctx, rank, world))
+
+
+def set_slab_mode(ctx, min_shapes: int):
+    """Morton-slab build of the Dynamic tree when world > 1 and it has >= min_shapes leaves (0 = never)."""
+    lib().c2d_gpu_set_slab_mode.argtypes = [C.c_void_p, C.c_uint32]
+    _check(ctx, lib().c2d_gpu_set_slab_mode(ctx, min_shapes))
+
+
+class CommStats(C.Structure):
+    _fields_ = [("exchange_bytes", C.c_uint64), ("gather_bytes", C.c_uint64), ("local_pairs", C.c_uint64),
+                ("slab_owned", C.c_uint64), ("slab_leaves", C.c_uint64), ("ms_exchange", C.c_float),
+                ("ms_gather", C.c_float), ("ms_slab", C.c_float)]
+
+
+RESULTS_LOCAL, RESULTS_ALL, RESULTS_ROOT = 0, 1, 2
+
+
+def comm_unique_id() -> bytes:
+    """ncclUniqueId (128 bytes) created on this rank; hand it to every rank of the group."""
+    buf = C.create_string_buffer(128)
+    lib().c2d_gpu_comm_unique_id.argtypes = [C.c_void_p]
+    _check(None, lib().c2d_gpu_comm_unique_id(buf))
+    return buf.raw
+
+
+def comm_init(ctx, rank: int, world: int, unique_id: bytes):
+    lib().c2d_gpu_comm_init.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_char_p]
+    _check(ctx, lib().c2d_gpu_comm_init(ctx, rank, world, unique_id))
+
+
+def comm_init_torch(ctx):
+    """Joins the context to a group spanning the torch.distributed world: rank 0's ncclUniqueId travels by broadcast."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ident = [comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    comm_init(ctx, rank, world, ident[0])
+    torch.cuda.synchronize()
+
+
+def comm_destroy(ctx):
+    lib().c2d_gpu_comm_destroy.argtypes = [C.c_void_p]
+    _check(ctx, lib().c2d_gpu_comm_destroy(ctx))
+
+
+def comm_set_move_exchange(ctx, on: bool):
+    lib().c2d_gpu_comm_set_move_exchange.argtypes = [C.c_void_p, C.c_int]
+    _check(ctx, lib().c2d_gpu_comm_set_move_exchange(ctx, 1 if on else 0))
+
+
+def comm_set_result_mode(ctx, mode: int):
+    lib().c2d_gpu_comm_set_result_mode.argtypes = [C.c_void_p, C.c_int]
+    _check(ctx, lib().c2d_gpu_comm_set_result_mode(ctx, mode))
+
+
+def comm_stats(ctx) -> dict:
+    st = CommStats()
+    lib().c2d_gpu_comm_get_stats.argtypes = [C.c_void_p, C.POINTER(CommStats)]
+    _check(ctx, lib().c2d_gpu_comm_get_stats(ctx, C.byref(st)))
+    return {k: getattr(st, k) for k, _ in CommStats._fields_}
 
 
 def kernel_profile(ctx, reset: bool = True) -> dict:

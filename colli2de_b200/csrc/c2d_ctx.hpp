@@ -157,38 +157,42 @@ struct StagedBatch
 };
 
 // Multi-GPU (c2d_comm.cu): one context per GPU / process, joined by an NCCL communicator.  Shape state is REPLICATED
-// on every rank (each rank replays every mutation); what is sharded is the per-frame work.
+// on every rank (each rank replays every mutation, or receives the others' translations); what is sharded is the
+// per-frame work.
 struct CommState
 {
-    void* comm = nullptr; // ncclComm_t (NCCL is loaded with dlopen: libc2d_gpu.so has no link-time NCCL dependency)
-    bool exchangeMoves = false; // translation records logged on one rank are all-gathered to every rank at flush
-    bool gatherResults = false; // every rank receives every rank's pair records (otherwise: its own share)
-    DevBuf<uint32_t> dCounts;   // [world x 16] per-rank header of the record-count exchange
-    uint32_t* hCounts = nullptr; // pinned mirror
-    DevBuf<TransRec> gathered;  // world x stride translation records (padded all-gather)
+    void* comm = nullptr;       // ncclComm_t (NCCL is loaded with dlopen: libc2d_gpu.so has no link-time NCCL dependency)
+    bool exchangeMoves = false; // translation records logged on one rank are all-gathered to every rank at the frame's flush
+    int resultMode = 0;         // C2D_RESULTS_*
+    DevBuf<uint32_t> dHeader;   // [world x 4] per-rank header of the move exchange: count, body mask, 0, 0
+    uint32_t* hHeader = nullptr; // pinned: [0..3] mine, [4 ..] everybody's
+    DevBuf<TransRec> sendRecs;  // this rank's records, padded to the all-gather stride
+    DevBuf<TransRec> gathered;  // world x stride translation records
     DevBuf<PairOut> outAll;     // gathered results
     DevBuf<uint64_t> dPairCounts;
-    uint64_t* hPairCounts = nullptr; // pinned
-    std::vector<uint64_t> rankPairs; // pairs per rank of the last gathered frame
+    uint64_t* hPairCounts = nullptr; // pinned: [0] mine, [1 ..] everybody's
+    bool resultsGathered = false;    // the last frame's records are in outAll (gatheredPairs of them)
+    uint64_t gatheredPairs = 0;
     cudaEvent_t evX[4] = {};    // exchange start / stop, gather start / stop
     // statistics of the last frame
     uint64_t exchangeBytes = 0, gatherBytes = 0;
     bool exchangeTimed = false, gatherTimed = false;
 };
 
-// Morton-slab build of one tree (c2d_comm.cu): this rank's tree holds the shapes whose Morton key falls into its key
-// range ("owned") plus the later-ordered shapes of other ranks that may overlap them ("halo").
+// Morton-slab build of the Dynamic tree (build_slab_tree in c2d_gpu.cu, kernels in c2d_slab.cuh): this rank's tree holds
+// the shapes whose Morton key falls into its key range ("owned") plus the shapes of higher ranks that may overlap them
+// ("halo").
 struct SlabState
 {
     DevBuf<uint32_t> allKeys, allVals; // Morton keys / shape ids of ALL members (replicated pass)
-    DevBuf<uint32_t> hist;             // 4096 coarse bins + 8 x 4096 refinement bins
-    DevBuf<uint32_t> split;            // [0..world] splitter keys (device), [32..] scratch of the two split kernels
+    DevBuf<uint32_t> hist;             // 4096 coarse bins + 32 x 4096 refinement bins
+    DevBuf<uint32_t> split;            // splitter keys + scratch of the two split kernels (kSplitWords)
     DevBuf<uint8_t> cellMask;          // 256 x 256 cells touched by the owned shapes' leaf boxes
     DevBuf<uint32_t> counters;         // [0] selected, [1] owned
     uint32_t* hCounters = nullptr;     // pinned
-    uint32_t splitAge = 0;             // frames since the splitters were rebalanced from the key histogram
-    bool splitValid = false;
-    uint32_t lastOwned = 0, lastSelected = 0;
+    cudaEvent_t ev[2] = {};
+    bool timed = false;
+    uint32_t owned = 0, selected = 0;
 };
 
 struct TreeBuf
@@ -252,7 +256,7 @@ struct c2d_gpu_ctx
     uint32_t cellSize = 120;
     uint32_t shardRank = 0, shardWorld = 1;
     // Morton-slab build of the Dynamic tree when world > 1 and the tree has at least this many leaves (0 = never)
-    uint32_t slabMinShapes = 0;
+    uint32_t slabMinShapes = 65536;
     TreeBuf slabTree;       // the rank-local tree (owned + halo leaves) of the Dynamic body
     bool slabDirty = true;  // the Dynamic shapes changed since slabTree was built
     bool slabInUse = false; // this frame's Dynamic traversals run on slabTree
@@ -301,16 +305,14 @@ namespace c2d_host
 {
 // c2d_gpu.cu
 int fail(c2d_gpu_ctx* ctx, const std::string& msg);
-int flush(c2d_gpu_ctx* ctx);        // replays the mutation log
+int flush(c2d_gpu_ctx* ctx, bool collective = false); // replays the mutation log (collective: from c2d_gpu_collide*)
 int ensure_trees(c2d_gpu_ctx* ctx); // flush + rebuild of the dirty trees (launches k_frame_init first)
 int upload_members(c2d_gpu_ctx* ctx, int body); // host member list of one tree -> device, if it changed
 int copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, uint64_t bytes); // device -> pageable, threaded
 int copy_host(c2d_gpu_ctx* ctx, const void* srcHost, void* dstHost, uint64_t bytes);  // pinned -> pageable, threaded
-// c2d_comm.cu
-int comm_exchange_counts(c2d_gpu_ctx* ctx, const uint32_t* mine, uint32_t n); // all-gather of n <= 16 words per rank
-int comm_allgather_translations(c2d_gpu_ctx* ctx, const TransRec* local, uint32_t localCount, uint32_t stride);
-int comm_gather_results(c2d_gpu_ctx* ctx);
-int build_slab_tree(c2d_gpu_ctx* ctx); // the Dynamic tree of this rank's Morton slab
+// c2d_comm.cu (all collective over the group, enqueued on the context's stream)
+int comm_allgather(c2d_gpu_ctx* ctx, const void* send, void* recv, size_t bytesPerRank);
+int comm_gather_results(c2d_gpu_ctx* ctx); // after a frame: the records of all ranks -> comm.outAll (per the result mode)
 void comm_release(c2d_gpu_ctx* ctx);
 // c2d_rays.cu
 int exclusive_scan_u32(c2d_gpu_ctx* ctx, uint32_t* data, uint32_t n, DevBuf<uint32_t>& sums, uint32_t* dTotal);

@@ -10,6 +10,7 @@
 //   * a query = flush + (re)build of the dirty trees + 5 traversals + binning + narrowphase on one stream.
 #include "c2d_ctx.hpp"
 #include "c2d_kernels.cuh"
+#include "c2d_slab.cuh"
 
 #include <algorithm>
 #include <atomic>
@@ -179,11 +180,20 @@ inline void claim(c2d_gpu_ctx* ctx, uint32_t shape, Phase phase)
     ctx->stamp[shape] = (ctx->round << 2) | static_cast<uint32_t>(phase);
 }
 
+// the boxes or the membership of a body's tree changed (the slab tree of a multi-GPU group shadows the Dynamic tree)
+inline void mark_dirty(c2d_gpu_ctx* ctx, uint32_t body)
+{
+    ctx->treeDirty[body] = true;
+    if (body == C2D_DYNAMIC)
+        ctx->slabDirty = true;
+}
+
 void member_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
 {
     ctx->memberPos[shape] = static_cast<uint32_t>(ctx->members[body].size());
     ctx->members[body].push_back(shape);
-    ctx->membersDirty[body] = ctx->treeDirty[body] = true;
+    ctx->membersDirty[body] = true;
+    mark_dirty(ctx, body);
 }
 
 void member_remove(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
@@ -194,20 +204,98 @@ void member_remove(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
     list[pos] = last;
     ctx->memberPos[last] = pos;
     list.pop_back();
-    ctx->membersDirty[body] = ctx->treeDirty[body] = true;
+    ctx->membersDirty[body] = true;
+    mark_dirty(ctx, body);
 }
 
 } // namespace
 
-int c2d_host::flush(c2d_gpu_ctx* ctx)
+namespace
 {
-    if (ctx->rounds.empty())
+// Move exchange of a multi-GPU group (c2d_gpu_comm_set_move_exchange): the frame's translation records of every rank are
+// all-gathered device to device and applied on every rank.  Collective: called by every rank's c2d_gpu_collide* flush,
+// also by ranks that logged nothing.  `local` = this rank's records in the device log, bodies = the trees they touch.
+int exchange_translations(c2d_gpu_ctx* ctx, const TransRec* hostRecs, uint32_t count, uint32_t bodies)
+{
+    CommState& cm = ctx->comm;
+    cudaStream_t s = ctx->stream;
+    const uint32_t world = ctx->shardWorld;
+    C2D_CUDA(ctx, cudaEventRecord(cm.evX[0], s));
+    C2D_CUDA(ctx, cm.dHeader.reserve(4 * (world + 1)));
+    cm.hHeader[0] = count;
+    cm.hHeader[1] = bodies;
+    cm.hHeader[2] = cm.hHeader[3] = 0;
+    C2D_CUDA(ctx, cudaMemcpyAsync(cm.dHeader.ptr, cm.hHeader, 16, cudaMemcpyHostToDevice, s));
+    if (int rc = comm_allgather(ctx, cm.dHeader.ptr, cm.dHeader.ptr + 4, 16))
+        return rc;
+    C2D_CUDA(ctx, cudaMemcpyAsync(cm.hHeader + 4, cm.dHeader.ptr + 4, 16 * world, cudaMemcpyDeviceToHost, s));
+    C2D_CUDA(ctx, cudaStreamSynchronize(s));
+    uint32_t stride = 0, touched = 0;
+    uint64_t total = 0;
+    for (uint32_t r = 0; r < world; ++r)
+    {
+        stride = std::max(stride, cm.hHeader[4 + 4 * r]);
+        total += cm.hHeader[4 + 4 * r];
+        touched |= cm.hHeader[4 + 4 * r + 1];
+    }
+    cm.exchangeBytes = (total - count) * sizeof(TransRec);
+    if (stride)
+    {
+        C2D_CUDA(ctx, cm.sendRecs.reserve(stride));
+        C2D_CUDA(ctx, cm.gathered.reserve(static_cast<size_t>(stride) * world));
+        if (count)
+        {
+            C2D_CUDA(ctx, cudaMemcpyAsync(cm.sendRecs.ptr, hostRecs, count * sizeof(TransRec), cudaMemcpyHostToDevice, s));
+            ctx->h2dBytes += count * sizeof(TransRec);
+        }
+        if (int rc = comm_allgather(ctx, cm.sendRecs.ptr, cm.gathered.ptr, static_cast<size_t>(stride) * sizeof(TransRec)))
+            return rc;
+        const size_t threads = static_cast<size_t>(stride) * world;
+        C2D_TIMED(ctx, "k_apply_translates", k_apply_translates_gathered<<<blocks_for(threads, 256), 256, 0, s>>>(
+                      cm.gathered.ptr, stride, cm.dHeader.ptr + 4, world, ctx->d));
+        ++ctx->launches;
+        for (uint32_t b = 0; b < 3; ++b)
+            if (touched & (1u << b))
+                mark_dirty(ctx, b);
+    }
+    C2D_CUDA(ctx, cudaEventRecord(cm.evX[1], s));
+    cm.exchangeTimed = true;
+    return 0;
+}
+} // namespace
+
+// collective: this flush is the one inside c2d_gpu_collide*, which every rank of a group calls in step
+int c2d_host::flush(c2d_gpu_ctx* ctx, bool collective)
+{
+    const bool exchange = ctx->comm.exchangeMoves && ctx->comm.comm && ctx->shardWorld > 1;
+    if (exchange && !collective && ctx->transLog->size)
+        return fail(ctx, "translations are pending while the move exchange is on: only c2d_gpu_collide* (the collective) may "
+                         "flush them");
+    ctx->comm.exchangeTimed = false;
+    ctx->comm.exchangeBytes = 0;
+    if (exchange && collective)
+    {
+        // the frame's translations: one round at most (an entity is translated once per frame), applied after everything else
+        uint32_t roundsWithTranslations = 0;
+        for (size_t r = 0; r < ctx->rounds.size(); ++r)
+        {
+            const size_t t1 = r + 1 == ctx->rounds.size() ? ctx->transLog->size : ctx->rounds[r + 1].t0;
+            if (ctx->rounds[r].staged >= 0)
+                return fail(ctx, "staged move batches cannot be combined with the move exchange");
+            roundsWithTranslations += t1 > ctx->rounds[r].t0 ? 1 : 0;
+        }
+        if (roundsWithTranslations > 1)
+            return fail(ctx, "move exchange: an entity may be translated only once per frame");
+    }
+    if (ctx->rounds.empty() && !(exchange && collective))
         return 0;
     cudaStream_t s = ctx->stream;
     // every id the host tables accept (c2d_gpu_shape_set_active on a stale slot, Registry.hpp:353-358) must be addressable
     if (int rc = ensure_shape_capacity(ctx, std::max<uint32_t>(ctx->shapeSlots, static_cast<uint32_t>(ctx->hostMeta.size()))))
         return rc;
-    const size_t nf = ctx->flagLog->size, na = ctx->addLog->size, nt = ctx->transLog->size, nm = ctx->moveLog->size;
+    const size_t nf = ctx->flagLog->size, na = ctx->addLog->size, nm = ctx->moveLog->size;
+    const size_t ntLogged = ctx->transLog->size;
+    const size_t nt = exchange && collective ? 0 : ntLogged; // exchanged translations take their own path below
     if (nf)
     {
         C2D_CUDA(ctx, ctx->dFlagLog.reserve(nf));
@@ -246,7 +334,7 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
         const bool lastRound = r + 1 == ctx->rounds.size();
         const size_t f1 = lastRound ? nf : ctx->rounds[r + 1].f0;
         const size_t a1 = lastRound ? na : ctx->rounds[r + 1].a0;
-        const size_t t1 = lastRound ? nt : ctx->rounds[r + 1].t0;
+        const size_t t1 = nt == 0 ? cur.t0 : (lastRound ? nt : ctx->rounds[r + 1].t0);
         const size_t m1 = lastRound ? nm : ctx->rounds[r + 1].m0;
         if (f1 > cur.f0)
         {
@@ -272,6 +360,14 @@ int c2d_host::flush(c2d_gpu_ctx* ctx)
             C2D_TIMED(ctx, "k_apply_moves", k_apply_moves<<<blocks_for(n, 256), 256, 0, s>>>(ctx->dMoveLog.ptr + cur.m0, n, ctx->d));
             ++ctx->launches;
         }
+    }
+    if (exchange && collective)
+    {
+        uint32_t bodies = 0;
+        for (size_t i = 0; i < ntLogged; ++i)
+            bodies |= 1u << meta_body(ctx->hostMeta[ctx->transLog->data[i].shape]);
+        if (int rc = exchange_translations(ctx, ctx->transLog->data, static_cast<uint32_t>(ntLogged), bodies))
+            return rc;
     }
     C2D_CUDA(ctx, cudaGetLastError());
     // The pinned logs are double buffered: the host keeps logging into the other set while these copies drain, and
@@ -372,6 +468,87 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     return 0;
 }
 
+// The Dynamic tree of this rank's Morton slab (multi-GPU, c2d_slab.cuh): keys of all Dynamic shapes and their histogram
+// (replicated, identical on every rank), balanced splitters, the cells the owned leaf boxes touch, then the selection of
+// owned + halo leaves; only those are sorted, linked and fitted.  Owned leaves sort first (halo keys belong to higher
+// slabs), so the query range of the traversals is [0, owned).
+int build_slab_tree(c2d_gpu_ctx* ctx)
+{
+    SlabState& sl = ctx->slab;
+    TreeBuf& t = ctx->slabTree;
+    cudaStream_t s = ctx->stream;
+    const uint32_t n = static_cast<uint32_t>(ctx->members[C2D_DYNAMIC].size());
+    const uint32_t world = ctx->shardWorld, rank = ctx->shardRank;
+    if (int rc = upload_members(ctx, C2D_DYNAMIC))
+        return rc;
+    const uint32_t* members = ctx->tree[C2D_DYNAMIC].members.ptr;
+    if (!sl.hCounters)
+    {
+        C2D_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&sl.hCounters), 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        C2D_CUDA(ctx, cudaEventCreate(&sl.ev[0]));
+        C2D_CUDA(ctx, cudaEventCreate(&sl.ev[1]));
+    }
+    C2D_CUDA(ctx, sl.allKeys.reserve(n));
+    C2D_CUDA(ctx, sl.allVals.reserve(n));
+    C2D_CUDA(ctx, sl.hist.reserve(static_cast<size_t>(kSlabCoarseBins) * (1 + kSlabMaxWorld)));
+    C2D_CUDA(ctx, sl.split.reserve(kSplitWords));
+    C2D_CUDA(ctx, sl.cellMask.reserve(kSlabCells * kSlabCells));
+    C2D_CUDA(ctx, sl.counters.reserve(2));
+    C2D_CUDA(ctx, t.keys.reserve(n));
+    C2D_CUDA(ctx, t.vals.reserve(n));
+
+    C2D_CUDA(ctx, cudaEventRecord(sl.ev[0], s));
+    uint32_t* bounds = &ctx->dScratch->bounds[C2D_DYNAMIC][0];
+    const uint32_t grid = std::min<uint32_t>(blocks_for(n, 256), 148 * 8);
+    C2D_CUDA(ctx, cudaMemsetAsync(sl.hist.ptr, 0, static_cast<size_t>(kSlabCoarseBins) * (1 + world) * sizeof(uint32_t), s));
+    C2D_CUDA(ctx, cudaMemsetAsync(sl.split.ptr, 0, kSplitWords * sizeof(uint32_t), s));
+    C2D_CUDA(ctx, cudaMemsetAsync(sl.cellMask.ptr, 0, kSlabCells * kSlabCells, s));
+    C2D_CUDA(ctx, cudaMemsetAsync(sl.counters.ptr, 0, 2 * sizeof(uint32_t), s));
+    C2D_TIMED(ctx, "k_bounds", k_bounds<<<grid, 256, 0, s>>>(members, n, ctx->d.fat, bounds));
+    C2D_TIMED(ctx, "k_slab_keys", k_morton_hist<<<grid, 256, 0, s>>>(members, n, ctx->d.fat, bounds, sl.allKeys.ptr, sl.allVals.ptr, sl.hist.ptr));
+    C2D_TIMED(ctx, "k_slab_split", k_slab_split1<<<1, 1024, 0, s>>>(sl.hist.ptr, n, world, sl.split.ptr));
+    C2D_TIMED(ctx, "k_slab_hist2", k_slab_hist2<<<grid, 256, 0, s>>>(sl.allKeys.ptr, n, world, sl.split.ptr, sl.hist.ptr));
+    C2D_TIMED(ctx, "k_slab_split", k_slab_split2<<<world - 1, 1024, 0, s>>>(sl.hist.ptr, world, sl.split.ptr));
+    C2D_TIMED(ctx, "k_slab_mark", k_slab_mark<<<grid, 256, 0, s>>>(sl.allKeys.ptr, sl.allVals.ptr, n, ctx->d.fat, bounds, sl.split.ptr, rank, world, sl.cellMask.ptr));
+    C2D_TIMED(ctx, "k_slab_select", k_slab_select<<<grid, 256, 0, s>>>(sl.allKeys.ptr, sl.allVals.ptr, n, ctx->d.fat, bounds, sl.split.ptr, rank, world,
+                                                                      sl.cellMask.ptr, t.keys.ptr, t.vals.ptr, sl.counters.ptr));
+    ctx->launches += 7;
+    C2D_CUDA(ctx, cudaEventRecord(sl.ev[1], s));
+    sl.timed = true;
+    C2D_CUDA(ctx, cudaMemcpyAsync(sl.hCounters, sl.counters.ptr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    C2D_CUDA(ctx, cudaStreamSynchronize(s)); // the sort and the grids below are sized by the selection
+    C2D_CUDA(ctx, cudaGetLastError());
+    const uint32_t m = sl.hCounters[0];
+    sl.selected = m;
+    sl.owned = sl.hCounters[1];
+    t.n = m;
+    ctx->slabDirty = false;
+    if (m == 0)
+        return 0;
+    C2D_CUDA(ctx, t.keysTmp.reserve(n));
+    C2D_CUDA(ctx, t.valsTmp.reserve(n));
+    C2D_CUDA(ctx, t.nodes.reserve(n));
+    C2D_CUDA(ctx, t.nodeParent.reserve(n));
+    C2D_CUDA(ctx, t.leafParent.reserve(n));
+    C2D_CUDA(ctx, t.arrival.reserve(n));
+    C2D_CUDA(ctx, t.sortWs.reserve(sort_workspace_bytes(n, 4)));
+    {
+        ProfScope ps(ctx, "radix_sort(1 memset + 5 kernels)");
+        ctx->launches += radix_sort_pairs(s, t.keys.ptr, t.vals.ptr, t.keysTmp.ptr, t.valsTmp.ptr, m, 4, t.sortWs.ptr);
+    }
+    if (m > 1)
+    {
+        C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, m * sizeof(uint32_t), s));
+        C2D_TIMED(ctx, "k_karras_build", k_karras_build<<<blocks_for(m - 1, 256), 256, 0, s>>>(t.keys.ptr, t.vals.ptr, static_cast<int>(m), t.nodes.ptr,
+                                                             t.nodeParent.ptr, t.leafParent.ptr));
+        C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(m, 256), 256, 0, s>>>(static_cast<int>(m), t.vals.ptr, ctx->d.fat, ctx->d.category,
+                                                 t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
+        ctx->launches += 2;
+    }
+    C2D_CUDA(ctx, cudaGetLastError());
+    return 0;
+}
+
 } // namespace
 
 int c2d_host::ensure_trees(c2d_gpu_ctx* ctx)
@@ -433,6 +610,16 @@ void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)
 
 void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats);
 
+// the records a query returns: this rank's, or the group's when the result mode gathered them (c2d_comm.cu)
+inline const PairOut* result_ptr(const c2d_gpu_ctx* ctx)
+{
+    return ctx->comm.resultsGathered ? ctx->comm.outAll.ptr : ctx->out.ptr;
+}
+inline uint64_t result_count(const c2d_gpu_ctx* ctx)
+{
+    return ctx->comm.resultsGathered ? ctx->comm.gatheredPairs : ctx->lastPairs;
+}
+
 // One attempt at traversal + narrowphase with the current pair-list capacities; everything is enqueued on the
 // stream, the frame counters follow in an asynchronous copy to the pinned FrameScratch.
 int pipeline_attempt(c2d_gpu_ctx* ctx)
@@ -465,11 +652,26 @@ int pipeline_attempt(c2d_gpu_ctx* ctx)
     else
     {
         // groups in the reference's order (Registry.hpp:487-545)
-        launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC);
-        launch_traverse<true>(ctx, C2D_DYNAMIC, C2D_DYNAMIC);
-        launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
-        launch_traverse<false>(ctx, C2D_BULLET, C2D_DYNAMIC);
-        launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
+        if (ctx->slabInUse)
+        {
+            // multi-GPU slab: the owned Dynamic leaves [0, owned) query; every bullet meets the OWNED Dynamic leaves of
+            // each rank exactly once (halo leaves rejected)
+            const TreeBuf& slab = ctx->slabTree;
+            const TreeBuf& bullets = ctx->tree[C2D_BULLET];
+            launch_traverse_trees<false>(ctx, slab, ctx->tree[C2D_STATIC], 0, ctx->slab.owned, 0u);
+            launch_traverse_trees<true>(ctx, slab, slab, 0, ctx->slab.owned, 0u);
+            launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
+            launch_traverse_trees<false>(ctx, bullets, slab, 0, bullets.n, kLeafGhost);
+            launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
+        }
+        else
+        {
+            launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC);
+            launch_traverse<true>(ctx, C2D_DYNAMIC, C2D_DYNAMIC);
+            launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
+            launch_traverse<false>(ctx, C2D_BULLET, C2D_DYNAMIC);
+            launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
+        }
     }
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
 
@@ -504,7 +706,7 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
     ctx->h2dBytes = 0;
 
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
-    if (int rc = flush(ctx))
+    if (int rc = flush(ctx, true))
         return rc;
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
 
@@ -521,10 +723,22 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
                 return rc;
     }
     else if (ctx->broadphase != C2D_BROADPHASE_GRID)
+    {
+        ctx->slabInUse = ctx->shardWorld > 1 && ctx->slabMinShapes > 0 && ctx->members[C2D_DYNAMIC].size() >= ctx->slabMinShapes;
         for (int body = 0; body < 3; ++body)
-            if (ctx->treeDirty[body])
+        {
+            if (body == C2D_DYNAMIC && ctx->slabInUse)
+            {
+                // the full Dynamic tree stays stale (rays and per-entity queries rebuild it on demand, ensure_trees)
+                if (ctx->slabDirty)
+                    if (int rc = build_slab_tree(ctx))
+                        return rc;
+            }
+            else if (ctx->treeDirty[body])
                 if (int rc = build_tree(ctx, body))
                     return rc;
+        }
+    }
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[2], s));
 
     if (ctx->cand.capacity == 0)
@@ -580,6 +794,8 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
     }
     ctx->lastCandidates = candCount;
     ctx->lastPairs = pairCount;
+    if (int rc = comm_gather_results(ctx)) // multi-GPU group with a result mode: collective, once per frame
+        return rc;
     if (ctx->profiling)
         collect_profile(ctx);
     if (stats)
@@ -592,7 +808,7 @@ void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
     std::memset(stats, 0, sizeof(*stats));
     stats->shapes_alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
     stats->candidates = ctx->lastCandidates;
-    stats->pairs = ctx->lastPairs;
+    stats->pairs = result_count(ctx);
     stats->h2d_bytes = ctx->h2dBytes;
     stats->d2h_bytes = ctx->frame.d2h;
     stats->kernel_launches = ctx->launches;
@@ -609,12 +825,12 @@ void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
 // Records of the last frame -> the library's pinned buffer (one copy), for the pointer-returning entry points.
 int download_records(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
 {
-    const uint64_t pairCount = ctx->lastPairs;
+    const uint64_t pairCount = result_count(ctx);
     if (pairCount)
     {
         if (!ctx->hostOut.reserve(pairCount))
             return fail(ctx, "pinned host allocation failed");
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hostOut.data, ctx->out.ptr, static_cast<size_t>(pairCount) * sizeof(PairOut),
+        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hostOut.data, result_ptr(ctx), static_cast<size_t>(pairCount) * sizeof(PairOut),
                                       cudaMemcpyDeviceToHost, ctx->stream));
         C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         ctx->frame.d2h += pairCount * sizeof(PairOut);
@@ -637,7 +853,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
     if (outRecords)
         *outRecords = reinterpret_cast<const c2d_pair_record*>(ctx->hostOut.data);
     if (outCount)
-        *outCount = ctx->lastPairs;
+        *outCount = result_count(ctx);
     return 0;
 }
 
@@ -709,6 +925,12 @@ void c2d_gpu_destroy(c2d_gpu_ctx* ctx)
     cudaFree(ctx->d.geom);
     cudaFree(ctx->dScratch);
     cudaFreeHost(ctx->hScratch);
+    comm_release(ctx);
+    if (ctx->slab.hCounters)
+        cudaFreeHost(ctx->slab.hCounters);
+    for (cudaEvent_t ev : ctx->slab.ev)
+        if (ev)
+            cudaEventDestroy(ev);
     for (StagedBatch* sb : ctx->staged)
         delete sb;
     for (auto& ev : ctx->ev)
@@ -748,7 +970,7 @@ int c2d_gpu_clear(c2d_gpu_ctx* ctx)
     {
         ctx->members[b].clear();
         ctx->membersDirty[b] = true;
-        ctx->treeDirty[b] = true;
+        mark_dirty(ctx, b);
         ctx->tree[b].n = 0;
     }
     if (ctx->capacity)
@@ -810,8 +1032,18 @@ int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world)
 {
     if (world == 0 || rank >= world)
         return fail(ctx, "c2d_gpu_set_shard: rank must be < world");
+    if (world > static_cast<uint32_t>(kSlabMaxWorld))
+        return fail(ctx, "c2d_gpu_set_shard: at most 32 ranks");
     ctx->shardRank = rank;
     ctx->shardWorld = world;
+    ctx->slabDirty = true;
+    return 0;
+}
+
+int c2d_gpu_set_slab_mode(c2d_gpu_ctx* ctx, uint32_t min_shapes)
+{
+    ctx->slabMinShapes = min_shapes;
+    ctx->slabDirty = true;
     return 0;
 }
 
@@ -902,7 +1134,7 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
     r->shape = shape;
     r->dx = dx;
     r->dy = dy;
-    ctx->treeDirty[meta_body(ctx->hostMeta[shape])] = true;
+    mark_dirty(ctx, meta_body(ctx->hostMeta[shape]));
     return 0;
 }
 
@@ -934,7 +1166,7 @@ int c2d_gpu_shape_move(c2d_gpu_ctx* ctx, uint32_t shape, const c2d_xf* xf)
     r->cos = xf->cos;
     r->csin = xf->csin;
     r->ccos = xf->ccos;
-    ctx->treeDirty[meta_body(ctx->hostMeta[shape])] = true;
+    mark_dirty(ctx, meta_body(ctx->hostMeta[shape]));
     return 0;
 }
 
@@ -993,7 +1225,7 @@ int c2d_gpu_apply_staged(c2d_gpu_ctx* ctx, uint32_t handle)
     begin_round(ctx);
     for (int b = 0; b < 3; ++b)
         if (sb->touches[b])
-            ctx->treeDirty[b] = true;
+            mark_dirty(ctx, b);
     return 0;
 }
 
@@ -1233,19 +1465,19 @@ int c2d_gpu_collide_end(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* st
     if (ctx->copyPool)
         ctx->copyPool->wait(); // the pre-fault job must not outlive the caller's storage
     if (out_count)
-        *out_count = rc ? 0 : ctx->lastPairs;
+        *out_count = rc ? 0 : result_count(ctx);
     return rc;
 }
 
 int c2d_gpu_collide_fetch(c2d_gpu_ctx* ctx, c2d_pair_record* dst, uint64_t count, c2d_gpu_stats* stats)
 {
     cudaSetDevice(ctx->device);
-    if (count > ctx->lastPairs)
+    if (count > result_count(ctx))
         return fail(ctx, "c2d_gpu_collide_fetch: more records requested than the last frame produced");
     if (count && !dst)
         return fail(ctx, "c2d_gpu_collide_fetch: dst is NULL");
     const uint64_t total = count * sizeof(PairOut);
-    if (int rc = c2d_host::copy_out(ctx, ctx->out.ptr, dst, total))
+    if (int rc = c2d_host::copy_out(ctx, result_ptr(ctx), dst, total))
         return rc;
     ctx->frame.d2h += total;
     if (stats)
@@ -1263,9 +1495,9 @@ int c2d_gpu_raycast(c2d_gpu_ctx* ctx, uint32_t, const c2d_ray*, const c2d_hit_re
 int c2d_gpu_device_records(c2d_gpu_ctx* ctx, const void** out_device_ptr, uint64_t* out_count)
 {
     if (out_device_ptr)
-        *out_device_ptr = ctx->out.ptr;
+        *out_device_ptr = result_ptr(ctx);
     if (out_count)
-        *out_count = ctx->lastPairs;
+        *out_count = result_count(ctx);
     return 0;
 }
 
@@ -1347,7 +1579,7 @@ int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const 
     C2D_CUDA(ctx, cudaStreamSynchronize(s));
     for (int body = 0; body < 3; ++body)
     {
-        ctx->treeDirty[body] = true; // every leaf box may have changed: rebuild, do not just refit
+        mark_dirty(ctx, body); // every leaf box may have changed: rebuild, do not just refit
         ctx->tree[body].membershipChanged = true;
     }
     return 0;

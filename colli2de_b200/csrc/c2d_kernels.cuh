@@ -103,12 +103,8 @@ __global__ void __launch_bounds__(128) k_apply_adds(const AddRec* __restrict__ l
 }
 
 // Registry::moveEntity(id, Translation) (reference Registry.hpp:434-453, 214-231)
-__global__ void __launch_bounds__(256) k_apply_translates(const TransRec* __restrict__ log, uint32_t n, ShapeArrays s)
+__device__ __forceinline__ void apply_translate(const TransRec rec, const ShapeArrays& s)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n)
-        return;
-    const TransRec rec = log[i]; // 12-byte records: three coalesced 4-byte loads per thread
     const uint32_t shape = rec.shape;
     const float dx = rec.dx, dy = rec.dy;
     const uint32_t meta = s.meta[shape];
@@ -134,6 +130,27 @@ __global__ void __launch_bounds__(256) k_apply_translates(const TransRec* __rest
     t.x += dx;
     t.y += dy;
     s.xf[shape] = t;
+}
+
+__global__ void __launch_bounds__(256) k_apply_translates(const TransRec* __restrict__ log, uint32_t n, ShapeArrays s)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    apply_translate(log[i], s); // 12-byte records: three coalesced 4-byte loads per thread
+}
+
+// The same over the all-gathered records of a multi-GPU group (c2d_gpu.cu: flush with the move exchange on):
+// `world` blocks of `stride` records, block r holding header[4 * r] valid ones.
+__global__ void __launch_bounds__(256) k_apply_translates_gathered(const TransRec* __restrict__ gathered, uint32_t stride,
+                                                                   const uint32_t* __restrict__ header, uint32_t world,
+                                                                   ShapeArrays s)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t r = i / stride, k = i - r * stride;
+    if (r >= world || k >= header[4 * r])
+        return;
+    apply_translate(gathered[i], s);
 }
 
 // Registry::moveEntity(id, Transform) / teleportEntity(id, Transform) (reference Registry.hpp:382-432, 191-212)

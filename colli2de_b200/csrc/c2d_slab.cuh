@@ -10,7 +10,8 @@
 //   k_slab_select    this rank's leaves: owned shapes + halo = shapes of HIGHER ranks whose leaf box touches a marked
 //                    cell (two overlapping boxes share a point, hence a cell).  Owner rule: a pair is emitted by the rank
 //                    that owns its first shape in global (key, slab) order; shapes of lower ranks come earlier in that
-//                    order, so they never have to be in the halo.  Halo leaves carry bit 31 in the sorted value array.
+//                    order, so they never have to be in the halo.  Halo leaves carry kLeafGhost (bit 30) in the sorted value array and in
+//                    their leaf link.
 #pragma once
 
 #include "c2d_internal.hpp"
@@ -18,14 +19,12 @@
 namespace c2d_dev
 {
 
-constexpr uint32_t kSlabGhostBit = 0x80000000u;
 constexpr uint32_t kSlabCoarseBins = 4096;
 constexpr int kSlabMaxWorld = 32;
 constexpr uint32_t kSlabCells = 256; // per axis
 constexpr int kSlabMaxCellSpan = 16; // boxes wider than this many cells are treated as touching everything
 
-// split[]: [0 .. world] splitter keys as uint64 halves? no: uint32 keys, split[world] is implied (2^32).
-// layout of the uint32 split buffer: [0..31] splitter keys (split[0] = 0), [32..63] coarse bin of splitter j,
+// layout of the uint32 split buffer (split[world] is implied: 2^32): [0..31] splitter keys (split[0] = 0), [32..63] coarse bin of splitter j,
 // [64..95] residual rank inside that bin, [96] "some owned box spans too many cells" flag.
 constexpr int kSplitKeys = 0, kSplitBin = 32, kSplitRest = 64, kSplitHuge = 96, kSplitWords = 128;
 
@@ -287,7 +286,7 @@ __global__ void __launch_bounds__(256) k_slab_select(const uint32_t* __restrict_
         {
             const uint32_t pos = slot + __popc(tb & ((1u << lane) - 1u));
             outKeys[pos] = key;
-            outVals[pos] = owned ? shape : (shape | kSlabGhostBit);
+            outVals[pos] = owned ? shape : (shape | kLeafGhost);
         }
     }
 }

@@ -133,9 +133,56 @@ int c2d_gpu_mutation_epoch(c2d_gpu_ctx* ctx, uint64_t* out_epoch);
  * lists and one narrowphase kernel (same candidate predicate, same results) - the ~30 dependent launches of the
  * tree pipeline cost more than the work at that size.  Default 8192; 0 disables the shortcut. */
 int c2d_gpu_set_small_scene_limit(c2d_gpu_ctx* ctx, uint32_t shapes);
-/* Multi-GPU sharding of the query leaves: this context emits only the pairs whose
- * query leaf lies in Morton-rank slab `rank` of `world`.  Default 0 of 1. */
+/* ---- multi-GPU --------------------------------------------------------------------
+ * One context per GPU (one process per GPU under torchrun, or several contexts in one process).  Shape state is
+ * REPLICATED: every rank of a group replays every mutation (or receives the other ranks' translations, below), so
+ * ownership needs no communication - every rank derives the same Morton keys and the same slab boundaries from the same
+ * boxes.  What is sharded is the per-frame work of Registry::getCollidingPairs (Registry.hpp:464-549): each rank sorts,
+ * builds, refits and traverses only ITS slab and returns its share of the pairs; the union over the ranks is the
+ * reference's pair set, each pair exactly once (owner rule).  (The grid broadphase splits its sorted cell entries instead.)
+ *
+ * c2d_gpu_set_shard: this context is `rank` of `world`.  Default 0 of 1.
+ *   - the Dynamic tree (c2d_gpu_set_slab_mode, below) is cut into Morton-key slabs balanced from the global key histogram
+ *     every frame; a rank's tree holds the shapes whose key falls into its slab plus the HALO: shapes of higher ranks whose
+ *     leaf box may overlap an owned one.  Only owned leaves query; a pair of two slabs is emitted by the lower rank.
+ *   - Bullet queries are split by index range; Bullet x Dynamic pairs are emitted by the rank that owns the Dynamic shape. */
 int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world);
+/* Morton-slab build of the Dynamic tree when world > 1 and the tree has at least `min_shapes` leaves (smaller trees are
+ * mirrored on every rank and only the query leaves are split).  0 = never.  Default 65536. */
+int c2d_gpu_set_slab_mode(c2d_gpu_ctx* ctx, uint32_t min_shapes);
+/* The NCCL communicator of the group (libnccl.so.2 is loaded with dlopen on first use; C2D_NCCL_LIB overrides the path).
+ * c2d_gpu_comm_unique_id writes the 128-byte ncclUniqueId that rank 0 hands to the other ranks (by any out-of-band
+ * channel: torch.distributed, MPI, a file); c2d_gpu_comm_init is collective over the group and implies
+ * c2d_gpu_set_shard(rank, world). */
+int c2d_gpu_comm_unique_id(void* out_id128);
+int c2d_gpu_comm_init(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world, const void* id128);
+int c2d_gpu_comm_destroy(c2d_gpu_ctx* ctx);
+/* Move exchange (off by default = every rank logs every move itself).  On: each rank logs only the translations
+ * (c2d_gpu_shape_translate / c2d_gpu_shapes_translate) of the entities IT drives; the next c2d_gpu_collide* all-gathers
+ * the 12-byte records of all ranks over NVLink (ncclAllGather, device to device) and applies them everywhere, so the
+ * host-to-device upload of a frame shrinks to 1 / world per rank.  Contract: an entity is translated by one rank and at
+ * most once per frame; every other mutation stays replicated and is applied BEFORE the frame's translations; while
+ * translations are pending only c2d_gpu_collide* may flush them (it is the collective). */
+int c2d_gpu_comm_set_move_exchange(c2d_gpu_ctx* ctx, int on);
+/* Where the 84-byte records of a frame end up: C2D_RESULTS_LOCAL every rank keeps its share; C2D_RESULTS_ALL every rank
+ * receives all records (ncclAllGather of the counts + one ncclBroadcast per rank, device to device, in rank order);
+ * C2D_RESULTS_ROOT rank 0 receives all records (ncclSend / ncclRecv), the others keep their share. */
+enum { C2D_RESULTS_LOCAL = 0, C2D_RESULTS_ALL = 1, C2D_RESULTS_ROOT = 2 };
+int c2d_gpu_comm_set_result_mode(c2d_gpu_ctx* ctx, int mode);
+/* Collectives of the last c2d_gpu_collide* on this rank: payload bytes received and device milliseconds (CUDA events
+ * around the NCCL calls on the context's stream). */
+typedef struct c2d_gpu_comm_stats
+{
+    uint64_t exchange_bytes;  /* translation records received from all ranks */
+    uint64_t gather_bytes;    /* pair records received */
+    uint64_t local_pairs;     /* pairs this rank computed */
+    uint64_t slab_owned;      /* Dynamic leaves this rank owns / leaves in its tree incl. the halo */
+    uint64_t slab_leaves;
+    float ms_exchange;
+    float ms_gather;
+    float ms_slab;            /* keys + histogram + splitters + selection of the slab (before the sort) */
+} c2d_gpu_comm_stats;
+int c2d_gpu_comm_get_stats(c2d_gpu_ctx* ctx, c2d_gpu_comm_stats* out);
 
 /* Per-kernel CUDA-event timing of the queries (off by default).  c2d_gpu_kernel_profile writes one line per
  * kernel name, "name<TAB>launches<TAB>total_ms", accumulated since the last reset. */

@@ -52,6 +52,45 @@ def test_strong_query_slabs(method, world):
         assert got.tobytes() == want.tobytes()
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_morton_slab_trees(world):
+    """The in-library decomposition (c2d_gpu_set_shard + c2d_gpu_set_slab_mode): every rank mirrors the
+    shape state, owns one Morton-key slab of the Dynamic tree (+ the halo of higher slabs) and returns its share; the
+    union over the ranks is the single-registry result, each pair once; the slabs are balanced although the scene is
+    clustered; bullets and static shapes included."""
+    sc = _scene()
+    movable = sc["ent_body"] != 0
+    full = H.Backend(SUBJECT)
+    scenes.populate(full, sc)
+    ranks = []
+    for r in range(world):
+        b = H.Backend(SUBJECT)
+        scenes.populate(b, sc)
+        capi.set_shard(b.native_context(), r, world)
+        capi.set_slab_mode(b.native_context(), 1000)
+        ranks.append(b)
+    alive = np.ones(len(sc["ent_id"]), bool)
+    for f, d in enumerate(_moves(sc, 4)):
+        for b in [full] + ranks:
+            b.move_translate(sc["ent_id"][movable], d[movable])
+        if f == 2:  # a structural change in the middle: the slabs follow
+            for b in [full] + ranks:
+                b.remove_entities(sc["ent_id"][100:140])
+            alive[100:140] = False
+            movable = movable & alive
+        want = P.sort_pairs(full.get_colliding_pairs())
+        parts = [b.get_colliding_pairs() for b in ranks]
+        stats = [capi.comm_stats(b.native_context()) for b in ranks]
+        got = P.sort_pairs(np.concatenate(parts))
+        assert len(want) > 5000
+        assert got.tobytes() == want.tobytes()
+        owned = np.array([s["slab_owned"] for s in stats])
+        leaves = np.array([s["slab_leaves"] for s in stats])
+        assert owned.sum() == int(((sc["ent_body"] == 1) & alive).sum())  # every Dynamic shape (one per entity) has one owner
+        assert owned.min() > 0.8 * owned.sum() / world and owned.max() < 1.2 * owned.sum() / world, owned
+        assert (leaves >= owned).all() and leaves.sum() < 1.6 * owned.sum(), (owned, leaves)
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_weak_spatial_slabs_with_ghosts(world):
     sc = _scene()
