@@ -175,7 +175,46 @@ def run_reference(args, scene, n_dyn, as_baseline: bool):
 
 
 # ---------------------------------------------------------------------------------------------------------
-def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
+def workload_label(name: str, n_dyn: int, n_sta: int) -> str:
+    """config.workload, the same string on both arms"""
+    return (f"{name}: {n_dyn} dynamic mixed circle/capsule/segment/polygon + {n_sta} static polygons, per-frame jitter "
+            f"U(-0.5,0.5)^2, LCG seed 4242 (SURVEY.md 8(d) cfg 3)")
+
+
+def parity_frames(b, scene, dyn, chunk, rank, world, frames: int):
+    """`frames` frames of the e2e configuration (move exchange on, results gathered to rank 0 when N > 1) compared with
+    the UNMODIFIED reference on rank 0: exact tuple set, manifolds within 1e-5 (bit-identical counted), orientation-
+    ambiguous segment pairs classified.  Collective over the ranks."""
+    from tests import harness as H, parity as P
+
+    which = "reference" if H.available("reference") else "oracle"
+    ref, idx = None, None
+    if rank == 0:
+        ref = H.Backend(which)
+        scenes.populate(ref, scene)
+        idx = P.SceneIndex(scene)
+    rng = scenes.LCG(777)
+    out = {"checker": "oracle/_ref (the unmodified reference)" if which == "reference" else "oracle/c2d_oracle.c",
+           "frames": frames, "expected": 0, "got": 0, "ambiguous": 0, "bit_identical": 0, "not_bit_identical": 0, "ok": True}
+    for _ in range(frames):
+        d = scenes.jitter(rng, len(dyn), 0.5)
+        b.move_translate(dyn[chunk], d[chunk])
+        got = b.get_colliding_pairs()
+        if rank == 0:
+            ref.move_translate(dyn, d)
+            try:
+                res = P.compare_pairs(which, ref, idx, ref.get_colliding_pairs(), got)
+                for k in ("expected", "got", "ambiguous", "bit_identical", "not_bit_identical"):
+                    out[k] += res[k]
+            except AssertionError as e:  # reported, not hidden: the line says parity failed
+                out["ok"] = False
+                out["error"] = str(e)[:300]
+    if ref is not None:
+        ref.close()
+    return out
+
+
+def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     import torch
     import torch.distributed as dist
 
@@ -189,28 +228,15 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     capi.lib()  # fail loudly if libc2d_gpu.so is missing
     b = H.Backend("b200", 1 if args.grid_cell > 0 else 0, max(args.grid_cell, 1))
-    weak = world > 1 and args.scaling in ("auto", "weak")
-    n_total_dyn, n_total_sta = n_dyn, n_sta
-    if weak:
-        # this rank's spatial slab of the N-times larger world + halo copies of the neighbours' boundary shapes
-        world_body = scene["ent_body"]
-        world_ids = scene["ent_id"]
-        scene, ghost_mask, local_index, owned_mask, export_mask = local_slab(scene, rank, world)
-        owned_dyn = world_ids[owned_mask & (world_body != 0)]
-        export_dyn = world_ids[export_mask & (world_body != 0)]
-        ghost_dyn = np.sort(scene["ent_id"][ghost_mask & (scene["ent_body"] != 0)])
-        ids = scenes.populate(b, scene)
-        b.set_ghost(ids[ghost_mask], np.ones(int(ghost_mask.sum()), np.uint8))
-        dyn = scene["ent_id"][scene["ent_body"] != 0]
-        n_dyn, n_sta = len(dyn), len(scene["ent_id"]) - len(dyn)
-    else:
-        scenes.populate(b, scene)
-        dyn = np.arange(n_dyn, dtype=np.uint32)
+    scenes.populate(b, scene)  # every rank mirrors the scene; the per-frame work is what the library shards
+    dyn = np.arange(n_dyn, dtype=np.uint32)
     ctx = b.native_context()
-    if not weak:
-        capi.set_shard(ctx, rank, world)
+    if world > 1:
+        b.group_join_torch()  # Registry::joinGroup: one NCCL communicator over the ranks' contexts
     capi.set_rebuild_period(ctx, args.rebuild_period)
     K, W = args.steps, args.warmup
+    # the entities this rank drives in the end-to-end loop (move exchange): one contiguous block of the dynamic ids
+    chunk = slice((n_dyn * rank) // world, (n_dyn * (rank + 1)) // world)
 
     def barrier():
         if world > 1:
@@ -231,16 +257,20 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
+    # ---- parity against the reference, in the end-to-end configuration ---------------------------------------------
+    if world > 1:
+        b.group_options(results=capi.RESULTS_ROOT, exchange=True)
+    parity = None
+    if args.parity_frames > 0:
+        parity = parity_frames(b, scene, dyn, chunk if world > 1 else slice(None), rank, world, args.parity_frames)
+    if world > 1:
+        b.group_options(results=capi.RESULTS_LOCAL, exchange=False)
+
     # ---- device-resident arm: move batches staged in HBM before the timed region -------------------------------
     rng = scenes.LCG(2024)
 
     def frame_moves():
-        """The frame's move of every dynamic entity this rank holds.  Weak mode: the moves are a function of the global
-        entity id (every rank draws the world's stream and keeps its slab), so halo copies move exactly like their
-        originals without any exchange."""
-        if not weak:
-            return scenes.jitter(rng, n_dyn, 0.5)
-        return scenes.jitter(rng, n_total_dyn, 0.5)[dyn]
+        return scenes.jitter(rng, n_dyn, 0.5)
 
     handles = [b.stage_translations(dyn, frame_moves()) for _ in range(W + K)]
     for h in handles[:W]:
@@ -253,6 +283,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     pairs_total = 0
     stage_ms = dict(ms_refit=0.0, ms_build=0.0, ms_broad=0.0, ms_narrow=0.0, ms_device=0.0)
     cand_total = 0
+    slab = dict(slab_owned=0.0, slab_leaves=0.0, ms_slab=0.0)
     barrier()
     t0 = time.perf_counter()
     for h in handles[W:]:
@@ -264,6 +295,10 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
         launches += int(st["kernel_launches"])
         for k in stage_ms:
             stage_ms[k] += st[k]
+        if world > 1:
+            cs = capi.comm_stats(ctx)
+            for k in slab:
+                slab[k] += cs[k]
     barrier()
     elapsed = allmax(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
@@ -277,77 +312,63 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     value = pairs_all / elapsed
 
     # ---- end-to-end arm: host buffers through the drop-in API ----------------------------------------------------
-    from colli2de_b200 import sharding
-    from tests.harness import PAIR_DTYPE
+    # N > 1: every rank calls moveEntity for the block of entities it drives (1/N of the host work and of the upload);
+    # the library all-gathers the 12-byte records over NVLink inside getCollidingPairs (move exchange), each rank
+    # computes its Morton slab and returns ITS share of the pairs into its own host memory.
+    def e2e_loop(frames: int, skip: int):
+        times, moves, pairs, up, down, xms, gms, xbytes, gbytes = [], [], 0, 0.0, 0.0, [], [], 0.0, 0.0
+        for f in range(skip + frames):
+            d = frame_moves()
+            if f == skip:
+                barrier()
+            tm = time.perf_counter()
+            b.move_translate(dyn[chunk], d[chunk])
+            tm = time.perf_counter() - tm
+            sec = C.c_double(0.0)
+            n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
+            b._check()
+            if f >= skip:
+                st = b.stats()
+                times.append(sec.value)
+                moves.append(tm)
+                pairs += n
+                up += st["h2d_bytes"]
+                down += st["d2h_bytes"]
+                if world > 1:
+                    cs = capi.comm_stats(ctx)
+                    xms.append(cs["ms_exchange"])
+                    gms.append(cs["ms_gather"])
+                    xbytes += cs["exchange_bytes"]
+                    gbytes += cs["gather_bytes"]
+        barrier()
+        return dict(elapsed=allmax(float(np.sum(times))), pairs=pairs, h2d=allsum(up) / frames, d2h=allsum(down) / frames,
+                    moves_ms=allmax(1e3 * float(np.mean(moves))), exchange_ms=float(np.mean(xms)) if xms else 0.0,
+                    gather_ms=float(np.mean(gms)) if gms else 0.0, exchange_bytes=xbytes / frames, gather_bytes=gbytes / frames)
 
-    e2e_times, move_times, e2e_pairs, h2d, d2h, gather_times, exchange_times = [], [], 0, 0.0, 0.0, [], []
-    pinned = {}
-    plan, ghost_ids = None, None
-    for f in range(2 + K):
-        tx = 0.0
-        if weak:
-            # the exchange step of the decomposition: a rank decides the moves of the entities it OWNS; the moves of its
-            # boundary entities reach the neighbours' halo copies through one NCCL all-gather per frame
-            d_world = scenes.jitter(rng, n_total_dyn, 0.5)
-            if plan is None:
-                # built once for the decomposition: where in the all-gathered buffer each halo copy's move arrives
-                plan = sharding.ExchangePlan(export_dyn, ghost_dyn)
-                ghost_ids = ghost_dyn[plan.found]
-            d_export = d_world[export_dyn]
-            dist.barrier()
-            tx = time.perf_counter()
-            d_ghost = plan.exchange(d_export)
-            tx = time.perf_counter() - tx
-            step_ids = np.concatenate([owned_dyn, ghost_ids])
-            d = np.concatenate([d_world[owned_dyn], d_ghost[plan.found]])
-        else:
-            step_ids, d = dyn, frame_moves()
-        if f == 2:
-            barrier()
-        tm = time.perf_counter()
-        b.move_translate(step_ids, d)
-        tm = time.perf_counter() - tm
-        sec = C.c_double(0.0)
-        tg = 0.0
-        # every rank: Registry::getCollidingPairs() of ITS registry (its slab), host vector and all; the union of the
-        # ranks' vectors is the world's pair set, each pair exactly once (owner rule; tests/test_gpu_sharding.py)
-        n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
-        b._check()
-        st_frame = b.stats()
-        if world > 1:
-            # optional global view, NOT part of e2e: the 84-byte records of all ranks gathered GPU-to-GPU (NCCL) and
-            # downloaded once on rank 0
-            dist.barrier()
-            tg = time.perf_counter()
-            ptr, cnt = capi.device_records(ctx)
-            gathered, total = sharding.gather_device_records(ptr, cnt, PAIR_DTYPE.itemsize, dst=0, pinned=pinned)
-            torch.cuda.synchronize()
-            tg = time.perf_counter() - tg
-            if rank == 0 and f == 2:
-                recs = np.frombuffer(gathered.tobytes(), dtype=PAIR_DTYPE)
-                key = ["entityA", "entityB"] if weak else ["shapeA", "shapeB"]  # shape ids are rank-local in weak mode
-                assert len(recs) == total and len(np.unique(recs[key])) == total, "duplicate pair across slabs"
-        if f >= 2:
-            st = st_frame
-            e2e_times.append(sec.value + tx)
-            gather_times.append(tg)
-            exchange_times.append(tx)
-            move_times.append(tm)
-            e2e_pairs += n
-            h2d += st["h2d_bytes"]
-            d2h += st["d2h_bytes"]
+    if world > 1:
+        b.group_options(results=capi.RESULTS_LOCAL, exchange=True)
+    e2e = e2e_loop(K, 2)
+    e2e_pairs_all = allsum(float(e2e["pairs"]))
+    root = None
+    if world > 1:
+        # the single-caller view: all records gathered to rank 0 over NVLink and downloaded there
+        b.group_options(results=capi.RESULTS_ROOT, exchange=True)
+        root = e2e_loop(min(K, 8), 1)
+        b.group_options(results=capi.RESULTS_LOCAL, exchange=False)
     # same loop through the zero-copy extension (a view of the pinned result buffer instead of a fresh std::vector)
     view_times = []
-    for f in range(1 + min(K, 8)):
-        b.move_translate(dyn, frame_moves())
-        sec, ptr = C.c_double(0.0), C.c_void_p()
-        b.lib.rn_get_colliding_pairs_view(b.ctx, C.byref(sec), C.byref(ptr))
-        b._check()
-        if f >= 1:
-            view_times.append(sec.value)
+    if world == 1:
+        for f in range(1 + min(K, 8)):
+            b.move_translate(dyn, frame_moves())
+            sec, ptr = C.c_double(0.0), C.c_void_p()
+            b.lib.rn_get_colliding_pairs_view(b.ctx, C.byref(sec), C.byref(ptr))
+            b._check()
+            if f >= 1:
+                view_times.append(sec.value)
     barrier()
-    e2e_elapsed = allmax(float(np.sum(e2e_times)))
-    e2e_pairs_all = allsum(float(e2e_pairs))
+    e2e_elapsed = e2e["elapsed"]
+    if world > 1:
+        b.group_leave()
 
     if rank != 0:
         return None
@@ -356,26 +377,32 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     peak, peak_src = measured_peak_gbs()
     dom_name, (dom_count, dom_ms) = max(profile.items(), key=lambda kv: kv[1][1])
     n_shapes = n_dyn + n_sta
-    cand_per_frame = cand_all / K / world
-    pairs_per_frame = pairs_all / K
+    cand_per_frame = cand_all / K / world        # per rank
+    pairs_per_frame = pairs_all / K              # whole job
+    n_query = slab["slab_owned"] / K if world > 1 and slab["slab_owned"] else n_dyn   # Dynamic query leaves of this rank
+    n_tree = slab["slab_leaves"] / K if world > 1 and slab["slab_leaves"] else n_dyn  # leaves of its Dynamic tree
     g_all = geometry_bytes(scene, np.ones(n_shapes, bool))
     g_np = float(np.where(scene["shp_type"] == 3, 4 + 16 * scene["shp_count"].astype(np.float64),
                           np.where(scene["shp_type"] == 0, 12, np.where(scene["shp_type"] == 1, 20, 16))).mean())
     alg = {
         # per-launch algorithmic bytes of each kernel (DESIGN.md "Roofline")
         "k_apply_translates": n_dyn * (12 + 4 + 16 + 16 + 16 + 16 + 16 + 16),
-        "k_traverse<self>": n_dyn * (4 + 16 + 8) + (n_dyn - 1) * 64 + 0.8 * cand_per_frame * 8,
-        "k_traverse<cross>": n_dyn * (4 + 16 + 8) + (n_sta - 1) * 64 + 0.2 * cand_per_frame * 8,
+        "k_traverse<self>": n_query * (4 + 16 + 8) + (n_tree - 1) * 64 + 0.8 * cand_per_frame * 8,
+        "k_traverse<cross>": n_query * (4 + 16 + 8) + (n_sta - 1) * 64 + 0.2 * cand_per_frame * 8,
         # narrowphase: the polygon bin (polygon vs polygon|capsule|segment) holds ~45 % of the candidates of this mix
         "k_narrow_filter": 0.55 * cand_per_frame * (8 + 2 * (4 + 4 + 16 + 20)) + 0.2 * cand_per_frame * 16,
         "k_narrow_filter_pp": 0.45 * cand_per_frame * (8 + 2 * (4 + 4 + 16 + 4 + 16 * 5.5)) + 0.15 * cand_per_frame * 16,
         "k_narrow_manifold": 0.55 * pairs_per_frame / world * (16 + 2 * (4 + 4 + 16 + 20) + 84),
         "k_narrow_manifold_pp": 0.45 * pairs_per_frame / world * (16 + 2 * (4 + 4 + 16 + 4 + 16 * 5.5) + 84),
-        "radix_sort(1 memset + 5 kernels)": n_dyn * (4 + 4 * 16),
-        "k_fit": n_dyn * (4 + 16 + 8 + 4) + (n_dyn - 1) * (64 + 4 + 4),
-        "k_karras_build": n_dyn * 4 + (n_dyn - 1) * (16 + 8),
+        "radix_sort(1 memset + 5 kernels)": n_tree * (4 + 4 * 16),
+        "k_fit": n_tree * (4 + 16 + 8 + 4) + (n_tree - 1) * (64 + 4 + 4),
+        "k_karras_build": n_tree * 4 + (n_tree - 1) * (16 + 8),
         "k_morton": n_dyn * (4 + 16 + 8),
         "k_bounds": n_dyn * (4 + 16),
+        "k_slab_keys": n_dyn * (4 + 16 + 8),
+        "k_slab_hist2": n_dyn * 4,
+        "k_slab_mark": n_dyn * (8 + 16 / world),
+        "k_slab_select": n_dyn * (8 + 16) + n_tree * 8,
         "k_bin_count": cand_per_frame * (8 + 8),
         "k_bin_scatter": cand_per_frame * (8 + 8 + 8),
     }
@@ -386,60 +413,73 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local):
     kernels = {k: {"launches": c, "avg_ms": ms / max(c, 1), "share": ms / max(sum(v[1] for v in profile.values()), 1e-9),
                    "alg_gbs": (alg.get(k, 0.0) / (ms / max(c, 1) * 1e-3) / 1e9) if ms > 0 else 0.0}
                for k, (c, ms) in sorted(profile.items(), key=lambda kv: -kv[1][1])}
-    # DRAM traffic per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/)
+    # DRAM traffic per launch of the dominant kernel from the newest committed `ncu --set full` capture (profiles/)
     traffic, traffic_src = None, None
-    tpath = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
-    if os.path.exists(tpath):
+    tpaths = sorted(p for p in os.listdir(os.path.join(REPO, "profiles")) if p.endswith("_ncu_traffic.json"))
+    if tpaths and world == 1 and args.workload == "cfg3-clustered":
+        tdoc = json.load(open(os.path.join(REPO, "profiles", tpaths[-1])))
         ncu_name = {"k_traverse<self>": "k_traverse<1>", "k_traverse<cross>": "k_traverse<0>"}.get(dom_name, dom_name)
-        rec = json.load(open(tpath)).get(ncu_name)
+        rec = tdoc.get(ncu_name)
         if rec:
             traffic = rec["dram"]
-            traffic_src = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/r01_ncu_full_top_kernels_v3.csv "
-                           f"(cold-cache, serialised replay; {rec['launches_profiled']} launches)")
+            traffic_src = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/{tpaths[-1]} "
+                           f"({tdoc.get('_source', 'ncu --set full')}; cold-cache, serialised replay; "
+                           f"{rec['launches_profiled']} launches)")
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "alg_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_avg_ms,
                 "frame": {"alg_bytes": frame_alg, "achieved": frame_alg / (ms_per_step * 1e-3) / 1e9,
                           "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak},
-                "note": "latency/divergence-bound path (SURVEY.md 8(d)): whole-frame algorithmic traffic is ~0.2 GB",
+                "note": "latency/divergence-bound path (SURVEY.md 8(d)): whole-frame algorithmic traffic is ~0.2-0.3 GB",
                 "kernels": kernels}
 
+    if world == 1:
+        parallelism = "single GPU"
+    else:
+        parallelism = (f"{'weak: ' + str(world) + ' x the workload in one world' if weak else 'strong: the fixed workload'} on {world} "
+                       f"GPUs, one process each; in-library decomposition (include/c2d_gpu.h multi-GPU): scene mirrored, the "
+                       f"Dynamic tree cut into Morton-key slabs balanced from the key histogram every frame (rank 0: "
+                       f"{n_query:.0f} owned + {n_tree - n_query:.0f} halo leaves of {n_dyn}), owner rule, no data-path "
+                       f"collective in the device-resident loop; e2e loop: ncclAllGather of the 12-byte move records")
+    e2e_out = {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
+               "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
+               "moves_host_ms": e2e["moves_ms"],
+               "whole_frame_ms": e2e["moves_ms"] + 1e3 * e2e_elapsed / K,
+               "call": ("c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity" if world == 1
+                        else "per rank: moveEntity(id, Translation) for the 1/N of the entities it drives, then the collective "
+                             "c2d::Registry<uint32_t>::getCollidingPairs() returning the rank's share into host memory; time = "
+                             "max over ranks, pairs = sum over ranks")}
+    if world == 1:
+        e2e_out["view_ms_per_step"] = 1e3 * float(np.mean(view_times))
+        e2e_out["view_call"] = "Registry::getCollidingPairsView() (extension: span over the pinned result buffer)"
+    else:
+        e2e_out["collective"] = {"name": "ncclAllGather (16-byte header + 12-byte move records, device to device)",
+                                 "bytes_received_per_rank_per_step": e2e["exchange_bytes"],
+                                 "device_ms_per_step": e2e["exchange_ms"]}
+        e2e_out["root_gather"] = {"what": "GroupResults::Root - all records gathered to rank 0 over NVLink (ncclAllGather of "
+                                          "the counts + ncclSend/ncclRecv) and returned by rank 0's getCollidingPairs()",
+                                  "ms_per_step": 1e3 * root["elapsed"] / min(K, 8),
+                                  "gather_bytes_per_step": root["gather_bytes"], "gather_device_ms": root["gather_ms"]}
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {n_dyn} dynamic mixed circle/capsule/segment/polygon + {n_sta} static "
-                               f"polygons, per-frame jitter U(-0.5,0.5)^2, LCG seed 4242 (SURVEY.md 8(d) cfg 3)",
-                   "parallelism": ("single GPU" if world == 1 else
-                                   f"weak: {world} x the workload ({n_total_dyn} dynamic + {n_total_sta} static in one world), one "
-                                   f"equal-population x-slab per GPU + halo copies within {HALO_MARGIN} units, owner rule, no "
-                                   f"data-path collective in the device-resident loop (moves are a function of the global id); the e2e "
-                                   f"loop exchanges the boundary moves with one NCCL all-gather per frame "
-                                   f"(rank 0 slab: {n_dyn} dynamic + {n_sta} static incl. halo)" if weak else
-                                   f"strong: fixed workload mirrored on {world} GPUs, query leaves sharded by Morton-rank slab"),
+        "config": {"workload": workload_label(args.workload, n_dyn, n_sta),
+                   "parallelism": parallelism,
                    "l2": "inputs larger than L2 (fresh 12 MB move batch per frame; ~255 MB shape state + ~100 MB "
                          "sort/tree buffers rewritten every frame vs 126 MB L2), no explicit flush",
                    "lbvh_rebuild_period": args.rebuild_period,
                    "broadphase": f"uniform grid, cell {args.grid_cell}" if args.grid_cell > 0 else "LBVH",
                    "pairs_per_frame": pairs_per_frame, "candidates_per_frame": cand_per_frame * world,
                    "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()}},
-        "e2e": {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
-                "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
-                "moves_host_ms": 1e3 * float(np.mean(move_times)),
-                "gather_to_rank0_ms_per_step": 1e3 * float(np.mean(gather_times)) if gather_times else 0.0,
-                "gather_note": "optional global view (all ranks' records gathered over NCCL + one download on rank 0); NOT "
-                               "part of e2e.value: every rank returns the pairs of its own slab to its own host",
-                "boundary_exchange_ms_per_step": 1e3 * float(np.mean(exchange_times)) if exchange_times else 0.0,
-                "view_ms_per_step": 1e3 * float(np.mean(view_times)),
-                "view_call": "Registry::getCollidingPairsView() (extension: span over the pinned result buffer)",
-                "call": ("c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity" if world == 1
-                         else "per rank: boundary-move exchange (ExchangePlan: one NCCL all-gather of the 8-byte moves) + "
-                              "c2d::Registry<uint32_t>::getCollidingPairs() of the rank's slab into host memory; time = max "
-                              "over ranks, pairs = sum over ranks")},
+        "e2e": e2e_out,
+        "parity": parity,
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,
     }
+    if world > 1:
+        out["config"]["slab_ms_per_step"] = slab["ms_slab"] / K
     return out
 
 
@@ -460,10 +500,11 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--scaling", default="auto", choices=["auto", "weak", "strong"],
-                    help="multi-GPU mode: weak = the world grows with N (N x the workload, every rank owns one spatial slab "
-                         "+ halo copies, no data-path collective); strong = the fixed workload mirrored on every rank, "
-                         "query leaves sharded by Morton slab.  auto = weak for N > 1")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="multi-GPU mode: strong (default) = the metric's fixed workload on N GPUs; weak = an N-times larger "
+                         "world at the same density.  Either way the library cuts the Dynamic tree into Morton-key slabs")
+    ap.add_argument("--parity-frames", type=int, default=2,
+                    help="frames compared with the unmodified reference on rank 0 before the timed regions (0 = skip)")
     ap.add_argument("--grid-cell", type=int, default=0,
                     help="> 0: use Registry<Grid>(cell) = the uniform-grid sort-and-sweep broadphase instead of the LBVH")
     ap.add_argument("--rebuild-period", type=int, default=4,
@@ -475,23 +516,22 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        weak = args.gpus > 1 and args.scaling in ("auto", "weak")
+        weak = args.gpus > 1 and args.scaling == "weak"
         scene, n_dyn, n_sta = build_scene(args.workload, args.gpus if weak else 1)
         r = run_reference(args, scene, n_dyn, as_baseline=False)
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                 "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {n_dyn} dynamic + {n_sta} static (same scene and seed as the own arm)",
-                           "pairs_per_frame": r["pairs_per_frame"]},
+                "config": {"workload": workload_label(args.workload, n_dyn, n_sta), "pairs_per_frame": r["pairs_per_frame"]},
                 "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "host_cores")},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
         print(json.dumps(line), file=JSON_OUT, flush=True)
         return 0
 
-    weak = world > 1 and args.scaling in ("auto", "weak")
+    weak = world > 1 and args.scaling == "weak"
     scene, n_dyn, n_sta = build_scene(args.workload, world if weak else 1)
-    out = run_b200(args, scene, n_dyn, n_sta, rank, world, local)
+    out = run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = run_reference(args, scene, n_dyn, as_baseline=True)

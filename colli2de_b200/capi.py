@@ -21,7 +21,7 @@ EXPORTS = [
     "c2d_gpu_read_candidates", "c2d_gpu_shape_slots", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
     "c2d_gpu_compute_aabb_batch",
     "c2d_gpu_set_slab_mode", "c2d_gpu_comm_unique_id", "c2d_gpu_comm_init", "c2d_gpu_comm_destroy",
-    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats",
+    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats", "c2d_gpu_read_transforms",
 ]
 
 _lib = None

@@ -1557,6 +1557,28 @@ int c2d_gpu_read_shapes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, uint8_
     return 0;
 }
 
+int c2d_gpu_read_transforms(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* out_xf4, float* out_xa4, float* out_pxf4,
+                            float* out_pxa4)
+{
+    cudaSetDevice(ctx->device);
+    if (int rc = flush(ctx))
+        return rc;
+    if (static_cast<uint64_t>(first) + count > ctx->capacity)
+        return fail(ctx, "c2d_gpu_read_transforms: range out of bounds");
+    cudaStream_t s = ctx->stream;
+    const size_t bytes = static_cast<size_t>(count) * sizeof(float4);
+    const struct
+    {
+        float* dst;
+        const float4* src;
+    } parts[] = {{out_xf4, ctx->d.xf}, {out_xa4, ctx->d.xa}, {out_pxf4, ctx->d.pxf}, {out_pxa4, ctx->d.pxa}};
+    for (const auto& p : parts)
+        if (p.dst && count)
+            C2D_CUDA(ctx, cudaMemcpyAsync(p.dst, p.src + first, bytes, cudaMemcpyDeviceToHost, s));
+    C2D_CUDA(ctx, cudaStreamSynchronize(s));
+    return 0;
+}
+
 int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const float* tight4, const float* fat4)
 {
     ++ctx->mutationEpoch;

@@ -294,6 +294,12 @@ int c2d_gpu_read_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* 
  * bit 2 ghost), category / mask bits and the 32-float geometry block; any output may be NULL.  Flushes first. */
 int c2d_gpu_read_shapes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, uint8_t* out_type, uint8_t* out_vertex_count,
                         uint8_t* out_flags, uint64_t* out_category, uint64_t* out_mask, float* out_geom32);
+/* Per-shape entity transforms as the device holds them: xf4 = (tx, ty, sin, cos), xa4 = (angle, sin(angle), cos(angle), 0)
+ * and the same for the previous transform of bullets (Registry.hpp:191-260 mBulletPreviousTransforms).  Used by a
+ * Registry of a multi-GPU group to bring its host mirror up to date after other ranks' translations arrived through
+ * the move exchange.  Any output may be NULL.  Flushes first. */
+int c2d_gpu_read_transforms(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, float* out_xf4, float* out_xa4, float* out_pxf4,
+                            float* out_pxa4);
 /* Restores the tight (ShapeInstance::mBoundingBox) and leaf (BVHNode::mBoundingBox) boxes of a shape range, e.g. after
  * Registry::deserialize (Registry.hpp:1266-1344) re-added the shapes of a snapshot: both boxes are HISTORY (the tight
  * box is shifted by translations, the leaf box follows the fat-leaf rule), so they cannot be recomputed.  Either

@@ -33,6 +33,7 @@
 #include <c2d_gpu.h>
 
 #include <algorithm>
+#include <array>
 #include <bit>
 #include <cmath>
 #include <cstddef>
@@ -316,6 +317,59 @@ class Registry
         static_assert(kDirectTag, "setShapeGhost needs a 4-byte trivially copyable EntityId (global entity tags)");
         check(c2d_gpu_shape_set_ghost(mCtx, shapeId, isGhost ? 1 : 0));
     }
+    // ---- multi-GPU group (include/c2d_gpu.h "multi-GPU") --------------------------------
+    // One Registry per GPU (one process per GPU, or several Registries in one process), all holding the SAME scene
+    // (every rank replays every mutation).  getCollidingPairs() is then collective: each rank sorts, builds and
+    // traverses only its Morton-key slab of the Dynamic tree and returns ITS share of the pairs; the union over the
+    // ranks is the reference's pair set, each pair once.  The id comes from createGroupId() on one rank and travels to
+    // the others by any channel (MPI, torch.distributed, a file).
+    using GroupId = std::array<unsigned char, 128>;
+    static GroupId createGroupId()
+    {
+        GroupId id{};
+        if (c2d_gpu_comm_unique_id(id.data()) != 0)
+            throw std::runtime_error(std::string("colli2de-b200: ") + c2d_gpu_last_error(nullptr));
+        return id;
+    }
+    void joinGroup(uint32_t rank, uint32_t world, const GroupId& id)
+    {
+        check(c2d_gpu_comm_init(mCtx, rank, world, id.data()));
+        mGroupWorld = world;
+    }
+    void leaveGroup()
+    {
+        syncHost();
+        check(c2d_gpu_comm_set_result_mode(mCtx, C2D_RESULTS_LOCAL));
+        check(c2d_gpu_comm_destroy(mCtx));
+        check(c2d_gpu_set_shard(mCtx, 0, 1));
+        mGroupWorld = 1;
+        mGroupMoveExchange = false;
+    }
+    // Which records getCollidingPairs() returns on this rank: its own share (default), everybody's on every rank, or
+    // everybody's on rank 0 (the other ranks keep their share).  Gathered over NCCL device to device.
+    enum class GroupResults
+    {
+        Local = C2D_RESULTS_LOCAL,
+        All = C2D_RESULTS_ALL,
+        Root = C2D_RESULTS_ROOT
+    };
+    void setGroupResults(GroupResults mode) { check(c2d_gpu_comm_set_result_mode(mCtx, static_cast<int>(mode))); }
+    // Move exchange: moveEntity(id, Translation) is called for an entity on ONE rank only (the rank that simulates it),
+    // at most once per frame; the next getCollidingPairs() all-gathers the 12-byte records over NVLink and applies them
+    // on every rank.  All other mutators stay replicated.  The host mirror of the entities other ranks moved is brought
+    // up to date lazily (one download of the device transforms) by the next call that reads a transform.
+    void setGroupMoveExchange(bool on)
+    {
+        syncHost();
+        check(c2d_gpu_comm_set_move_exchange(mCtx, on ? 1 : 0));
+        mGroupMoveExchange = on;
+    }
+    c2d_gpu_comm_stats lastGroupStats() const
+    {
+        c2d_gpu_comm_stats st{};
+        check(c2d_gpu_comm_get_stats(mCtx, &st));
+        return st;
+    }
     // Counters and CUDA-event timings of the last getCollidingPairs() / rayCast().
     const c2d_gpu_stats& lastQueryStats() const { return mStats; }
     // Runs the pipeline but leaves the records on the device; returns the number of colliding pairs.
@@ -511,9 +565,34 @@ class Registry
             }
         }
         mPendingApplies.clear();
+        if (mRemoteMovesPending)
+            pullTransforms();
+    }
+    // move exchange: other ranks' translations reached the device, not this host mirror - read the transforms back
+    // (the first shape of an entity carries the entity's transform; an entity without shapes is never exchanged)
+    void pullTransforms() const
+    {
+        mRemoteMovesPending = false;
+        const uint32_t n = static_cast<uint32_t>(mShapes.size());
+        if (n == 0)
+            return;
+        std::vector<float> xf(4 * static_cast<size_t>(n)), pxf(xf.size());
+        check(c2d_gpu_read_transforms(mCtx, 0, n, xf.data(), nullptr, pxf.data(), nullptr));
+        for (EntityInfo& e : mEntities)
+        {
+            if (!e.alive || e.firstShape == kNone || e.type == BodyType::Static)
+                continue;
+            const size_t s = 4 * static_cast<size_t>(e.firstShape);
+            e.transform.translation = Vec2{xf[s], xf[s + 1]}; // translations only: the rotation never travels
+            if (e.type == BodyType::Bullet)
+                e.previous.translation = Vec2{pxf[s], pxf[s + 1]};
+        }
     }
 
     c2d_gpu_ctx* mCtx = nullptr;
+    uint32_t mGroupWorld = 1;
+    bool mGroupMoveExchange = false;
+    mutable bool mRemoteMovesPending = false;
     detail::IndexMap<EntityId, KeyOf> mIndex;
     mutable std::vector<EntityInfo> mEntities;
     std::vector<StagedMoves> mStaged;
@@ -826,6 +905,7 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
         // reference does (Registry.hpp:467, 547), let the library touch its pages while the GPU works, then have
         // the records copied straight into it
         check(c2d_gpu_collide_begin(mCtx));
+        mRemoteMovesPending |= mGroupMoveExchange;
         std::vector<EntityCollision> out;
         out.reserve(static_cast<std::size_t>(mPreviousAllCollisionsCount) + mPreviousAllCollisionsCount / 8 + 64);
         check(c2d_gpu_prefault(mCtx, static_cast<void*>(out.data()), out.capacity() * sizeof(EntityCollision)));
@@ -841,6 +921,7 @@ std::vector<typename Registry<EntityId, Method>::EntityCollision> Registry<Entit
         const c2d_pair_record* records = nullptr;
         uint64_t count = 0;
         check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
+    mRemoteMovesPending |= mGroupMoveExchange;
         mPreviousAllCollisionsCount = static_cast<uint32_t>(count);
         return toCollisions(records, count);
     }
@@ -852,6 +933,7 @@ std::span<const typename Registry<EntityId, Method>::EntityCollision> Registry<E
     const c2d_pair_record* records = nullptr;
     uint64_t count = 0;
     check(c2d_gpu_collide(mCtx, &records, &count, &mStats));
+    mRemoteMovesPending |= mGroupMoveExchange;
     mPreviousAllCollisionsCount = static_cast<uint32_t>(count);
     if constexpr (kDirectTag && sizeof(EntityCollision) == sizeof(c2d_pair_record) &&
                   std::is_trivially_copyable_v<EntityCollision>)
@@ -976,6 +1058,7 @@ uint64_t Registry<EntityId, Method>::countCollidingPairsOnDevice()
 {
     uint64_t count = 0;
     check(c2d_gpu_collide_device(mCtx, &count, &mStats));
+    mRemoteMovesPending |= mGroupMoveExchange;
     return count;
 }
 

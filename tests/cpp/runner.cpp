@@ -161,6 +161,10 @@ struct IRegistry
     virtual uint64_t pairsView(double* seconds, const void** records) = 0;
     virtual void* native() const = 0;
     virtual void setGhost(ShapeId s, bool g) = 0;
+    virtual void groupId(unsigned char* out128) = 0;
+    virtual void groupJoin(uint32_t rank, uint32_t world, const unsigned char* id128) = 0;
+    virtual void groupOptions(int results, int exchange) = 0;
+    virtual void groupLeave() = 0;
     virtual void stats(double* out16) const = 0;
     virtual int stage(uint32_t n, const uint32_t* ids, const float* dxy) = 0;
     virtual void applyStaged(int handle) = 0;
@@ -300,6 +304,26 @@ struct RegistryHolder final : IRegistry
     void setGhost(ShapeId s, bool g) override
     {
         reg.setShapeGhost(s, g);
+    }
+    void groupId(unsigned char* out128) override
+    {
+        const auto id = Reg::createGroupId();
+        std::memcpy(out128, id.data(), id.size());
+    }
+    void groupJoin(uint32_t rank, uint32_t world, const unsigned char* id128) override
+    {
+        typename Reg::GroupId id;
+        std::memcpy(id.data(), id128, id.size());
+        reg.joinGroup(rank, world, id);
+    }
+    void groupOptions(int results, int exchange) override
+    {
+        reg.setGroupResults(static_cast<typename Reg::GroupResults>(results));
+        reg.setGroupMoveExchange(exchange != 0);
+    }
+    void groupLeave() override
+    {
+        reg.leaveGroup();
     }
     uint64_t pairsView(double* seconds, const void** records) override
     {
@@ -465,6 +489,22 @@ struct RegistryHolder final : IRegistry
     void setGhost(ShapeId, bool) override
     {
         throw std::runtime_error("ghost shapes are an extension of the B200 build");
+    }
+    void groupId(unsigned char*) override
+    {
+        throw std::runtime_error("multi-GPU groups are an extension of the B200 build");
+    }
+    void groupJoin(uint32_t, uint32_t, const unsigned char*) override
+    {
+        throw std::runtime_error("multi-GPU groups are an extension of the B200 build");
+    }
+    void groupOptions(int, int) override
+    {
+        throw std::runtime_error("multi-GPU groups are an extension of the B200 build");
+    }
+    void groupLeave() override
+    {
+        throw std::runtime_error("multi-GPU groups are an extension of the B200 build");
     }
     uint64_t pairsView(double* seconds, const void** records) override
     {
@@ -911,6 +951,34 @@ void rn_set_ghost(rn_ctx* ctx, uint32_t n, const uint32_t* shape_ids, const uint
     RN_TRY(ctx)
     for (uint32_t i = 0; i < n; ++i)
         ctx->reg->setGhost(shape_ids[i], ghost[i] != 0);
+    RN_CATCH(ctx)
+}
+
+void rn_group_id(rn_ctx* ctx, void* out128)
+{
+    RN_TRY(ctx)
+    ctx->reg->groupId(static_cast<unsigned char*>(out128));
+    RN_CATCH(ctx)
+}
+
+void rn_group_join(rn_ctx* ctx, uint32_t rank, uint32_t world, const void* id128)
+{
+    RN_TRY(ctx)
+    ctx->reg->groupJoin(rank, world, static_cast<const unsigned char*>(id128));
+    RN_CATCH(ctx)
+}
+
+void rn_group_options(rn_ctx* ctx, int results, int exchange)
+{
+    RN_TRY(ctx)
+    ctx->reg->groupOptions(results, exchange);
+    RN_CATCH(ctx)
+}
+
+void rn_group_leave(rn_ctx* ctx)
+{
+    RN_TRY(ctx)
+    ctx->reg->groupLeave();
     RN_CATCH(ctx)
 }
 

@@ -97,6 +97,13 @@ void rn_seed_entities(rn_ctx*, uint32_t n, const uint32_t* ids, const uint8_t* b
 int rn_equals(rn_ctx* a, rn_ctx* b);
 void rn_set_ghost(rn_ctx*, uint32_t n, const uint32_t* shape_ids, const uint8_t* ghost);
 
+/* Multi-GPU group of Registries (extension, B200 only; not in the C oracle): Registry::createGroupId / joinGroup /
+ * setGroupResults (0 local, 1 all, 2 root) + setGroupMoveExchange / leaveGroup. */
+void rn_group_id(rn_ctx*, void* out128);
+void rn_group_join(rn_ctx*, uint32_t rank, uint32_t world, const void* id128);
+void rn_group_options(rn_ctx*, int results, int exchange);
+void rn_group_leave(rn_ctx*);
+
 /* Secondary oracles.  Reference: read from the Registry's private members
  * (mShapes[i].mBoundingBox; the leaf box mTrees[body].getNode(mShapeTreeHandles[i]).mBoundingBox; the five
  * mTrees[..].findAllCollisions groups of Registry.hpp:487-545) - PartitioningMethod::None only.  B200: c2d_gpu_read_boxes /

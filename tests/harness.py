@@ -133,6 +133,10 @@ def load(name: str) -> C.CDLL:
         "rn_copy_candidates": (None, [vp, pu32]),
         "rn_set_ghost": (None, [vp, u32, pu32, pu8]),
         "rn_get_colliding_pairs_view": (u64, [vp, pd, C.POINTER(vp)]),
+        "rn_group_id": (None, [vp, vp]),
+        "rn_group_join": (None, [vp, u32, u32, vp]),
+        "rn_group_options": (None, [vp, i32, i32]),
+        "rn_group_leave": (None, [vp]),
         "rn_get_collisions": (u64, [vp, u32]),
         "rn_get_collisions_many": (u64, [vp, u32, pu32, pd]),
         "rn_serialize": (u64, [vp]),
@@ -154,7 +158,8 @@ def load(name: str) -> C.CDLL:
         "rn_compute_aabb": (None, [u32, pu8, pf, pu8, pf, pf]),
         "rn_polygon_normals": (None, [u32, pf, pu8, pf]),
     }
-    optional = {"rn_serialize", "rn_copy_blob", "rn_deserialize", "rn_seed_entities", "rn_equals"}  # not in the C oracle
+    optional = {"rn_serialize", "rn_copy_blob", "rn_deserialize", "rn_seed_entities", "rn_equals", "rn_group_id",
+                "rn_group_join", "rn_group_options", "rn_group_leave"}  # not in the C oracle
     for fn, (res, args) in sig.items():
         if fn in optional and not hasattr(lib, fn):
             continue
@@ -277,6 +282,34 @@ class Backend:
     def set_ghost(self, shape_ids, ghost):
         s, g = _u32(shape_ids), _u8(ghost)
         self.lib.rn_set_ghost(self.ctx, len(s), _p(s, C.c_uint32), _p(g, C.c_uint8))
+        self._check()
+
+    # multi-GPU group of Registries (B200 only): Registry::createGroupId / joinGroup / setGroupResults + setGroupMoveExchange
+    def group_id(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.lib.rn_group_id(self.ctx, buf)
+        self._check()
+        return buf.raw
+
+    def group_join(self, rank: int, world: int, ident: bytes):
+        self.lib.rn_group_join(self.ctx, rank, world, C.c_char_p(ident))
+        self._check()
+
+    def group_join_torch(self):
+        """Joins a group spanning the torch.distributed world (the id travels by broadcast_object_list)."""
+        import torch.distributed as dist
+
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = [self.group_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        self.group_join(rank, world, ident[0])
+
+    def group_options(self, results: int = 0, exchange: bool = False):
+        self.lib.rn_group_options(self.ctx, results, 1 if exchange else 0)
+        self._check()
+
+    def group_leave(self):
+        self.lib.rn_group_leave(self.ctx)
         self._check()
 
     def move_translate(self, ids, dxy):

@@ -1,0 +1,114 @@
+"""Multi-GPU group on REAL ranks (one process per GPU over NCCL): run under torchrun, e.g.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/multigpu_check.py
+
+Every rank holds a c2d::Registry of the same scene joined to one group (Registry::joinGroup).  Frame by frame the ranks
+move the entities they drive (move exchange: ncclAllGather of the 12-byte records), call the collective
+getCollidingPairs() in each result mode, and rank 0 compares the union with the UNMODIFIED reference (oracle/_ref):
+exact tuple set, manifolds, ambiguous segment pairs classified (tests/parity.py).  Structural changes in the middle are
+replicated on every rank.  Also checked: the host mirror of entities moved by OTHER ranks (getEntityTransform after an
+exchange) is bit-identical to the reference's transforms.  Prints MULTIGPU_OK on rank 0.
+
+TEST INFRASTRUCTURE (tests/test_gpu_multigpu.py launches it when the box has >= 2 GPUs)."""
+import os
+import sys
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from colli2de_b200 import capi, scenes  # noqa: E402
+from tests import harness as H, parity as P  # noqa: E402
+
+
+def gather_numpy(arr: np.ndarray):
+    """all ranks' structured arrays concatenated on every rank (python-side union for the LOCAL result mode)"""
+    parts = [None] * dist.get_world_size()
+    dist.all_gather_object(parts, arr.tobytes())
+    return np.concatenate([np.frombuffer(p, dtype=arr.dtype) for p in parts])
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_dyn, n_sta = int(os.environ.get("C2D_CHECK_DYN", "120000")), int(os.environ.get("C2D_CHECK_STA", "12000"))
+    sc = scenes.mixed_scene(n_dyn, n_sta, 1700.0 * (n_dyn / 120000.0) ** 0.5, seed=23, clustered=True)
+    sc["ent_body"][:n_dyn:41] = 2  # bullets among the dynamic entities
+    which = "reference" if H.available("reference") else "oracle"
+    b = H.Backend("b200")
+    scenes.populate(b, sc)
+    b.group_join_torch()
+    ctx = b.native_context()
+    capi.set_slab_mode(ctx, 1000)
+    ref, idx = None, None
+    if rank == 0:
+        ref = H.Backend(which)
+        scenes.populate(ref, sc)
+        idx = P.SceneIndex(sc)
+    movable = np.nonzero(sc["ent_body"] != 0)[0].astype(np.uint32)
+    alive = np.ones(len(movable), bool)
+    rng = scenes.LCG(99)
+    modes = [(capi.RESULTS_ROOT, True), (capi.RESULTS_ALL, True), (capi.RESULTS_LOCAL, True), (capi.RESULTS_ALL, False),
+             (capi.RESULTS_ROOT, True), (capi.RESULTS_LOCAL, False)]
+    totals = dict(expected=0, ambiguous=0, not_bit_identical=0)
+    for f, (mode, exchange) in enumerate(modes):
+        d = scenes.jitter(rng, len(movable), 0.6)
+        if f == 3:
+            # structural change, replicated on every rank: entities leave, shapes are switched off
+            gone = movable[200:260]
+            off = np.arange(5000, 5040, dtype=np.uint32)
+            for x in [b] + ([ref] if ref else []):
+                x.remove_entities(gone)
+                x.set_active(off, np.zeros(len(off), np.uint8))
+            alive[200:260] = False
+        ids, dd = movable[alive], d[alive]
+        b.group_options(results=mode, exchange=exchange)
+        if exchange:  # this rank drives one block of the entities
+            lo, hi = (len(ids) * rank) // world, (len(ids) * (rank + 1)) // world
+            b.move_translate(ids[lo:hi], dd[lo:hi])
+        else:
+            b.move_translate(ids, dd)
+        got = b.get_colliding_pairs()
+        st = capi.comm_stats(ctx)
+        if mode == capi.RESULTS_LOCAL:
+            got = gather_numpy(got)
+        elif mode == capi.RESULTS_ROOT and rank != 0:
+            assert len(got) == st["local_pairs"]
+        counts = [None] * world
+        dist.all_gather_object(counts, int(st["local_pairs"]))
+        assert min(counts) > 0, counts
+        if exchange:
+            assert st["exchange_bytes"] == 12 * (len(ids) - (hi - lo)), (st, len(ids), hi - lo)
+        assert st["slab_owned"] > 0 and st["slab_leaves"] >= st["slab_owned"]
+        if rank == 0:
+            ref.move_translate(ids, dd)
+            res = P.compare_pairs(which, ref, idx, ref.get_colliding_pairs(), got, max_ambiguous=20)
+            assert res["expected"] > 20000 and res["not_bit_identical"] == 0, res
+            assert sum(counts) == res["got"]
+            for k in totals:
+                totals[k] += res[k]
+        if exchange and f in (1, 4):
+            # host mirror of entities other ranks moved: read back lazily from the device, equal to the reference's
+            probe = ids[:: max(1, len(ids) // 500)]
+            mine = b.get_transforms(probe)
+            want = [mine.tobytes() if rank != 0 else ref.get_transforms(probe).tobytes()]
+            dist.broadcast_object_list(want, src=0)
+            assert mine.tobytes() == want[0], "host transforms differ from the reference after a move exchange"
+    b.group_leave()
+    # out of the group the registry is a plain single-GPU registry again
+    single = b.get_colliding_pairs()
+    if rank == 0:
+        res = P.compare_pairs(which, ref, idx, ref.get_colliding_pairs(), single, max_ambiguous=20)
+        print("MULTIGPU_OK", world, totals, flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
