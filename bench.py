@@ -324,6 +324,8 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
             tm = time.perf_counter()
             b.move_translate(dyn[chunk], d[chunk])
             tm = time.perf_counter() - tm
+            if world > 1:
+                barrier()  # the collective call starts together on every rank: the ranks' host move loops differ by milliseconds
             sec = C.c_double(0.0)
             n = int(b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec)))
             b._check()

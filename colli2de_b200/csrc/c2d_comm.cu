@@ -268,7 +268,8 @@ int c2d_gpu_comm_get_stats(c2d_gpu_ctx* ctx, c2d_gpu_comm_stats* out)
     out->gather_bytes = cm.gatherBytes;
     out->local_pairs = ctx->lastPairs;
     out->slab_owned = ctx->slabInUse ? ctx->slab.owned : 0;
-    out->slab_leaves = ctx->slabInUse ? ctx->slab.selected : 0;
+    // owned leaves + the halo shapes that queried them (the halo count arrives with the frame's asynchronous copies)
+    out->slab_leaves = ctx->slabInUse ? ctx->slab.owned + (ctx->slab.hCounters ? ctx->slab.hCounters[0] : 0) : 0;
     cudaSetDevice(ctx->device);
     if (cm.exchangeTimed)
         cudaEventElapsedTime(&out->ms_exchange, cm.evX[0], cm.evX[1]);

@@ -179,20 +179,26 @@ struct CommState
     bool exchangeTimed = false, gatherTimed = false;
 };
 
-// Morton-slab build of the Dynamic tree (build_slab_tree in c2d_gpu.cu, kernels in c2d_slab.cuh): this rank's tree holds
-// the shapes whose Morton key falls into its key range ("owned") plus the shapes of higher ranks that may overlap them
-// ("halo").
+// Morton slab of the Dynamic tree (update_slab in c2d_gpu.cu, kernels in c2d_slab.cuh): this rank's tree holds the leaves
+// whose position in the (replicated) Morton order falls into its range; the shapes of higher ranks that may overlap
+// them ("halo") are selected every frame and query that tree.
 struct SlabState
 {
-    DevBuf<uint32_t> allKeys, allVals; // Morton keys / shape ids of ALL members (replicated pass)
-    DevBuf<uint32_t> hist;             // 4096 coarse bins + 32 x 4096 refinement bins
-    DevBuf<uint32_t> split;            // splitter keys + scratch of the two split kernels (kSplitWords)
-    DevBuf<uint8_t> cellMask;          // 256 x 256 cells touched by the owned shapes' leaf boxes
-    DevBuf<uint32_t> counters;         // [0] selected, [1] owned
-    uint32_t* hCounters = nullptr;     // pinned
+    DevBuf<uint32_t> allKeys, allVals, keysTmp, valsTmp; // Morton order of ALL Dynamic members as of the last rebalance
+    DevBuf<unsigned char> sortWs;
+    DevBuf<uint32_t> bounds;           // centre bounds of that rebalance (the cell frame of mark / select)
+    DevBuf<uint32_t> cellBits;         // 256 x 256 cells touched by the owned shapes' leaf boxes, one bit each
+    DevBuf<uint32_t> halo;             // halo shape ids of this frame
+    DevBuf<uint32_t> counters;         // [0] halo count, [1] "an owned box spans too many cells"
+    uint32_t* hCounters = nullptr;     // pinned: the counters of the last frame (statistics only, copied asynchronously)
     cudaEvent_t ev[2] = {};
     bool timed = false;
-    uint32_t owned = 0, selected = 0;
+    bool valid = false;                // allKeys / allVals / the slab tree topology describe the current membership
+    bool membershipChanged = true;     // a Dynamic shape was added or removed since the last rebalance
+    uint32_t age = 0;                  // frames since the last rebalance
+    uint32_t n = 0;                    // Dynamic members at the last rebalance
+    uint32_t lo = 0, hi = 0;           // this rank's positions in the order
+    uint32_t owned = 0, laterCount = 0;
 };
 
 struct TreeBuf
@@ -257,7 +263,7 @@ struct c2d_gpu_ctx
     uint32_t shardRank = 0, shardWorld = 1;
     // Morton-slab build of the Dynamic tree when world > 1 and the tree has at least this many leaves (0 = never)
     uint32_t slabMinShapes = 65536;
-    TreeBuf slabTree;       // the rank-local tree (owned + halo leaves) of the Dynamic body
+    TreeBuf slabTree;       // the rank-local tree (owned leaves) of the Dynamic body
     bool slabDirty = true;  // the Dynamic shapes changed since slabTree was built
     bool slabInUse = false; // this frame's Dynamic traversals run on slabTree
     c2d_host::SlabState slab;

@@ -193,6 +193,8 @@ void member_add(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
     ctx->memberPos[shape] = static_cast<uint32_t>(ctx->members[body].size());
     ctx->members[body].push_back(shape);
     ctx->membersDirty[body] = true;
+    if (body == C2D_DYNAMIC)
+        ctx->slab.membershipChanged = true;
     mark_dirty(ctx, body);
 }
 
@@ -205,6 +207,8 @@ void member_remove(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
     ctx->memberPos[last] = pos;
     list.pop_back();
     ctx->membersDirty[body] = true;
+    if (body == C2D_DYNAMIC)
+        ctx->slab.membershipChanged = true;
     mark_dirty(ctx, body);
 }
 
@@ -468,85 +472,126 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     return 0;
 }
 
-// The Dynamic tree of this rank's Morton slab (multi-GPU, c2d_slab.cuh): keys of all Dynamic shapes and their histogram
-// (replicated, identical on every rank), balanced splitters, the cells the owned leaf boxes touch, then the selection of
-// owned + halo leaves; only those are sorted, linked and fitted.  Owned leaves sort first (halo keys belong to higher
-// slabs), so the query range of the traversals is [0, owned).
-int build_slab_tree(c2d_gpu_ctx* ctx)
+// The Dynamic tree of this rank's Morton slab (multi-GPU, c2d_slab.cuh).  Rebalance (membership changed, or every
+// rebuildPeriod-th frame): keys of ALL Dynamic shapes, one sort (replicated, identical on every rank), the rank's range of
+// the order becomes its tree.  Every frame: refit of that tree, the cells its leaf boxes touch, the halo selection.
+// Nothing here waits for the device.
+int update_slab(c2d_gpu_ctx* ctx)
 {
     SlabState& sl = ctx->slab;
     TreeBuf& t = ctx->slabTree;
     cudaStream_t s = ctx->stream;
     const uint32_t n = static_cast<uint32_t>(ctx->members[C2D_DYNAMIC].size());
     const uint32_t world = ctx->shardWorld, rank = ctx->shardRank;
-    if (int rc = upload_members(ctx, C2D_DYNAMIC))
-        return rc;
-    const uint32_t* members = ctx->tree[C2D_DYNAMIC].members.ptr;
     if (!sl.hCounters)
     {
-        C2D_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&sl.hCounters), 2 * sizeof(uint32_t), cudaHostAllocDefault));
+        C2D_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&sl.hCounters), kSlabCounterWords * sizeof(uint32_t), cudaHostAllocDefault));
+        std::memset(sl.hCounters, 0, kSlabCounterWords * sizeof(uint32_t));
         C2D_CUDA(ctx, cudaEventCreate(&sl.ev[0]));
         C2D_CUDA(ctx, cudaEventCreate(&sl.ev[1]));
+        C2D_CUDA(ctx, sl.bounds.reserve(4));
+        C2D_CUDA(ctx, sl.cellBits.reserve(kSlabMaskWords));
+        C2D_CUDA(ctx, sl.counters.reserve(kSlabCounterWords));
     }
-    C2D_CUDA(ctx, sl.allKeys.reserve(n));
-    C2D_CUDA(ctx, sl.allVals.reserve(n));
-    C2D_CUDA(ctx, sl.hist.reserve(static_cast<size_t>(kSlabCoarseBins) * (1 + kSlabMaxWorld)));
-    C2D_CUDA(ctx, sl.split.reserve(kSplitWords));
-    C2D_CUDA(ctx, sl.cellMask.reserve(kSlabCells * kSlabCells));
-    C2D_CUDA(ctx, sl.counters.reserve(2));
-    C2D_CUDA(ctx, t.keys.reserve(n));
-    C2D_CUDA(ctx, t.vals.reserve(n));
-
     C2D_CUDA(ctx, cudaEventRecord(sl.ev[0], s));
-    uint32_t* bounds = &ctx->dScratch->bounds[C2D_DYNAMIC][0];
-    const uint32_t grid = std::min<uint32_t>(blocks_for(n, 256), 148 * 8);
-    C2D_CUDA(ctx, cudaMemsetAsync(sl.hist.ptr, 0, static_cast<size_t>(kSlabCoarseBins) * (1 + world) * sizeof(uint32_t), s));
-    C2D_CUDA(ctx, cudaMemsetAsync(sl.split.ptr, 0, kSplitWords * sizeof(uint32_t), s));
-    C2D_CUDA(ctx, cudaMemsetAsync(sl.cellMask.ptr, 0, kSlabCells * kSlabCells, s));
-    C2D_CUDA(ctx, cudaMemsetAsync(sl.counters.ptr, 0, 2 * sizeof(uint32_t), s));
-    C2D_TIMED(ctx, "k_bounds", k_bounds<<<grid, 256, 0, s>>>(members, n, ctx->d.fat, bounds));
-    C2D_TIMED(ctx, "k_slab_keys", k_morton_hist<<<grid, 256, 0, s>>>(members, n, ctx->d.fat, bounds, sl.allKeys.ptr, sl.allVals.ptr, sl.hist.ptr));
-    C2D_TIMED(ctx, "k_slab_split", k_slab_split1<<<1, 1024, 0, s>>>(sl.hist.ptr, n, world, sl.split.ptr));
-    C2D_TIMED(ctx, "k_slab_hist2", k_slab_hist2<<<grid, 256, 0, s>>>(sl.allKeys.ptr, n, world, sl.split.ptr, sl.hist.ptr));
-    C2D_TIMED(ctx, "k_slab_split", k_slab_split2<<<world - 1, 1024, 0, s>>>(sl.hist.ptr, world, sl.split.ptr));
-    C2D_TIMED(ctx, "k_slab_mark", k_slab_mark<<<grid, 256, 0, s>>>(sl.allKeys.ptr, sl.allVals.ptr, n, ctx->d.fat, bounds, sl.split.ptr, rank, world, sl.cellMask.ptr));
-    C2D_TIMED(ctx, "k_slab_select", k_slab_select<<<grid, 256, 0, s>>>(sl.allKeys.ptr, sl.allVals.ptr, n, ctx->d.fat, bounds, sl.split.ptr, rank, world,
-                                                                      sl.cellMask.ptr, t.keys.ptr, t.vals.ptr, sl.counters.ptr));
-    ctx->launches += 7;
-    C2D_CUDA(ctx, cudaEventRecord(sl.ev[1], s));
-    sl.timed = true;
-    C2D_CUDA(ctx, cudaMemcpyAsync(sl.hCounters, sl.counters.ptr, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-    C2D_CUDA(ctx, cudaStreamSynchronize(s)); // the sort and the grids below are sized by the selection
-    C2D_CUDA(ctx, cudaGetLastError());
-    const uint32_t m = sl.hCounters[0];
-    sl.selected = m;
-    sl.owned = sl.hCounters[1];
-    t.n = m;
-    ctx->slabDirty = false;
-    if (m == 0)
-        return 0;
-    C2D_CUDA(ctx, t.keysTmp.reserve(n));
-    C2D_CUDA(ctx, t.valsTmp.reserve(n));
-    C2D_CUDA(ctx, t.nodes.reserve(n));
-    C2D_CUDA(ctx, t.nodeParent.reserve(n));
-    C2D_CUDA(ctx, t.leafParent.reserve(n));
-    C2D_CUDA(ctx, t.arrival.reserve(n));
-    C2D_CUDA(ctx, t.sortWs.reserve(sort_workspace_bytes(n, 4)));
+    const bool rebalance = !sl.valid || sl.membershipChanged || sl.n != n || sl.age + 1 >= ctx->rebuildPeriod;
+    if (rebalance)
     {
-        ProfScope ps(ctx, "radix_sort(1 memset + 5 kernels)");
-        ctx->launches += radix_sort_pairs(s, t.keys.ptr, t.vals.ptr, t.keysTmp.ptr, t.valsTmp.ptr, m, 4, t.sortWs.ptr);
+        if (int rc = upload_members(ctx, C2D_DYNAMIC))
+            return rc;
+        const uint32_t* members = ctx->tree[C2D_DYNAMIC].members.ptr;
+        C2D_CUDA(ctx, sl.allKeys.reserve(n));
+        C2D_CUDA(ctx, sl.allVals.reserve(n));
+        C2D_CUDA(ctx, sl.keysTmp.reserve(n));
+        C2D_CUDA(ctx, sl.valsTmp.reserve(n));
+        C2D_CUDA(ctx, sl.halo.reserve(n));
+        C2D_CUDA(ctx, sl.sortWs.reserve(sort_workspace_bytes(n, 4)));
+        const uint32_t grid = std::min<uint32_t>(blocks_for(n, 256), 148 * 8);
+        k_slab_reset_bounds<<<1, 32, 0, s>>>(sl.bounds.ptr);
+        C2D_TIMED(ctx, "k_bounds", k_bounds<<<grid, 256, 0, s>>>(members, n, ctx->d.fat, sl.bounds.ptr));
+        C2D_TIMED(ctx, "k_morton", k_morton<<<blocks_for(n, 256), 256, 0, s>>>(members, n, ctx->d.fat, sl.bounds.ptr, sl.allKeys.ptr, sl.allVals.ptr));
+        ctx->launches += 3;
+        {
+            ProfScope ps(ctx, "radix_sort(1 memset + 5 kernels)");
+            ctx->launches += radix_sort_pairs(s, sl.allKeys.ptr, sl.allVals.ptr, sl.keysTmp.ptr, sl.valsTmp.ptr, n, 4, sl.sortWs.ptr);
+        }
+        sl.lo = static_cast<uint32_t>(static_cast<uint64_t>(n) * rank / world);
+        sl.hi = static_cast<uint32_t>(static_cast<uint64_t>(n) * (rank + 1) / world);
+        sl.owned = sl.hi - sl.lo;
+        sl.laterCount = n - sl.hi;
+        sl.n = n;
+        sl.age = 0;
+        sl.valid = true;
+        sl.membershipChanged = false;
+        const uint32_t m = sl.owned;
+        t.n = m;
+        if (m)
+        {
+            C2D_CUDA(ctx, t.keys.reserve(m));
+            C2D_CUDA(ctx, t.vals.reserve(m));
+            C2D_CUDA(ctx, t.nodes.reserve(m));
+            C2D_CUDA(ctx, t.nodeParent.reserve(m));
+            C2D_CUDA(ctx, t.leafParent.reserve(m));
+            C2D_CUDA(ctx, t.arrival.reserve(m));
+            C2D_CUDA(ctx, cudaMemcpyAsync(t.keys.ptr, sl.allKeys.ptr + sl.lo, m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+            C2D_CUDA(ctx, cudaMemcpyAsync(t.vals.ptr, sl.allVals.ptr + sl.lo, m * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+        }
+        if (m > 1)
+        {
+            C2D_TIMED(ctx, "k_karras_build", k_karras_build<<<blocks_for(m - 1, 256), 256, 0, s>>>(t.keys.ptr, t.vals.ptr, static_cast<int>(m), t.nodes.ptr,
+                                                                 t.nodeParent.ptr, t.leafParent.ptr));
+            ++ctx->launches;
+        }
     }
+    else
+        ++sl.age;
+    const uint32_t m = sl.owned;
     if (m > 1)
     {
         C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, m * sizeof(uint32_t), s));
-        C2D_TIMED(ctx, "k_karras_build", k_karras_build<<<blocks_for(m - 1, 256), 256, 0, s>>>(t.keys.ptr, t.vals.ptr, static_cast<int>(m), t.nodes.ptr,
-                                                             t.nodeParent.ptr, t.leafParent.ptr));
         C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(m, 256), 256, 0, s>>>(static_cast<int>(m), t.vals.ptr, ctx->d.fat, ctx->d.category,
                                                  t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
+        ++ctx->launches;
+    }
+    // the halo of this frame: exact for the CURRENT boxes
+    C2D_CUDA(ctx, cudaMemsetAsync(sl.cellBits.ptr, 0, kSlabMaskWords * sizeof(uint32_t), s));
+    C2D_CUDA(ctx, cudaMemsetAsync(sl.counters.ptr, 0, kSlabCounterWords * sizeof(uint32_t), s));
+    if (m && sl.laterCount)
+    {
+        C2D_TIMED(ctx, "k_slab_mark", k_slab_mark<<<std::min<uint32_t>(blocks_for(m, 256), 148 * 2), 256, 0, s>>>(
+                      t.vals.ptr, m, ctx->d.fat, sl.bounds.ptr, sl.cellBits.ptr, sl.counters.ptr));
+        C2D_TIMED(ctx, "k_slab_select", k_slab_select<<<std::min<uint32_t>(blocks_for(sl.laterCount, 256), 148 * 4), 256, 0, s>>>(
+                      sl.allVals.ptr + sl.hi, sl.laterCount, ctx->d.fat, sl.bounds.ptr, sl.cellBits.ptr, sl.halo.ptr, sl.counters.ptr));
         ctx->launches += 2;
     }
+    C2D_CUDA(ctx, cudaEventRecord(sl.ev[1], s));
+    sl.timed = true;
+    // statistics only: read by c2d_gpu_comm_get_stats after the frame
+    C2D_CUDA(ctx, cudaMemcpyAsync(sl.hCounters, sl.counters.ptr, kSlabCounterWords * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ctx->slabDirty = false;
     C2D_CUDA(ctx, cudaGetLastError());
     return 0;
+}
+
+// Halo shapes of the slab query the rank's own Dynamic leaves: the Dynamic x Dynamic pairs that straddle two slabs.  The
+// launch is sized by the number of later shapes; the kernel reads the real count on the device.
+void launch_traverse_halo(c2d_gpu_ctx* ctx)
+{
+    const SlabState& sl = ctx->slab;
+    const TreeBuf& t = ctx->slabTree;
+    if (t.n < 2 || sl.laterCount == 0)
+        return;
+    // most launches have a few thousand halo shapes: a grid for laterCount would be mostly empty blocks, so the grid covers
+    // a quarter of the later shapes per pass (every pass reads the count; passes beyond it exit at once)
+    const uint32_t span = std::max<uint32_t>(4096u, (sl.laterCount + 3) / 4);
+    for (uint32_t lo = 0; lo < sl.laterCount; lo += span)
+    {
+        const uint32_t hi = std::min(sl.laterCount, lo + span);
+        C2D_TIMED(ctx, "k_traverse<halo>", (k_traverse_sync<false, true><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+                      sl.halo.ptr, sl.laterCount, lo, hi, sl.counters.ptr + kSlabHaloCount, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category,
+                      0u, ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, &ctx->dScratch->stackOverflow)));
+        ++ctx->launches;
+    }
 }
 
 } // namespace
@@ -592,7 +637,7 @@ void launch_traverse_trees(c2d_gpu_ctx* ctx, const TreeBuf& q, const TreeBuf& t,
         static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
     else
         C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse_sync<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
-        q.vals.ptr, q.n, lo, hi, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, rejectLeaf, ctx->cand.ptr,
+        q.vals.ptr, q.n, lo, hi, nullptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, rejectLeaf, ctx->cand.ptr,
         static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
     ++ctx->launches;
 }
@@ -654,14 +699,15 @@ int pipeline_attempt(c2d_gpu_ctx* ctx)
         // groups in the reference's order (Registry.hpp:487-545)
         if (ctx->slabInUse)
         {
-            // multi-GPU slab: the owned Dynamic leaves [0, owned) query; every bullet meets the OWNED Dynamic leaves of
-            // each rank exactly once (halo leaves rejected)
+            // multi-GPU slab: the rank's tree holds its owned Dynamic leaves; the halo shapes (higher ranks) query it;
+            // every bullet meets the owned Dynamic leaves of each rank exactly once
             const TreeBuf& slab = ctx->slabTree;
             const TreeBuf& bullets = ctx->tree[C2D_BULLET];
-            launch_traverse_trees<false>(ctx, slab, ctx->tree[C2D_STATIC], 0, ctx->slab.owned, 0u);
-            launch_traverse_trees<true>(ctx, slab, slab, 0, ctx->slab.owned, 0u);
+            launch_traverse_trees<false>(ctx, slab, ctx->tree[C2D_STATIC], 0, slab.n, 0u);
+            launch_traverse_trees<true>(ctx, slab, slab, 0, slab.n, 0u);
+            launch_traverse_halo(ctx);
             launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
-            launch_traverse_trees<false>(ctx, bullets, slab, 0, bullets.n, kLeafGhost);
+            launch_traverse_trees<false>(ctx, bullets, slab, 0, bullets.n, 0u);
             launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
         }
         else
@@ -724,14 +770,15 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
     }
     else if (ctx->broadphase != C2D_BROADPHASE_GRID)
     {
-        ctx->slabInUse = ctx->shardWorld > 1 && ctx->slabMinShapes > 0 && ctx->members[C2D_DYNAMIC].size() >= ctx->slabMinShapes;
+        ctx->slabInUse = ctx->shardWorld > 1 && ctx->slabMinShapes > 0 && ctx->members[C2D_DYNAMIC].size() >= ctx->slabMinShapes &&
+                         ctx->members[C2D_DYNAMIC].size() >= 4ull * ctx->shardWorld;
         for (int body = 0; body < 3; ++body)
         {
             if (body == C2D_DYNAMIC && ctx->slabInUse)
             {
                 // the full Dynamic tree stays stale (rays and per-entity queries rebuild it on demand, ensure_trees)
                 if (ctx->slabDirty)
-                    if (int rc = build_slab_tree(ctx))
+                    if (int rc = update_slab(ctx))
                         return rc;
             }
             else if (ctx->treeDirty[body])
@@ -973,6 +1020,7 @@ int c2d_gpu_clear(c2d_gpu_ctx* ctx)
         mark_dirty(ctx, b);
         ctx->tree[b].n = 0;
     }
+    ctx->slab.valid = false;
     if (ctx->capacity)
         C2D_CUDA(ctx, cudaMemsetAsync(ctx->d.meta, 0, ctx->capacity * sizeof(uint32_t), ctx->stream));
     return 0;
@@ -1037,6 +1085,7 @@ int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world)
     ctx->shardRank = rank;
     ctx->shardWorld = world;
     ctx->slabDirty = true;
+    ctx->slab.valid = false;
     return 0;
 }
 
@@ -1044,6 +1093,7 @@ int c2d_gpu_set_slab_mode(c2d_gpu_ctx* ctx, uint32_t min_shapes)
 {
     ctx->slabMinShapes = min_shapes;
     ctx->slabDirty = true;
+    ctx->slab.valid = false;
     return 0;
 }
 
@@ -1603,6 +1653,7 @@ int c2d_gpu_write_boxes(c2d_gpu_ctx* ctx, uint32_t first, uint32_t count, const 
     {
         mark_dirty(ctx, body); // every leaf box may have changed: rebuild, do not just refit
         ctx->tree[body].membershipChanged = true;
+        ctx->slab.membershipChanged = true;
     }
     return 0;
 }

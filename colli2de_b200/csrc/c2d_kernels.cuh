@@ -543,19 +543,23 @@ __device__ __forceinline__ void stage_flush32(uint2* stage, int& staged, uint2* 
     staged = rest;
 }
 
-template <bool SELF>
+// ORD: emit (min, max) shape ids although the query is not a leaf of the tree (halo shapes of a multi-GPU slab querying the
+// rank's own Dynamic leaves: a same-tree pair of the reference).  qCount (may be null): device-side length of the query
+// list, so a launch sized by an upper bound needs no host round trip.
+template <bool SELF, bool ORD = SELF>
 __global__ void __launch_bounds__(128)
-    k_traverse_sync(const uint32_t* __restrict__ qSorted, uint32_t qn, uint32_t qLo, uint32_t qHi, uint32_t tn,
-                    const BvhNode* __restrict__ nodes, const float4* __restrict__ fat,
-                    const uint64_t* __restrict__ category, uint32_t rejectLeaf, uint2* __restrict__ out,
-                    uint32_t capacity, uint32_t* counter, uint32_t* stackOverflow)
+    k_traverse_sync(const uint32_t* __restrict__ qSorted, uint32_t qn, uint32_t qLo, uint32_t qHi,
+                    const uint32_t* __restrict__ qCount, uint32_t tn, const BvhNode* __restrict__ nodes,
+                    const float4* __restrict__ fat, const uint64_t* __restrict__ category, uint32_t rejectLeaf,
+                    uint2* __restrict__ out, uint32_t capacity, uint32_t* counter, uint32_t* stackOverflow)
 {
     __shared__ uint2 stages[4][kStageCap];
     uint2* stage = stages[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t i = qLo + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < qHi && i < qn && tn >= 2;
+    const uint32_t qEnd = qCount ? min(qHi, *qCount) : qHi;
+    const bool live = i < qEnd && i < qn && tn >= 2;
     uint32_t qs = 0;
     float4 qb = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     uint64_t qc = 0;
@@ -607,13 +611,13 @@ __global__ void __launch_bounds__(128)
             if (emitL)
             {
                 const uint32_t ts = leaf_shape(links.x);
-                stage[staged + __popc(eL & ltMask)] = make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
+                stage[staged + __popc(eL & ltMask)] = make_uint2(ORD ? min(qs, ts) : qs, ORD ? max(qs, ts) : ts);
             }
             if (emitR)
             {
                 const uint32_t ts = leaf_shape(links.y);
                 stage[staged + __popc(eL) + __popc(eR & ltMask)] =
-                    make_uint2(SELF ? min(qs, ts) : qs, SELF ? max(qs, ts) : ts);
+                    make_uint2(ORD ? min(qs, ts) : qs, ORD ? max(qs, ts) : ts);
             }
             staged += __popc(eL) + __popc(eR);
             __syncwarp();

@@ -142,9 +142,13 @@ int c2d_gpu_set_small_scene_limit(c2d_gpu_ctx* ctx, uint32_t shapes);
  * reference's pair set, each pair exactly once (owner rule).  (The grid broadphase splits its sorted cell entries instead.)
  *
  * c2d_gpu_set_shard: this context is `rank` of `world`.  Default 0 of 1.
- *   - the Dynamic tree (c2d_gpu_set_slab_mode, below) is cut into Morton-key slabs balanced from the global key histogram
- *     every frame; a rank's tree holds the shapes whose key falls into its slab plus the HALO: shapes of higher ranks whose
- *     leaf box may overlap an owned one.  Only owned leaves query; a pair of two slabs is emitted by the lower rank.
+ *   - the Dynamic tree (c2d_gpu_set_slab_mode, below) is cut into Morton slabs: all Dynamic shapes are ordered by the
+ *     Morton key of their leaf box (the same stable sort on every rank) and rank r owns positions [n r / world, n (r+1) / world)
+ *     - balanced by construction.  The order is renewed when shapes are added / removed and every `rebuild period` frames
+ *     (c2d_gpu_set_rebuild_period); ownership is frozen in between.  A rank's tree holds its owned leaves (refit every
+ *     frame); the HALO - shapes of higher ranks whose current leaf box may overlap an owned one - is selected every frame on
+ *     the device and queries that tree.  Only owned leaves and halo shapes query; a pair of two slabs is emitted by the
+ *     lower rank.
  *   - Bullet queries are split by index range; Bullet x Dynamic pairs are emitted by the rank that owns the Dynamic shape. */
 int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world);
 /* Morton-slab build of the Dynamic tree when world > 1 and the tree has at least `min_shapes` leaves (smaller trees are
