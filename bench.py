@@ -317,6 +317,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     # computes its Morton slab and returns ITS share of the pairs into its own host memory.
     def e2e_loop(frames: int, skip: int):
         times, moves, pairs, up, down, xms, gms, xbytes, gbytes = [], [], 0, 0.0, 0.0, [], [], 0.0, 0.0
+        stages = dict(ms_refit=0.0, ms_build=0.0, ms_broad=0.0, ms_narrow=0.0, ms_device=0.0, ms_total=0.0)
         for f in range(skip + frames):
             d = frame_moves()
             if f == skip:
@@ -333,6 +334,8 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
                 st = b.stats()
                 times.append(sec.value)
                 moves.append(tm)
+                for k in stages:
+                    stages[k] += st[k] / frames
                 pairs += n
                 up += st["h2d_bytes"]
                 down += st["d2h_bytes"]
@@ -345,7 +348,8 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
         barrier()
         return dict(elapsed=allmax(float(np.sum(times))), pairs=pairs, h2d=allsum(up) / frames, d2h=allsum(down) / frames,
                     moves_ms=allmax(1e3 * float(np.mean(moves))), exchange_ms=float(np.mean(xms)) if xms else 0.0,
-                    gather_ms=float(np.mean(gms)) if gms else 0.0, exchange_bytes=xbytes / frames, gather_bytes=gbytes / frames)
+                    gather_ms=float(np.mean(gms)) if gms else 0.0, exchange_bytes=xbytes / frames, gather_bytes=gbytes / frames,
+                    stages=stages)
 
     if world > 1:
         b.group_options(results=capi.RESULTS_LOCAL, exchange=True)
@@ -442,11 +446,12 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
                        f"GPUs, one process each; in-library decomposition (include/c2d_gpu.h multi-GPU): scene mirrored, the "
                        f"Dynamic tree cut into Morton-key slabs balanced from the key histogram every frame (rank 0: "
                        f"{n_query:.0f} owned + {n_tree - n_query:.0f} halo leaves of {n_dyn}), owner rule, no data-path "
-                       f"collective in the device-resident loop; e2e loop: ncclAllGather of the 12-byte move records")
+                       f"collective in the device-resident loop; e2e loop: the 12-byte move records of every rank broadcast over NVLink")
     e2e_out = {"value": e2e_pairs_all / e2e_elapsed, "unit": UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
                "h2d_bytes_per_step": e2e["h2d"], "d2h_bytes_per_step": e2e["d2h"],
                "moves_host_ms": e2e["moves_ms"],
                "whole_frame_ms": e2e["moves_ms"] + 1e3 * e2e_elapsed / K,
+               "rank0_stage_ms": e2e["stages"],
                "call": ("c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity" if world == 1
                         else "per rank: moveEntity(id, Translation) for the 1/N of the entities it drives, then the collective "
                              "c2d::Registry<uint32_t>::getCollidingPairs() returning the rank's share into host memory; time = "
@@ -455,7 +460,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
         e2e_out["view_ms_per_step"] = 1e3 * float(np.mean(view_times))
         e2e_out["view_call"] = "Registry::getCollidingPairsView() (extension: span over the pinned result buffer)"
     else:
-        e2e_out["collective"] = {"name": "ncclAllGather (16-byte header + 12-byte move records, device to device)",
+        e2e_out["collective"] = {"name": "ncclAllGather of a 16-byte header + one grouped ncclBroadcast per rank of its 12-byte move records (device to device)",
                                  "bytes_received_per_rank_per_step": e2e["exchange_bytes"],
                                  "device_ms_per_step": e2e["exchange_ms"]}
         e2e_out["root_gather"] = {"what": "GroupResults::Root - all records gathered to rank 0 over NVLink (ncclAllGather of "

@@ -2,8 +2,8 @@
 //
 // One context per GPU, one communicator per group.  Two data-path collectives exist, both device to device over
 // NVLink / NVSwitch and both enqueued on the context's own stream (no host staging, no torch):
-//   * the move exchange of a frame: ncclAllGather of a 16-byte header per rank, then ncclAllGather of the 12-byte
-//     translation records padded to the largest rank's count (c2d_gpu.cu: flush);
+//   * the move exchange of a frame: ncclAllGather of a 16-byte header per rank, then one grouped ncclBroadcast per rank
+//     of exactly its 12-byte translation records, straight out of the rank's device log (c2d_gpu.cu: flush);
 //   * the result gather: ncclAllGather of the pair counts, then one ncclBroadcast per rank (C2D_RESULTS_ALL) or
 //     ncclSend / ncclRecv to rank 0 (C2D_RESULTS_ROOT) of the 84-byte records.
 // Everything else of the decomposition (slab ownership, halo, owner rule) needs no communication: shape state is
@@ -106,6 +106,24 @@ int c2d_host::comm_allgather(c2d_gpu_ctx* ctx, const void* send, void* recv, siz
     if (!ctx->comm.comm)
         return fail(ctx, "no communicator: call c2d_gpu_comm_init first");
     C2D_NCCL(ctx, nccl_api().AllGather(send, recv, bytesPerRank, ncclChar, comm_of(ctx), ctx->stream));
+    return 0;
+}
+
+int c2d_host::comm_gatherv(c2d_gpu_ctx* ctx, const void* send, void* recvBase, const size_t* bytes, size_t strideBytes)
+{
+    if (!ctx->comm.comm)
+        return fail(ctx, "no communicator: call c2d_gpu_comm_init first");
+    NcclApi& api = nccl_api();
+    C2D_NCCL(ctx, api.GroupStart());
+    for (uint32_t r = 0; r < ctx->shardWorld; ++r)
+    {
+        if (!bytes[r])
+            continue;
+        char* dst = static_cast<char*>(recvBase) + static_cast<size_t>(r) * strideBytes;
+        C2D_NCCL(ctx, api.Broadcast(r == ctx->shardRank ? send : dst, dst, bytes[r], ncclChar, static_cast<int>(r), comm_of(ctx),
+                                    ctx->stream));
+    }
+    C2D_NCCL(ctx, api.GroupEnd());
     return 0;
 }
 

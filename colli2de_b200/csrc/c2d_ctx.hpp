@@ -166,7 +166,6 @@ struct CommState
     int resultMode = 0;         // C2D_RESULTS_*
     DevBuf<uint32_t> dHeader;   // [world x 4] per-rank header of the move exchange: count, body mask, 0, 0
     uint32_t* hHeader = nullptr; // pinned: [0..3] mine, [4 ..] everybody's
-    DevBuf<TransRec> sendRecs;  // this rank's records, padded to the all-gather stride
     DevBuf<TransRec> gathered;  // world x stride translation records
     DevBuf<PairOut> outAll;     // gathered results
     DevBuf<uint64_t> dPairCounts;
@@ -249,6 +248,13 @@ struct c2d_gpu_ctx
     PinnedVec<MoveRec>* moveLog = &moveLogs[0];
     int logIndex = 0;
     cudaEvent_t logConsumed[2] = {}; // recorded after the H2D copies of a set were enqueued
+    // Early upload of the translation log: while the host is still inside its moveEntity loop, every ~1 MB of new records
+    // goes up on a second stream, so the query's flush only uploads the tail (c2d_gpu.cu: early_upload_translations)
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t transApplied = nullptr;  // main stream: the last kernels that read dTransLog
+    cudaEvent_t transUploadedEv = nullptr; // copy stream: the last early chunk
+    size_t transUploaded = 0;            // records of the current transLog already enqueued into dTransLog
+    bool earlyUpload = true;
     std::vector<Round> rounds;
     DevBuf<FlagRec> dFlagLog;
     DevBuf<AddRec> dAddLog;
@@ -318,6 +324,8 @@ int copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, uint64_t by
 int copy_host(c2d_gpu_ctx* ctx, const void* srcHost, void* dstHost, uint64_t bytes);  // pinned -> pageable, threaded
 // c2d_comm.cu (all collective over the group, enqueued on the context's stream)
 int comm_allgather(c2d_gpu_ctx* ctx, const void* send, void* recv, size_t bytesPerRank);
+// rank r's bytes[r] bytes at `send` arrive at recvBase + r * strideBytes on every rank (one grouped ncclBroadcast per rank)
+int comm_gatherv(c2d_gpu_ctx* ctx, const void* send, void* recvBase, const size_t* bytes, size_t strideBytes);
 int comm_gather_results(c2d_gpu_ctx* ctx); // after a frame: the records of all ranks -> comm.outAll (per the result mode)
 void comm_release(c2d_gpu_ctx* ctx);
 // c2d_rays.cu

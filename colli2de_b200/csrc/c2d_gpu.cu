@@ -219,7 +219,7 @@ namespace
 // Move exchange of a multi-GPU group (c2d_gpu_comm_set_move_exchange): the frame's translation records of every rank are
 // all-gathered device to device and applied on every rank.  Collective: called by every rank's c2d_gpu_collide* flush,
 // also by ranks that logged nothing.  `local` = this rank's records in the device log, bodies = the trees they touch.
-int exchange_translations(c2d_gpu_ctx* ctx, const TransRec* hostRecs, uint32_t count, uint32_t bodies)
+int exchange_translations(c2d_gpu_ctx* ctx, uint32_t count, uint32_t bodies)
 {
     CommState& cm = ctx->comm;
     cudaStream_t s = ctx->stream;
@@ -245,14 +245,13 @@ int exchange_translations(c2d_gpu_ctx* ctx, const TransRec* hostRecs, uint32_t c
     cm.exchangeBytes = (total - count) * sizeof(TransRec);
     if (stride)
     {
-        C2D_CUDA(ctx, cm.sendRecs.reserve(stride));
+        // this rank's records are in dTransLog already (flush: early chunks + tail); every rank broadcasts exactly its
+        // count into block r of the gathered buffer
         C2D_CUDA(ctx, cm.gathered.reserve(static_cast<size_t>(stride) * world));
-        if (count)
-        {
-            C2D_CUDA(ctx, cudaMemcpyAsync(cm.sendRecs.ptr, hostRecs, count * sizeof(TransRec), cudaMemcpyHostToDevice, s));
-            ctx->h2dBytes += count * sizeof(TransRec);
-        }
-        if (int rc = comm_allgather(ctx, cm.sendRecs.ptr, cm.gathered.ptr, static_cast<size_t>(stride) * sizeof(TransRec)))
+        size_t bytes[kSlabMaxWorld];
+        for (uint32_t r = 0; r < world; ++r)
+            bytes[r] = static_cast<size_t>(cm.hHeader[4 + 4 * r]) * sizeof(TransRec);
+        if (int rc = comm_gatherv(ctx, ctx->dTransLog.ptr, cm.gathered.ptr, bytes, static_cast<size_t>(stride) * sizeof(TransRec)))
             return rc;
         const size_t threads = static_cast<size_t>(stride) * world;
         C2D_TIMED(ctx, "k_apply_translates", k_apply_translates_gathered<<<blocks_for(threads, 256), 256, 0, s>>>(
@@ -264,6 +263,33 @@ int exchange_translations(c2d_gpu_ctx* ctx, const TransRec* hostRecs, uint32_t c
     }
     C2D_CUDA(ctx, cudaEventRecord(cm.evX[1], s));
     cm.exchangeTimed = true;
+    return 0;
+}
+} // namespace
+
+namespace
+{
+constexpr size_t kEarlyUploadRecords = (1u << 20) / sizeof(TransRec); // ~1 MB of 12-byte records per chunk
+
+// Records [transUploaded, size) of the translation log -> the same offsets of dTransLog, on the copy stream.  The copies
+// overlap the caller's own moveEntity loop; flush() makes the main stream wait for them and uploads only the tail.
+int early_upload_translations(c2d_gpu_ctx* ctx)
+{
+    PinnedVec<TransRec>& log = *ctx->transLog;
+    if (ctx->dTransLog.capacity < log.capacity)
+    {
+        // growing the device log drops its contents: start over (warm-up only; both logs settle at the frame's size)
+        C2D_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
+        C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        C2D_CUDA(ctx, ctx->dTransLog.reserve(log.capacity));
+        ctx->transUploaded = 0;
+    }
+    if (ctx->transUploaded == 0)
+        C2D_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->transApplied, 0)); // last frame's kernels still read dTransLog
+    const size_t first = ctx->transUploaded, count = log.size - first;
+    C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dTransLog.ptr + first, log.data + first, count * sizeof(TransRec), cudaMemcpyHostToDevice,
+                                  ctx->copyStream));
+    ctx->transUploaded = log.size;
     return 0;
 }
 } // namespace
@@ -310,17 +336,33 @@ int c2d_host::flush(c2d_gpu_ctx* ctx, bool collective)
         C2D_CUDA(ctx, ctx->dAddLog.reserve(na));
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dAddLog.ptr, ctx->addLog->data, na * sizeof(AddRec), cudaMemcpyHostToDevice, s));
     }
-    if (nt)
+    if (ntLogged)
     {
-        C2D_CUDA(ctx, ctx->dTransLog.reserve(nt));
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dTransLog.ptr, ctx->transLog->data, nt * sizeof(TransRec), cudaMemcpyHostToDevice, s));
+        // the chunks that went up during the caller's move loop, then the tail (in a group with the move exchange the
+        // device log is this rank's send buffer)
+        size_t done = std::min(ctx->transUploaded, ntLogged);
+        if (ctx->dTransLog.capacity < ntLogged)
+        {
+            C2D_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
+            C2D_CUDA(ctx, ctx->dTransLog.reserve(ntLogged));
+            done = 0;
+        }
+        if (done)
+        {
+            C2D_CUDA(ctx, cudaEventRecord(ctx->transUploadedEv, ctx->copyStream));
+            C2D_CUDA(ctx, cudaStreamWaitEvent(s, ctx->transUploadedEv, 0));
+        }
+        if (ntLogged > done)
+            C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dTransLog.ptr + done, ctx->transLog->data + done, (ntLogged - done) * sizeof(TransRec),
+                                          cudaMemcpyHostToDevice, s));
     }
+    ctx->transUploaded = 0;
     if (nm)
     {
         C2D_CUDA(ctx, ctx->dMoveLog.reserve(nm));
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dMoveLog.ptr, ctx->moveLog->data, nm * sizeof(MoveRec), cudaMemcpyHostToDevice, s));
     }
-    ctx->h2dBytes += nf * sizeof(FlagRec) + na * sizeof(AddRec) + nt * sizeof(TransRec) + nm * sizeof(MoveRec);
+    ctx->h2dBytes += nf * sizeof(FlagRec) + na * sizeof(AddRec) + ntLogged * sizeof(TransRec) + nm * sizeof(MoveRec);
 
     for (size_t r = 0; r < ctx->rounds.size(); ++r)
     {
@@ -370,10 +412,11 @@ int c2d_host::flush(c2d_gpu_ctx* ctx, bool collective)
         uint32_t bodies = 0;
         for (size_t i = 0; i < ntLogged; ++i)
             bodies |= 1u << meta_body(ctx->hostMeta[ctx->transLog->data[i].shape]);
-        if (int rc = exchange_translations(ctx, ctx->transLog->data, static_cast<uint32_t>(ntLogged), bodies))
+        if (int rc = exchange_translations(ctx, static_cast<uint32_t>(ntLogged), bodies))
             return rc;
     }
     C2D_CUDA(ctx, cudaGetLastError());
+    C2D_CUDA(ctx, cudaEventRecord(ctx->transApplied, s));
     // The pinned logs are double buffered: the host keeps logging into the other set while these copies drain, and
     // only waits (normally not at all) if that set's previous upload has not completed yet.
     C2D_CUDA(ctx, cudaEventRecord(ctx->logConsumed[ctx->logIndex], s));
@@ -938,6 +981,12 @@ int c2d_gpu_create(int device, c2d_gpu_ctx** out_ctx)
     for (int i = 0; i < 2 && e == cudaSuccess; ++i)
         e = cudaEventCreateWithFlags(&ctx->logConsumed[i], cudaEventDisableTiming);
     if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaEventCreateWithFlags(&ctx->transApplied, cudaEventDisableTiming);
+    if (e == cudaSuccess)
+        e = cudaEventCreateWithFlags(&ctx->transUploadedEv, cudaEventDisableTiming);
+    if (e == cudaSuccess)
         e = cudaMalloc(reinterpret_cast<void**>(&ctx->dScratch), sizeof(FrameScratch));
     if (e == cudaSuccess)
         e = cudaHostAlloc(reinterpret_cast<void**>(&ctx->hScratch), sizeof(FrameScratch), cudaHostAllocDefault);
@@ -988,6 +1037,15 @@ void c2d_gpu_destroy(c2d_gpu_ctx* ctx)
     ctx->copyPool.reset();
     for (cudaEvent_t ev : ctx->copyEvents)
         cudaEventDestroy(ev);
+    if (ctx->copyStream)
+    {
+        cudaStreamSynchronize(ctx->copyStream);
+        cudaStreamDestroy(ctx->copyStream);
+    }
+    if (ctx->transApplied)
+        cudaEventDestroy(ctx->transApplied);
+    if (ctx->transUploadedEv)
+        cudaEventDestroy(ctx->transUploadedEv);
     for (cudaEvent_t ev : ctx->logConsumed)
         if (ev)
             cudaEventDestroy(ev);
@@ -1005,6 +1063,8 @@ int c2d_gpu_clear(c2d_gpu_ctx* ctx)
     ++ctx->mutationEpoch;
     cudaSetDevice(ctx->device);
     C2D_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    C2D_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
+    ctx->transUploaded = 0;
     ctx->flagLog->size = ctx->addLog->size = ctx->transLog->size = ctx->moveLog->size = 0;
     ctx->rounds.clear();
     for (StagedBatch* sb : ctx->staged)
@@ -1178,6 +1238,8 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
     if (shape >= ctx->hostMeta.size() || !(ctx->hostMeta[shape] & META_ALIVE))
         return fail(ctx, "c2d_gpu_shape_translate: unknown shape");
     claim(ctx, shape, PH_TRANS);
+    if (ctx->transUploaded && ctx->transLog->size == ctx->transLog->capacity)
+        cudaStreamSynchronize(ctx->copyStream); // the pinned log is about to move: its chunks in flight must land first
     TransRec* r = ctx->transLog->push();
     if (!r)
         return fail(ctx, "pinned host allocation failed");
@@ -1185,12 +1247,16 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
     r->dx = dx;
     r->dy = dy;
     mark_dirty(ctx, meta_body(ctx->hostMeta[shape]));
+    if (ctx->earlyUpload && ctx->transLog->size - ctx->transUploaded >= kEarlyUploadRecords)
+        return early_upload_translations(ctx);
     return 0;
 }
 
 int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy)
 {
     ++ctx->mutationEpoch;
+    if (ctx->transUploaded && ctx->transLog->size + n > ctx->transLog->capacity)
+        cudaStreamSynchronize(ctx->copyStream);
     if (!ctx->transLog->reserve(ctx->transLog->size + n))
         return fail(ctx, "pinned host allocation failed");
     for (uint32_t i = 0; i < n; ++i)
