@@ -255,6 +255,7 @@ struct c2d_gpu_ctx
     cudaEvent_t transUploadedEv = nullptr; // copy stream: the last early chunk
     size_t transUploaded = 0;            // records of the current transLog already enqueued into dTransLog
     bool earlyUpload = true;
+    uint32_t transBodies = 0;            // bodies (bit per BodyType) touched by the translations logged since the last flush
     std::vector<Round> rounds;
     DevBuf<FlagRec> dFlagLog;
     DevBuf<AddRec> dAddLog;

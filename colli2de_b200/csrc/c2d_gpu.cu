@@ -409,12 +409,10 @@ int c2d_host::flush(c2d_gpu_ctx* ctx, bool collective)
     }
     if (exchange && collective)
     {
-        uint32_t bodies = 0;
-        for (size_t i = 0; i < ntLogged; ++i)
-            bodies |= 1u << meta_body(ctx->hostMeta[ctx->transLog->data[i].shape]);
-        if (int rc = exchange_translations(ctx, static_cast<uint32_t>(ntLogged), bodies))
+        if (int rc = exchange_translations(ctx, static_cast<uint32_t>(ntLogged), ctx->transBodies))
             return rc;
     }
+    ctx->transBodies = 0;
     C2D_CUDA(ctx, cudaGetLastError());
     C2D_CUDA(ctx, cudaEventRecord(ctx->transApplied, s));
     // The pinned logs are double buffered: the host keeps logging into the other set while these copies drain, and
@@ -1246,7 +1244,9 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
     r->shape = shape;
     r->dx = dx;
     r->dy = dy;
-    mark_dirty(ctx, meta_body(ctx->hostMeta[shape]));
+    const uint32_t body = meta_body(ctx->hostMeta[shape]);
+    ctx->transBodies |= 1u << body;
+    mark_dirty(ctx, body);
     if (ctx->earlyUpload && ctx->transLog->size - ctx->transUploaded >= kEarlyUploadRecords)
         return early_upload_translations(ctx);
     return 0;
@@ -1381,8 +1381,8 @@ int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats*
 namespace
 {
 constexpr uint64_t kPoolThresholdBytes = 4ull << 20; // smaller results: one copy on the calling thread
-constexpr uint64_t kFetchChunkBytes = 1ull << 20;
-constexpr uint32_t kFetchWaveChunks = 64; // 64 MB per wave; two staging halves alternate
+constexpr uint64_t kFetchWaveBytes = 64ull << 20; // 64 MB per wave; two staging halves alternate
+constexpr uint64_t kFetchChunkBytes = 1ull << 20; // copy_host: pinned -> pageable split between the helper threads
 
 // Destination buffers are usually freshly allocated (a new std::vector per call): ask for transparent huge pages so
 // that filling a GB-sized result costs thousands of page faults instead of hundreds of thousands.  A hint only.
@@ -1397,6 +1397,14 @@ void advise_huge_pages(void* dst, uint64_t bytes)
 #else
     (void)dst, (void)bytes;
 #endif
+}
+
+uint64_t env_kb(const char* name, uint64_t fallbackKb)
+{
+    const char* env = std::getenv(name);
+    uint64_t kb = env ? std::strtoull(env, nullptr, 10) : fallbackKb;
+    kb = kb < 16 ? 16 : (kb > 65536 ? 65536 : kb);
+    return kb << 10;
 }
 
 c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
@@ -1421,8 +1429,13 @@ c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
 }
 } // namespace
 
-// Device memory -> caller (pageable) memory: device-to-host copies of 1 MB chunks into pinned staging, moved on to
-// `dst` by the helper threads (and this thread) as each chunk lands.
+// Device memory -> caller (pageable) memory: device-to-host copies into pinned staging, moved on to `dst` by the helper
+// threads (and this thread) as the data lands.  Measured on B200 / PCIe 5 (scripts/probe_copy.py, 35 MB): one copy into
+// pinned memory takes 0.63 ms (55.7 GB/s); one thread moves pinned -> pageable memory at ~9 GB/s; a cudaMemcpyAsync +
+// cudaEventRecord pair costs ~8 us of host time.  So the DMA goes in 4 MB chunks (few API calls, few bubbles on the
+// link), each chunk is memcpy'd as eight 512 KB units by whichever workers are free, and the last two chunks are cut
+// into 256 KB DMA pieces because the memcpy of the very last piece is the tail nobody can overlap: 0.77 ms
+// (1 MB chunks = units: 0.85-0.93 ms; 8 MB: 0.83 ms; 256 KB: 1.2 ms, issue bound).
 int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, uint64_t total)
 {
     if (!total)
@@ -1439,15 +1452,44 @@ int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, u
         std::memcpy(out, ctx->copyStage.data, total);
         return 0;
     }
+    // DMA chunk (one cudaMemcpyAsync + one event), memcpy unit of the workers, DMA piece size inside the tail region
+    static const uint64_t chunkBytes = env_kb("C2D_FETCH_CHUNK_KB", 4096), unitBytes = env_kb("C2D_FETCH_UNIT_KB", 512),
+                          tailPiece = env_kb("C2D_FETCH_TAIL_KB", 256);
     c2d_host::CopyPool* pool = copy_pool(ctx);
     pool->wait();
     advise_huge_pages(dstHost, total);
     // two staging halves: while the workers drain wave w, the device-to-host copies of wave w + 1 are already in flight
-    const uint64_t waveBytes = kFetchWaveChunks * kFetchChunkBytes;
+    const uint64_t waveBytes = kFetchWaveBytes;
     const uint64_t waves = (total + waveBytes - 1) / waveBytes;
     if (!ctx->copyStage.reserve(waves > 1 ? 2 * waveBytes : waveBytes))
         return fail(ctx, "pinned host allocation failed");
-    while (ctx->copyEvents.size() < 2 * kFetchWaveChunks)
+    struct Unit
+    {
+        uint64_t off, len; // within the wave
+        uint32_t event;    // index of the DMA chunk that carries it
+    };
+    struct Chunk
+    {
+        uint64_t off, len;
+    };
+    const auto wave_bytes = [&](uint64_t w) { return (w + 1) * waveBytes <= total ? waveBytes : total - w * waveBytes; };
+    const auto plan = [&](uint64_t w, std::vector<Chunk>& chunks, std::vector<Unit>& units) {
+        chunks.clear();
+        units.clear();
+        const uint64_t bytes = wave_bytes(w);
+        for (uint64_t off = 0; off < bytes;)
+        {
+            uint64_t len = std::min(chunkBytes, bytes - off);
+            if (w + 1 == waves && off + len + chunkBytes >= bytes) // tail region of the transfer: small DMA pieces
+                len = std::min(tailPiece, bytes - off);
+            for (uint64_t p = 0; p < len; p += unitBytes)
+                units.push_back(Unit{off + p, std::min(unitBytes, len - p), static_cast<uint32_t>(chunks.size())});
+            chunks.push_back(Chunk{off, len});
+            off += len;
+        }
+    };
+    const size_t maxChunks = static_cast<size_t>(waveBytes / chunkBytes + 2 * chunkBytes / tailPiece + 4);
+    while (ctx->copyEvents.size() < 2 * maxChunks)
     {
         cudaEvent_t ev = nullptr;
         C2D_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
@@ -1455,16 +1497,17 @@ int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, u
     }
     char* stageBase = reinterpret_cast<char*>(ctx->copyStage.data);
     const int device = ctx->device;
-    const auto wave_bytes = [&](uint64_t w) { return (w + 1) * waveBytes <= total ? waveBytes : total - w * waveBytes; };
+    std::vector<Chunk> chunkPlan[2];
+    std::vector<Unit> unitPlan[2];
     const auto issue = [&](uint64_t w) -> int {
-        const uint64_t bytes = wave_bytes(w);
-        const uint32_t chunks = static_cast<uint32_t>((bytes + kFetchChunkBytes - 1) / kFetchChunkBytes);
+        std::vector<Chunk>& chunks = chunkPlan[w & 1];
+        plan(w, chunks, unitPlan[w & 1]);
         char* stage = stageBase + (w & 1) * waveBytes;
-        for (uint32_t k = 0; k < chunks; ++k)
+        for (size_t k = 0; k < chunks.size(); ++k)
         {
-            const uint64_t off = k * kFetchChunkBytes, len = off + kFetchChunkBytes < bytes ? kFetchChunkBytes : bytes - off;
-            C2D_CUDA(ctx, cudaMemcpyAsync(stage + off, src + w * waveBytes + off, len, cudaMemcpyDeviceToHost, s));
-            C2D_CUDA(ctx, cudaEventRecord(ctx->copyEvents[(w & 1) * kFetchWaveChunks + k], s));
+            C2D_CUDA(ctx, cudaMemcpyAsync(stage + chunks[k].off, src + w * waveBytes + chunks[k].off, chunks[k].len,
+                                          cudaMemcpyDeviceToHost, s));
+            C2D_CUDA(ctx, cudaEventRecord(ctx->copyEvents[(w & 1) * maxChunks + k], s));
         }
         return 0;
     };
@@ -1475,26 +1518,30 @@ int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, u
         if (w + 1 < waves)
             if (int rc = issue(w + 1))
                 return rc;
-        const uint64_t bytes = wave_bytes(w);
-        const uint32_t chunks = static_cast<uint32_t>((bytes + kFetchChunkBytes - 1) / kFetchChunkBytes);
-        // every worker (helpers + this thread) takes the next chunk whose device-to-host copy has landed
+        // every worker (helpers + this thread) takes the next unit as soon as the chunk that carries it has landed
         std::atomic<uint32_t> next{0};
         std::atomic<int> cudaErr{0};
         const char* stage = stageBase + (w & 1) * waveBytes;
         char* dst = out + w * waveBytes;
-        const cudaEvent_t* events = ctx->copyEvents.data() + (w & 1) * kFetchWaveChunks;
-        auto work = [&next, &cudaErr, device, events, chunks, bytes, stage, dst](unsigned) {
+        const cudaEvent_t* events = ctx->copyEvents.data() + (w & 1) * maxChunks;
+        const Unit* units = unitPlan[w & 1].data();
+        const uint32_t count = static_cast<uint32_t>(unitPlan[w & 1].size());
+        auto work = [&next, &cudaErr, device, events, units, count, stage, dst](unsigned) {
             cudaSetDevice(device);
-            for (uint32_t k = next.fetch_add(1); k < chunks; k = next.fetch_add(1))
+            uint32_t landed = 0xffffffffu; // last chunk this thread saw complete (chunks complete in order)
+            for (uint32_t k = next.fetch_add(1); k < count; k = next.fetch_add(1))
             {
-                const cudaError_t e = cudaEventSynchronize(events[k]);
-                if (e != cudaSuccess)
+                if (landed == 0xffffffffu || units[k].event > landed)
                 {
-                    cudaErr.store(static_cast<int>(e));
-                    continue;
+                    const cudaError_t e = cudaEventSynchronize(events[units[k].event]);
+                    if (e != cudaSuccess)
+                    {
+                        cudaErr.store(static_cast<int>(e));
+                        continue;
+                    }
+                    landed = units[k].event;
                 }
-                const uint64_t off = k * kFetchChunkBytes, len = off + kFetchChunkBytes < bytes ? kFetchChunkBytes : bytes - off;
-                std::memcpy(dst + off, stage + off, len);
+                std::memcpy(dst + units[k].off, stage + units[k].off, units[k].len);
             }
         };
         pool->launch(work);
