@@ -490,6 +490,189 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------------
+# cfg 5: batched rayCast, 1 M rays (odd: finite, length 50; even: infinite) against a 4 M-shape scene
+RAY_METRIC = "batched rayCast rays/sec, 1M rays vs 4M shapes (ms/batch = ms_per_step)"
+RAY_UNIT = "rays/s"
+RAY_SCENE = (3_640_000, 360_000, 9535.0, 77)  # dynamic, static, box, seed (SURVEY.md 8(d) cfg 5: cfg-3 mix, same density)
+
+
+def ray_workload_label(n_rays: int) -> str:
+    return (f"cfg5-rays: {n_rays} rays (even index infinite unit direction, odd index finite length 50, mask ~0) vs "
+            f"{RAY_SCENE[0]} dynamic mixed + {RAY_SCENE[1]} static polygons in [0,{RAY_SCENE[2]:.0f}]^2 (SURVEY.md 8(d) cfg 5)")
+
+
+def ray_reference(n_sample: int, ray4, inf, scene):
+    from tests import harness as H
+
+    which = "reference" if H.available("reference") else "oracle"
+    r = H.Backend(which)
+    scenes.populate(r, scene)
+    off, hits, sec = r.raycast(ray4[:n_sample], inf[:n_sample], with_time=True)
+    return r, which, off, hits, sec
+
+
+def run_rays_reference(args):
+    scene = scenes.mixed_scene(RAY_SCENE[0], RAY_SCENE[1], RAY_SCENE[2], seed=RAY_SCENE[3])
+    ray4, inf = scenes.rays(args.rays, RAY_SCENE[2], seed=13)
+    m = min(args.rays, 4000)
+    _, which, off, hits, sec = ray_reference(m, ray4, inf, scene)
+    return {"impl": "reference", "metric": RAY_METRIC, "value": m / sec, "unit": RAY_UNIT, "n_gpus": args.gpus, "steps": 1,
+            "warmup": 0, "ms_per_step": 1e3 * sec * args.rays / m, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": ray_workload_label(args.rays)},
+            "cpu_baseline": {"value": m / sec, "unit": RAY_UNIT, "cores": 1, "kind": "reference" if which == "reference" else "port",
+                             "sample": f"the first {m} rays of the batch looped through Registry::rayCast(ray) (single thread); "
+                                       f"ms_per_step is the extrapolation to the whole batch", "host_cores": os.cpu_count()},
+            "e2e": {"value": m / sec, "unit": RAY_UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def run_rays(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    from colli2de_b200 import capi
+    from tests import harness as H
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (own arm) needs a CUDA device: colli2de_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = capi.lib()
+    scene = scenes.mixed_scene(RAY_SCENE[0], RAY_SCENE[1], RAY_SCENE[2], seed=RAY_SCENE[3])
+    n = args.rays
+    ray4, inf = scenes.rays(n, RAY_SCENE[2], seed=13)
+    b = H.Backend("b200")
+    scenes.populate(b, scene)  # every rank mirrors the scene; the ray batch is what is sharded
+    ctx = b.native_context()
+    if world > 1:
+        capi.set_shard(ctx, rank, world)
+        b.group_ray_sharding(True)
+    K, W = args.steps, max(args.warmup, 3)
+    lo, hi = (n * rank) // world, (n * (rank + 1)) // world
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allred(x: float, op):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    # ---- parity: the first rays of the batch against the reference's rayCast on rank 0 ------------------------------
+    parity = None
+    if args.parity_frames > 0:
+        m = min(n, 1500)
+        off, hits = b.raycast(ray4[:m], inf[:m])
+        counts = (off[1:] - off[:-1]).astype(np.int64)
+        parts = [(counts.tobytes(), hits.tobytes())]
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (counts.tobytes(), hits.tobytes()))
+        if rank == 0:
+            got_counts = sum(np.frombuffer(c, np.int64) for c, _ in parts)  # every ray is non-empty on one rank only
+            got_hits = np.concatenate([np.frombuffer(h, hits.dtype) for _, h in parts])  # rank order = ray order
+            got_off = np.concatenate([[0], np.cumsum(got_counts)])
+            ref, which, roff, rhits, _ = ray_reference(m, ray4, inf, scene)
+            same = sum(1 for i in range(m) if rhits[int(roff[i]):int(roff[i + 1])].tobytes() ==
+                       got_hits[int(got_off[i]):int(got_off[i + 1])].tobytes())
+            parity = {"checker": "oracle/_ref (the unmodified reference)" if which == "reference" else "oracle/c2d_oracle.c",
+                      "rays": m, "rays_identical": same, "hits_expected": int(len(rhits)), "hits_got": int(len(got_hits)),
+                      "note": "rays whose hit list differs hold hits with exactly equal (entry, exit) keys, which std::set keeps "
+                              "one of by traversal order (SURVEY.md D10)", "ok": same >= m - 8 and len(rhits) == len(got_hits)}
+            ref.close()
+
+    # ---- device-resident arm: c2d_gpu_raycast_begin (the hits stay in HBM; offsets and the total come back) -----------
+    RAY = np.dtype([("sx", "<f4"), ("sy", "<f4"), ("ex", "<f4"), ("ey", "<f4"), ("mask", "<u8"), ("infinite", "<u4"), ("pad", "<u4")])
+    rays = np.zeros(n, RAY)
+    rays["sx"], rays["sy"], rays["ex"], rays["ey"] = ray4[:, 0], ray4[:, 1], ray4[:, 2], ray4[:, 3]
+    rays["mask"], rays["infinite"] = np.uint64(0xFFFFFFFFFFFFFFFF), inf
+    stats = capi.Stats()
+    lib.c2d_gpu_raycast_begin.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_void_p),
+                                          C.POINTER(capi.Stats)]
+    total, offs = C.c_uint64(0), C.c_void_p()
+
+    def begin():
+        rc = lib.c2d_gpu_raycast_begin(ctx, n, rays.ctypes.data, 0, C.byref(total), C.byref(offs), C.byref(stats))
+        if rc != 0:
+            raise RuntimeError(lib.c2d_gpu_last_error(ctx).decode())
+        return int(total.value)
+
+    for _ in range(W):
+        begin()
+    sampler = ClockSampler(local) if rank == 0 else None
+    barrier()
+    t0 = time.perf_counter()
+    hits_total, dev_ms, launches, leaf_hits = 0, 0.0, 0, 0
+    for _ in range(K):
+        hits_total += begin()
+        dev_ms += stats.ms_device
+        launches += int(stats.kernel_launches)
+        leaf_hits += int(stats.candidates)
+    barrier()
+    elapsed = allred(time.perf_counter() - t0, dist.ReduceOp.MAX if world > 1 else None)
+    clocks = sampler.stop() if sampler else None
+    hits_all = allred(float(hits_total), dist.ReduceOp.SUM if world > 1 else None)
+    leaf_all = allred(float(leaf_hits), dist.ReduceOp.SUM if world > 1 else None)
+    dev_ms_max = allred(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
+
+    # ---- end-to-end arm: Registry::rayCastBatch with host buffers (rays up, hit records down into a std::vector) ----------
+    offsets = np.zeros(n + 1, np.uint64)
+    e2e_times, up, down = [], 0.0, 0.0
+    for f in range(1 + K):
+        if f == 1:
+            barrier()
+        if world > 1:
+            barrier()
+        sec = C.c_double(0.0)
+        b.lib.rn_raycast(b.ctx, n, ray4.ctypes.data_as(C.POINTER(C.c_float)), inf.ctypes.data_as(C.POINTER(C.c_uint8)), None,
+                         offsets.ctypes.data_as(C.POINTER(C.c_uint64)), C.byref(sec))
+        b._check()
+        if f >= 1:
+            st = b.stats()
+            e2e_times.append(sec.value)
+            up += st["h2d_bytes"]
+            down += st["d2h_bytes"]
+    barrier()
+    e2e_elapsed = allred(float(np.sum(e2e_times)), dist.ReduceOp.MAX if world > 1 else None)
+    up_all = allred(up, dist.ReduceOp.SUM if world > 1 else None)
+    down_all = allred(down, dist.ReduceOp.SUM if world > 1 else None)
+    if rank != 0:
+        return None
+    peak, peak_src = measured_peak_gbs()
+    g_np = float(np.where(scene["shp_type"] == 3, 4 + 16 * scene["shp_count"].astype(np.float64),
+                          np.where(scene["shp_type"] == 0, 12, np.where(scene["shp_type"] == 1, 20, 16))).mean())
+    # bytes_alg(rayCast) = R*24 + L*(16 + 8) + H_c*(20 + g_np) + H*32, per batch and per rank
+    R, L, Hh = (hi - lo), leaf_all / K / world, hits_all / K / world
+    alg = R * 24 + L * 24 + L * (20 + g_np) + Hh * 32
+    batch_ms = dev_ms_max / K
+    achieved = alg / (batch_ms * 1e-3) / 1e9
+    return {
+        "metric": RAY_METRIC, "value": n * K / elapsed, "unit": RAY_UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * elapsed / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": ray_workload_label(n),
+                   "parallelism": "single GPU" if world == 1 else
+                   f"ray sharding (SURVEY.md 8(e)): the scene is mirrored on {world} GPUs, every rank is handed the whole batch "
+                   f"and casts its contiguous share ({hi - lo} rays); no exchange, every rank downloads its hits over its own PCIe link",
+                   "l2": "4 M-shape scene (~1 GB of shape state + trees) and ~8 GB of hit records per batch vs 126 MB L2, no explicit flush",
+                   "hits_per_batch": hits_all / K, "leaf_box_hits_per_batch": leaf_all / K},
+        "e2e": {"value": n * K / e2e_elapsed, "unit": RAY_UNIT, "ms_per_step": 1e3 * e2e_elapsed / K,
+                "h2d_bytes_per_step": up_all / K, "d2h_bytes_per_step": down_all / K,
+                "call": "c2d::Registry<uint32_t>::rayCastBatch(span<RayQuery>) -> offsets + std::vector<RayHit> in host memory"
+                        + ("" if world == 1 else " (per rank: its share of the batch; time = max over ranks)")},
+        "parity": parity, "gpu_launches": launches, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "rayCast batch (k_ray_block tiers + k_heavy_* + k_header_gather), whole batch on one rank",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "alg_bytes_per_launch": alg, "avg_launch_ms": batch_ms,
+                     "note": "divergent tree walks + per-ray sorting: latency bound, not bandwidth bound"},
+    }
+
+
 JSON_OUT = sys.stdout
 
 
@@ -505,7 +688,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS) + ["cfg5-rays"])
+    ap.add_argument("--rays", type=int, default=1_000_000, help="cfg5-rays: rays per batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="multi-GPU mode: strong (default) = the metric's fixed workload on N GPUs; weak = an N-times larger "
@@ -520,6 +704,21 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank, world, local = dist_env()
 
+    if args.workload == "cfg5-rays":
+        if args.impl == "reference":
+            if rank == 0:
+                print(json.dumps(run_rays_reference(args)), file=JSON_OUT, flush=True)
+            return 0
+        out = run_rays(args, rank, world, local)
+        if rank == 0:
+            if world == 1 and not args.no_cpu_baseline:
+                out["cpu_baseline"] = run_rays_reference(args)["cpu_baseline"]
+            print(json.dumps(out), file=JSON_OUT, flush=True)
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+        return 0
     if args.impl == "reference":
         if rank != 0:
             return 0

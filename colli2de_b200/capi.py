@@ -21,7 +21,7 @@ EXPORTS = [
     "c2d_gpu_read_candidates", "c2d_gpu_shape_slots", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
     "c2d_gpu_compute_aabb_batch",
     "c2d_gpu_set_slab_mode", "c2d_gpu_comm_unique_id", "c2d_gpu_comm_init", "c2d_gpu_comm_destroy",
-    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats", "c2d_gpu_read_transforms",
+    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats", "c2d_gpu_read_transforms", "c2d_gpu_set_ray_sharding",
 ]
 
 _lib = None
@@ -42,6 +42,14 @@ def lib() -> C.CDLL:
         _lib.c2d_gpu_read_boxes.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         _lib.c2d_gpu_read_candidates.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_uint64)]
     return _lib
+
+
+class Stats(C.Structure):
+    """c2d_gpu_stats"""
+    _fields_ = [("shapes_alive", C.c_uint64), ("candidates", C.c_uint64), ("pairs", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32), ("retries", C.c_uint32), ("ms_refit", C.c_float),
+                ("ms_build", C.c_float), ("ms_broad", C.c_float), ("ms_narrow", C.c_float), ("ms_device", C.c_float),
+                ("ms_total", C.c_float)]
 
 
 def _check(ctx, rc: int):
@@ -72,6 +80,12 @@ def set_slab_mode(ctx, min_shapes: int):
     """Morton-slab build of the Dynamic tree when world > 1 and it has >= min_shapes leaves (0 = never)."""
     lib().c2d_gpu_set_slab_mode.argtypes = [C.c_void_p, C.c_uint32]
     _check(ctx, lib().c2d_gpu_set_slab_mode(ctx, min_shapes))
+
+
+def set_ray_sharding(ctx, on: bool):
+    """Batched rayCast casts only this rank's contiguous share of the batch (the other rays return empty lists)."""
+    lib().c2d_gpu_set_ray_sharding.argtypes = [C.c_void_p, C.c_int]
+    _check(ctx, lib().c2d_gpu_set_ray_sharding(ctx, 1 if on else 0))
 
 
 class CommStats(C.Structure):

@@ -273,6 +273,7 @@ struct c2d_gpu_ctx
     TreeBuf slabTree;       // the rank-local tree (owned leaves) of the Dynamic body
     bool slabDirty = true;  // the Dynamic shapes changed since slabTree was built
     bool slabInUse = false; // this frame's Dynamic traversals run on slabTree
+    bool raySharding = false; // batched rayCast casts only this rank's share of the batch (c2d_gpu_set_ray_sharding)
     c2d_host::SlabState slab;
     c2d_host::CommState comm;
     int traverseVariant = 1;    // 0: divergent emit (k_traverse), 1: convergent loop + staged appends (k_traverse_sync)

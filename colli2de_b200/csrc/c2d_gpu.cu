@@ -1147,6 +1147,12 @@ int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world)
     return 0;
 }
 
+int c2d_gpu_set_ray_sharding(c2d_gpu_ctx* ctx, int on)
+{
+    ctx->raySharding = on != 0;
+    return 0;
+}
+
 int c2d_gpu_set_slab_mode(c2d_gpu_ctx* ctx, uint32_t min_shapes)
 {
     ctx->slabMinShapes = min_shapes;

@@ -1126,7 +1126,16 @@ int raycast_run(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, bool firstHit
 
     RayRun run{ctx, view_of(ctx, 0), view_of(ctx, 1), view_of(ctx, 2),
                ctx->broadphase == C2D_BROADPHASE_GRID ? static_cast<float>(static_cast<int32_t>(ctx->cellSize)) : 0.0f, firstHitOnly};
-    if (n > 0 && n <= kLatencyBatch)
+    // multi-GPU ray sharding (c2d_gpu_set_ray_sharding): every rank is handed the same batch over the same (mirrored) scene
+    // and casts the contiguous share [lo, hi) of it; the other rays come back with empty hit lists on this rank
+    uint32_t lo = 0, hi = n;
+    if (ctx->raySharding && ctx->shardWorld > 1)
+    {
+        lo = static_cast<uint32_t>(static_cast<uint64_t>(n) * ctx->shardRank / ctx->shardWorld);
+        hi = static_cast<uint32_t>(static_cast<uint64_t>(n) * (ctx->shardRank + 1) / ctx->shardWorld);
+    }
+    const bool sharded = lo != 0 || hi != n;
+    if (n > 0 && n <= kLatencyBatch && !sharded)
     {
         if (int rc = raycast_latency(run, n, rays, totalHits, leafHits, d2h, retries))
             return rc;
@@ -1136,9 +1145,11 @@ int raycast_run(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, bool firstHit
     {
         rb.resultOnHost = false;
         size_t ci = 0;
-        for (uint32_t first = 0; first < n; first += kRayChunk, ++ci)
+        for (uint32_t i = 0; i < lo; ++i)
+            rb.hostOffsets.data[i] = 0;
+        for (uint32_t first = lo; first < hi; first += kRayChunk, ++ci)
         {
-            const uint32_t m = std::min(kRayChunk, n - first);
+            const uint32_t m = std::min(kRayChunk, hi - first);
             C2D_CUDA(ctx, rb.dRays.reserve(m));
             if (!rb.hostOffsets32.reserve(m))
                 return fail(ctx, "pinned host allocation failed");
@@ -1155,7 +1166,8 @@ int raycast_run(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, bool firstHit
             totalHits += outCount;
             rb.chunkCount.push_back(outCount);
         }
-        rb.hostOffsets.data[n] = totalHits;
+        for (uint32_t i = hi; i <= n; ++i)
+            rb.hostOffsets.data[i] = totalHits;
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
         C2D_CUDA(ctx, cudaStreamSynchronize(s));
     }

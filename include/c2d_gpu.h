@@ -154,6 +154,12 @@ int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world);
 /* Morton-slab build of the Dynamic tree when world > 1 and the tree has at least `min_shapes` leaves (smaller trees are
  * mirrored on every rank and only the query leaves are split).  0 = never.  Default 65536. */
 int c2d_gpu_set_slab_mode(c2d_gpu_ctx* ctx, uint32_t min_shapes);
+/* Batched rayCast in a group (SURVEY.md section 8(e) "Rays", cfg 5): rays are independent units, so with ray sharding on every
+ * rank is handed the SAME batch (c2d_gpu_raycast / _begin / _first) over its mirror of the scene and casts the contiguous
+ * share [n rank / world, n (rank+1) / world) of it; the other rays come back with empty hit lists on this rank.  The
+ * per-ray lists of the ranks concatenate to the single-GPU result; no exchange, every rank downloads over its own PCIe
+ * link.  Needs c2d_gpu_set_shard (or c2d_gpu_comm_init) only.  Default off. */
+int c2d_gpu_set_ray_sharding(c2d_gpu_ctx* ctx, int on);
 /* The NCCL communicator of the group (libnccl.so.2 is loaded with dlopen on first use; C2D_NCCL_LIB overrides the path).
  * c2d_gpu_comm_unique_id writes the 128-byte ncclUniqueId that rank 0 hands to the other ranks (by any out-of-band
  * channel: torch.distributed, MPI, a file); c2d_gpu_comm_init is collective over the group and implies

@@ -342,6 +342,7 @@ class Registry
         check(c2d_gpu_comm_set_result_mode(mCtx, C2D_RESULTS_LOCAL));
         check(c2d_gpu_comm_destroy(mCtx));
         check(c2d_gpu_set_shard(mCtx, 0, 1));
+        check(c2d_gpu_set_ray_sharding(mCtx, 0));
         mGroupWorld = 1;
         mGroupMoveExchange = false;
     }
@@ -364,6 +365,9 @@ class Registry
         check(c2d_gpu_comm_set_move_exchange(mCtx, on ? 1 : 0));
         mGroupMoveExchange = on;
     }
+    // Ray sharding: every rank calls rayCastBatch with the SAME batch; this rank casts its contiguous share of it and
+    // returns empty hit lists for the other rays (the per-ray lists of the ranks concatenate to the full result).
+    void setGroupRaySharding(bool on) { check(c2d_gpu_set_ray_sharding(mCtx, on ? 1 : 0)); }
     c2d_gpu_comm_stats lastGroupStats() const
     {
         c2d_gpu_comm_stats st{};

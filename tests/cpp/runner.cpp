@@ -165,6 +165,7 @@ struct IRegistry
     virtual void groupJoin(uint32_t rank, uint32_t world, const unsigned char* id128) = 0;
     virtual void groupOptions(int results, int exchange) = 0;
     virtual void groupLeave() = 0;
+    virtual void groupRaySharding(bool on) = 0;
     virtual void stats(double* out16) const = 0;
     virtual int stage(uint32_t n, const uint32_t* ids, const float* dxy) = 0;
     virtual void applyStaged(int handle) = 0;
@@ -324,6 +325,10 @@ struct RegistryHolder final : IRegistry
     void groupLeave() override
     {
         reg.leaveGroup();
+    }
+    void groupRaySharding(bool on) override
+    {
+        reg.setGroupRaySharding(on);
     }
     uint64_t pairsView(double* seconds, const void** records) override
     {
@@ -503,6 +508,10 @@ struct RegistryHolder final : IRegistry
         throw std::runtime_error("multi-GPU groups are an extension of the B200 build");
     }
     void groupLeave() override
+    {
+        throw std::runtime_error("multi-GPU groups are an extension of the B200 build");
+    }
+    void groupRaySharding(bool) override
     {
         throw std::runtime_error("multi-GPU groups are an extension of the B200 build");
     }
@@ -972,6 +981,13 @@ void rn_group_options(rn_ctx* ctx, int results, int exchange)
 {
     RN_TRY(ctx)
     ctx->reg->groupOptions(results, exchange);
+    RN_CATCH(ctx)
+}
+
+void rn_group_ray_sharding(rn_ctx* ctx, int on)
+{
+    RN_TRY(ctx)
+    ctx->reg->groupRaySharding(on != 0);
     RN_CATCH(ctx)
 }
 

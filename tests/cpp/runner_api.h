@@ -103,6 +103,7 @@ void rn_group_id(rn_ctx*, void* out128);
 void rn_group_join(rn_ctx*, uint32_t rank, uint32_t world, const void* id128);
 void rn_group_options(rn_ctx*, int results, int exchange);
 void rn_group_leave(rn_ctx*);
+void rn_group_ray_sharding(rn_ctx*, int on); /* Registry::setGroupRaySharding */
 
 /* Secondary oracles.  Reference: read from the Registry's private members
  * (mShapes[i].mBoundingBox; the leaf box mTrees[body].getNode(mShapeTreeHandles[i]).mBoundingBox; the five

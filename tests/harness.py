@@ -137,6 +137,7 @@ def load(name: str) -> C.CDLL:
         "rn_group_join": (None, [vp, u32, u32, vp]),
         "rn_group_options": (None, [vp, i32, i32]),
         "rn_group_leave": (None, [vp]),
+        "rn_group_ray_sharding": (None, [vp, i32]),
         "rn_get_collisions": (u64, [vp, u32]),
         "rn_get_collisions_many": (u64, [vp, u32, pu32, pd]),
         "rn_serialize": (u64, [vp]),
@@ -159,7 +160,7 @@ def load(name: str) -> C.CDLL:
         "rn_polygon_normals": (None, [u32, pf, pu8, pf]),
     }
     optional = {"rn_serialize", "rn_copy_blob", "rn_deserialize", "rn_seed_entities", "rn_equals", "rn_group_id",
-                "rn_group_join", "rn_group_options", "rn_group_leave"}  # not in the C oracle
+                "rn_group_join", "rn_group_options", "rn_group_leave", "rn_group_ray_sharding"}  # not in the C oracle
     for fn, (res, args) in sig.items():
         if fn in optional and not hasattr(lib, fn):
             continue
@@ -306,6 +307,10 @@ class Backend:
 
     def group_options(self, results: int = 0, exchange: bool = False):
         self.lib.rn_group_options(self.ctx, results, 1 if exchange else 0)
+        self._check()
+
+    def group_ray_sharding(self, on: bool):
+        self.lib.rn_group_ray_sharding(self.ctx, 1 if on else 0)
         self._check()
 
     def group_leave(self):

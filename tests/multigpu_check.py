@@ -100,6 +100,28 @@ def main():
             want = [mine.tobytes() if rank != 0 else ref.get_transforms(probe).tobytes()]
             dist.broadcast_object_list(want, src=0)
             assert mine.tobytes() == want[0], "host transforms differ from the reference after a move exchange"
+    # batched rayCast with ray sharding: every rank is handed the same batch and casts its contiguous share; the per-ray
+    # lists of the ranks concatenate to the reference's rayCast results
+    ray4, inf = scenes.rays(1200, 1700.0 * (n_dyn / 120000.0) ** 0.5, seed=31, finite_len=60.0)
+    b.group_ray_sharding(True)
+    off, hits = b.raycast(ray4, inf)
+    counts = (off[1:] - off[:-1]).astype(np.int64)
+    lo, hi = (len(ray4) * rank) // world, (len(ray4) * (rank + 1)) // world
+    assert counts[:lo].sum() == 0 and counts[hi:].sum() == 0 and counts[lo:hi].sum() == len(hits) > 0
+    all_counts, all_hits = [None] * world, [None] * world
+    dist.all_gather_object(all_counts, counts[lo:hi].tobytes())
+    dist.all_gather_object(all_hits, hits.tobytes())
+    if rank == 0:
+        got_counts = np.concatenate([np.frombuffer(c, np.int64) for c in all_counts])
+        got_hits = np.concatenate([np.frombuffer(h, hits.dtype) for h in all_hits])
+        roff, rhits = ref.raycast(ray4, inf)
+        got_off = np.concatenate([[0], np.cumsum(got_counts)])
+        same = sum(1 for i in range(len(ray4)) if rhits[int(roff[i]):int(roff[i + 1])].tobytes() ==
+                   got_hits[int(got_off[i]):int(got_off[i + 1])].tobytes())
+        assert same >= len(ray4) - 4, f"only {same} of {len(ray4)} rays agree with the {which}"  # exact (entry, exit) ties (D10)
+        totals["rays_equal"] = same
+        totals["ray_hits"] = int(len(rhits))
+    b.group_ray_sharding(False)
     b.group_leave()
     # out of the group the registry is a plain single-GPU registry again
     single = b.get_colliding_pairs()

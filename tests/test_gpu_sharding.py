@@ -117,3 +117,33 @@ def test_weak_spatial_slabs_with_ghosts(world):
         assert len(np.unique(got)) == len(got), "a pair was reported by two ranks"
         assert np.array_equal(want, got)
         assert len(want) > 5000
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_ray_sharding(world):
+    """c2d_gpu_set_ray_sharding: every rank is handed the same batch and casts its contiguous share; the other rays come
+    back empty, and the per-ray lists of the ranks concatenate to the single-registry result (both tiers: a batch small
+    enough for the latency path when unsharded, and a throughput batch)."""
+    sc = _scene()
+    full = H.Backend(SUBJECT)
+    scenes.populate(full, sc)
+    ranks = []
+    for r in range(world):
+        b = H.Backend(SUBJECT)
+        scenes.populate(b, sc)
+        capi.set_shard(b.native_context(), r, world)
+        capi.set_ray_sharding(b.native_context(), True)
+        ranks.append(b)
+    for n in (40, 3000):
+        ray4, inf = scenes.rays(n, 800.0, seed=3 + n, finite_len=70.0)
+        woff, whits = full.raycast(ray4, inf)
+        parts = []
+        for r, b in enumerate(ranks):
+            off, hits = b.raycast(ray4, inf)
+            counts = (off[1:] - off[:-1]).astype(np.int64)
+            lo, hi = (n * r) // world, (n * (r + 1)) // world
+            assert counts[:lo].sum() == 0 and counts[hi:].sum() == 0 and int(off[-1]) == len(hits)
+            parts.append((counts, hits))
+        counts = sum(c for c, _ in parts)
+        assert (counts == (woff[1:] - woff[:-1]).astype(np.int64)).all()
+        assert np.concatenate([h for _, h in parts]).tobytes() == whits.tobytes()
