@@ -272,39 +272,58 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     def frame_moves():
         return scenes.jitter(rng, n_dyn, 0.5)
 
-    handles = [b.stage_translations(dyn, frame_moves()) for _ in range(W + K)]
+    # Warm-up with per-kernel CUDA events on ALL kernels: the full kernel table, and which kernel dominates.  The events
+    # cost ~0.12 ms per frame (one pair per launch, measured: --probe-profiling-cost), so in the TIMED region only the
+    # dominant kernel keeps its event pair (free) - its average launch duration there is what the roofline divides by.
+    handles = [b.stage_translations(dyn, frame_moves()) for _ in range(2 * W + K)]
+    all_handles = handles
     for h in handles[:W]:
         b.apply_staged(h)
         b.count_pairs_device()
     capi.set_profiling(ctx, True)
     capi.kernel_profile(ctx, reset=True)
+    for h in handles[W:2 * W]:
+        b.apply_staged(h)
+        b.count_pairs_device()
+    warm_profile = capi.kernel_profile(ctx, reset=True)
+    warm_frames = W
+    dom_name = max(warm_profile.items(), key=lambda kv: kv[1][1])[0]
+    plain_ms = None
+    if args.probe_profiling_cost:
+        extra = [b.stage_translations(dyn, frame_moves()) for _ in range(K)]
+        barrier()
+        tp = time.perf_counter()
+        b.run_staged_frames(extra)  # all kernels timed
+        barrier()
+        plain_ms = 1e3 * allmax(time.perf_counter() - tp) / K
+        capi.kernel_profile(ctx, reset=True)
+        for h in extra:
+            b.release_staged(h)
+    capi.set_profile_filter(ctx, dom_name)
+    handles = handles[W:]  # the timed loop below skips its first W again
     sampler = ClockSampler(local) if rank == 0 else None
-    launches = 0
-    pairs_total = 0
     stage_ms = dict(ms_refit=0.0, ms_build=0.0, ms_broad=0.0, ms_narrow=0.0, ms_device=0.0)
-    cand_total = 0
     slab = dict(slab_owned=0.0, slab_leaves=0.0, ms_slab=0.0)
     barrier()
     t0 = time.perf_counter()
-    for h in handles[W:]:
-        b.apply_staged(h)
-        n, _ = b.count_pairs_device()
-        st = b.stats()
-        pairs_total += n
-        cand_total += st["candidates"]
-        launches += int(st["kernel_launches"])
-        for k in stage_ms:
-            stage_ms[k] += st[k]
-        if world > 1:
-            cs = capi.comm_stats(ctx)
-            for k in slab:
-                slab[k] += cs[k]
+    # the K timed frames run in one native loop (tests/cpp/runner.cpp rn_run_staged_frames): Registry::applyStagedMoves +
+    # Registry::countCollidingPairsOnDevice per frame, no Python in between
+    pairs_total, sums, _ = b.run_staged_frames(handles[W:])
+    cand_total = sums["candidates"]
+    launches = int(sums["kernel_launches"])
+    for k in stage_ms:
+        stage_ms[k] = sums[k]
+    if world > 1:
+        cs = capi.comm_stats(ctx)  # of the last frame
+        for k in slab:
+            slab[k] = cs[k] * K
     barrier()
     elapsed = allmax(time.perf_counter() - t0)
     clocks = sampler.stop() if sampler else None
-    profile = capi.kernel_profile(ctx, reset=True)
+    profile = capi.kernel_profile(ctx, reset=True)  # the dominant kernel only, over the timed region
+    capi.set_profile_filter(ctx, None)
     capi.set_profiling(ctx, False)
-    for h in handles:
+    for h in all_handles:
         b.release_staged(h)
     pairs_all = allsum(float(pairs_total))
     cand_all = allsum(float(cand_total))
@@ -381,7 +400,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
 
     # ---- roofline of the dominant kernel (live CUDA-event times) ----------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    dom_name, (dom_count, dom_ms) = max(profile.items(), key=lambda kv: kv[1][1])
+    dom_count, dom_ms = profile[dom_name]
     n_shapes = n_dyn + n_sta
     cand_per_frame = cand_all / K / world        # per rank
     pairs_per_frame = pairs_all / K              # whole job
@@ -416,9 +435,10 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     dom_avg_ms = dom_ms / max(dom_count, 1)
     dom_bytes = float(alg.get(dom_name, 0.0))
     achieved = dom_bytes / (dom_avg_ms * 1e-3) / 1e9 if dom_avg_ms > 0 else 0.0
-    kernels = {k: {"launches": c, "avg_ms": ms / max(c, 1), "share": ms / max(sum(v[1] for v in profile.values()), 1e-9),
+    kernels = {k: {"launches_per_frame": c / warm_frames, "avg_ms": ms / max(c, 1),
+                   "share": ms / max(sum(v[1] for v in warm_profile.values()), 1e-9),
                    "alg_gbs": (alg.get(k, 0.0) / (ms / max(c, 1) * 1e-3) / 1e9) if ms > 0 else 0.0}
-               for k, (c, ms) in sorted(profile.items(), key=lambda kv: -kv[1][1])}
+               for k, (c, ms) in sorted(warm_profile.items(), key=lambda kv: -kv[1][1])}
     # DRAM traffic per launch of the dominant kernel from the newest committed `ncu --set full` capture (profiles/)
     traffic, traffic_src = None, None
     tpaths = sorted(p for p in os.listdir(os.path.join(REPO, "profiles")) if p.endswith("_ncu_traffic.json"))
@@ -437,6 +457,9 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
                 "frame": {"alg_bytes": frame_alg, "achieved": frame_alg / (ms_per_step * 1e-3) / 1e9,
                           "frac": frame_alg / (ms_per_step * 1e-3) / 1e9 / peak},
                 "note": "latency/divergence-bound path (SURVEY.md 8(d)): whole-frame algorithmic traffic is ~0.2-0.3 GB",
+                "timing": f"CUDA events around every launch of {dom_name} inside the timed region ({dom_count} launches); the table "
+                          f"`kernels` comes from {warm_frames} warm-up frames with events around every kernel (kept out of the timed "
+                          f"region: one event pair per launch costs ~0.12 ms per frame)",
                 "kernels": kernels}
 
     if world == 1:
@@ -478,7 +501,8 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
                    "lbvh_rebuild_period": args.rebuild_period,
                    "broadphase": f"uniform grid, cell {args.grid_cell}" if args.grid_cell > 0 else "LBVH",
                    "pairs_per_frame": pairs_per_frame, "candidates_per_frame": cand_per_frame * world,
-                   "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()}},
+                   "stage_ms_per_step": {k: v / K for k, v in stage_ms.items()},
+                   "ms_per_step_with_events_on_every_kernel": plain_ms},
         "e2e": e2e_out,
         "parity": parity,
         "gpu_launches": launches,
@@ -691,6 +715,8 @@ def main():
     ap.add_argument("--workload", default="cfg3-clustered", choices=sorted(WORKLOADS) + ["cfg5-rays"])
     ap.add_argument("--rays", type=int, default=1_000_000, help="cfg5-rays: rays per batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--probe-profiling-cost", action="store_true",
+                    help="also time K frames with CUDA events around EVERY kernel (config.ms_per_step_with_events_on_every_kernel)")
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="multi-GPU mode: strong (default) = the metric's fixed workload on N GPUs; weak = an N-times larger "
                          "world at the same density.  Either way the library cuts the Dynamic tree into Morton-key slabs")

@@ -307,6 +307,7 @@ struct c2d_gpu_ctx
 
     // optional per-kernel timing
     bool profiling = false;
+    std::string profileOnly; // non-empty: only the spans of this name are timed (c2d_gpu_set_profile_filter)
     std::vector<c2d_host::ProfSpan> spans;
     std::vector<cudaEvent_t> eventPool;
     std::map<std::string, std::pair<double, uint32_t>> kernelTotals;

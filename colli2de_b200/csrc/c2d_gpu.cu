@@ -59,6 +59,8 @@ struct ProfScope
     {
         if (!ctx->profiling)
             return;
+        if (!ctx->profileOnly.empty() && ctx->profileOnly != name)
+            return;
         cudaEvent_t a = nullptr;
         if (ctx->eventPool.size() >= 2)
         {
@@ -1096,6 +1098,12 @@ int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size)
 int c2d_gpu_set_profiling(c2d_gpu_ctx* ctx, int on)
 {
     ctx->profiling = on != 0;
+    return 0;
+}
+
+int c2d_gpu_set_profile_filter(c2d_gpu_ctx* ctx, const char* kernel_name)
+{
+    ctx->profileOnly = kernel_name ? kernel_name : "";
     return 0;
 }
 

@@ -16,7 +16,8 @@ for k in names:
     row = f"{k:40s}"
     for _, r in runs:
         e = r["roofline"]["kernels"].get(k)
-        row += f"{(e['avg_ms'] * e['launches'] / r['steps']) if e else float('nan'):30.4f}"
+        per_frame = e.get("launches_per_frame", e.get("launches", 0) / r["steps"]) if e else 0.0
+        row += f"{(e['avg_ms'] * per_frame) if e else float('nan'):30.4f}"
     print(row)
 print(f"{'ms_per_step (device-resident)':40s}" + "".join(f"{r['ms_per_step']:30.4f}" for _, r in runs))
 print(f"{'e2e ms_per_step':40s}" + "".join(f"{r['e2e']['ms_per_step']:30.4f}" for _, r in runs))

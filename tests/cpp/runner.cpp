@@ -1055,6 +1055,32 @@ void rn_apply_staged(rn_ctx* ctx, int handle)
     RN_CATCH(ctx)
 }
 
+// K frames of "apply a staged move batch, count the colliding pairs on the device" without leaving native code (the
+// device-resident arm of bench.py: a Python call per frame costs tens of microseconds, a visible share of a 0.5-1 ms
+// frame).  sums16 accumulates rn_query_stats over the frames; returns the summed pair counts.
+uint64_t rn_run_staged_frames(rn_ctx* ctx, uint32_t frames, const int* handles, double* sums16, double* seconds)
+{
+    RN_TRY(ctx)
+    uint64_t pairs = 0;
+    double one[16];
+    for (int k = 0; k < 16; ++k)
+        sums16[k] = 0.0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t f = 0; f < frames; ++f)
+    {
+        ctx->reg->applyStaged(handles[f]);
+        pairs += ctx->reg->countPairsDevice(nullptr);
+        ctx->reg->stats(one);
+        for (int k = 0; k < 16; ++k)
+            sums16[k] += one[k];
+    }
+    if (seconds)
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return pairs;
+    RN_CATCH(ctx)
+    return 0;
+}
+
 void rn_release_staged(rn_ctx* ctx, int handle)
 {
     RN_TRY(ctx)

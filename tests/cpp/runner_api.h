@@ -72,6 +72,9 @@ void rn_query_stats(rn_ctx*, double* out16);
 int rn_stage_translations(rn_ctx*, uint32_t n, const uint32_t* ids, const float* dxy);
 void rn_apply_staged(rn_ctx*, int handle);
 void rn_release_staged(rn_ctx*, int handle);
+/* `frames` x (rn_apply_staged(handles[f]); rn_count_colliding_pairs_device) in native code; sums16 = the frames' rn_query_stats
+ * summed; returns the summed pair counts (not in the C oracle) */
+uint64_t rn_run_staged_frames(rn_ctx*, uint32_t frames, const int* handles, double* sums16, double* seconds);
 
 /* getCollisions(id): keeps the result like rn_get_colliding_pairs; returns the count (copy with rn_copy_pairs). */
 uint64_t rn_get_collisions(rn_ctx*, uint32_t id);

@@ -150,6 +150,7 @@ def load(name: str) -> C.CDLL:
         "rn_stage_translations": (i32, [vp, u32, pu32, pf]),
         "rn_apply_staged": (None, [vp, i32]),
         "rn_release_staged": (None, [vp, i32]),
+        "rn_run_staged_frames": (u64, [vp, u32, C.POINTER(C.c_int), pd, pd]),
         "rn_raycast": (u64, [vp, u32, pf, pu8, pu64, pu64, pd]),
         "rn_copy_hits": (None, [vp, vp]),
         "rn_collide": (None, [u32, pu8, pf, pu8, pf, pu8, pf, pu8, pf, vp, pu8]),
@@ -160,7 +161,7 @@ def load(name: str) -> C.CDLL:
         "rn_polygon_normals": (None, [u32, pf, pu8, pf]),
     }
     optional = {"rn_serialize", "rn_copy_blob", "rn_deserialize", "rn_seed_entities", "rn_equals", "rn_group_id",
-                "rn_group_join", "rn_group_options", "rn_group_leave", "rn_group_ray_sharding"}  # not in the C oracle
+                "rn_group_join", "rn_group_options", "rn_group_leave", "rn_group_ray_sharding", "rn_run_staged_frames"}  # not in the C oracle
     for fn, (res, args) in sig.items():
         if fn in optional and not hasattr(lib, fn):
             continue
@@ -409,6 +410,15 @@ class Backend:
         out = np.zeros(16, np.float64)
         self.lib.rn_query_stats(self.ctx, _p(out, C.c_double))
         return dict(zip(self.STAT_FIELDS, out.tolist()))
+
+    def run_staged_frames(self, handles):
+        """apply_staged(h) + count_pairs_device() for every handle in native code: (summed pairs, summed stats, seconds)"""
+        hs = (C.c_int * len(handles))(*handles)
+        sums = np.zeros(16, np.float64)
+        sec = C.c_double(0.0)
+        pairs = int(self.lib.rn_run_staged_frames(self.ctx, len(handles), hs, _p(sums, C.c_double), C.byref(sec)))
+        self._check()
+        return pairs, dict(zip(self.STAT_FIELDS, sums.tolist())), sec.value
 
     def stage_translations(self, ids, dxy) -> int:
         ids, dxy = _u32(ids), _f32(dxy)
