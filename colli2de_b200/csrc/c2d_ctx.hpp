@@ -255,6 +255,14 @@ struct c2d_gpu_ctx
     cudaEvent_t transUploadedEv = nullptr; // copy stream: the last early chunk
     size_t transUploaded = 0;            // records of the current transLog already enqueued into dTransLog
     bool earlyUpload = true;
+    // Side stream of a frame: independent kernels of the pipeline run next to each other (the Dynamic x Static traversal
+    // next to the Dynamic tree's bottom-up fit, the two filter kernels, the two manifold kernels) - each of them is latency
+    // bound and leaves most of the SMs idle
+    cudaStream_t sideStream = nullptr;
+    cudaEvent_t evPreFit = nullptr;   // main: the Dynamic order / links of this frame are ready, its fit not yet launched
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    bool preFitRecorded = false;      // evPreFit belongs to this frame
+    bool overlap = true;              // c2d_gpu_set_overlap
     uint32_t transBodies = 0;            // bodies (bit per BodyType) touched by the translations logged since the last flush
     std::vector<Round> rounds;
     DevBuf<FlagRec> dFlagLog;

@@ -54,8 +54,9 @@ namespace
 struct ProfScope
 {
     c2d_gpu_ctx* ctx;
+    cudaStream_t stream;
     cudaEvent_t stop = nullptr;
-    ProfScope(c2d_gpu_ctx* c, const char* name) : ctx(c)
+    ProfScope(c2d_gpu_ctx* c, const char* name, cudaStream_t st = nullptr) : ctx(c), stream(st ? st : c->stream)
     {
         if (!ctx->profiling)
             return;
@@ -74,19 +75,25 @@ struct ProfScope
             cudaEventCreate(&a);
             cudaEventCreate(&stop);
         }
-        cudaEventRecord(a, ctx->stream);
+        cudaEventRecord(a, stream);
         ctx->spans.push_back(ProfSpan{name, a, stop});
     }
     ~ProfScope()
     {
         if (stop)
-            cudaEventRecord(stop, ctx->stream);
+            cudaEventRecord(stop, stream);
     }
 };
 #define C2D_TIMED(ctx, name, ...)                                                                                      \
     do                                                                                                                 \
     {                                                                                                                  \
         ProfScope _ps(ctx, name);                                                                                      \
+        __VA_ARGS__;                                                                                                   \
+    } while (0)
+#define C2D_TIMED_ON(ctx, stream, name, ...)                                                                           \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        ProfScope _ps(ctx, name, stream);                                                                              \
         __VA_ARGS__;                                                                                                   \
     } while (0)
 
@@ -474,6 +481,11 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
     if (topologyValid)
     {
         ++t.age;
+        if (body == C2D_DYNAMIC)
+        {
+            C2D_CUDA(ctx, cudaEventRecord(ctx->evPreFit, s));
+            ctx->preFitRecorded = true;
+        }
         C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
         C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
                                                  t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
@@ -507,6 +519,11 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
         C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
         C2D_TIMED(ctx, "k_karras_build", k_karras_build<<<blocks_for(n - 1, 256), 256, 0, s>>>(t.keys.ptr, t.vals.ptr, static_cast<int>(n), t.nodes.ptr,
                                                              t.nodeParent.ptr, t.leafParent.ptr));
+        if (body == C2D_DYNAMIC)
+        {
+            C2D_CUDA(ctx, cudaEventRecord(ctx->evPreFit, s));
+            ctx->preFitRecorded = true;
+        }
         C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
                                                  t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
         ctx->launches += 2;
@@ -589,6 +606,8 @@ int update_slab(c2d_gpu_ctx* ctx)
     else
         ++sl.age;
     const uint32_t m = sl.owned;
+    C2D_CUDA(ctx, cudaEventRecord(ctx->evPreFit, s));
+    ctx->preFitRecorded = true;
     if (m > 1)
     {
         C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, m * sizeof(uint32_t), s));
@@ -663,37 +682,40 @@ namespace
 // Traversal of the query leaves [lo, hi) of tree `q` against tree `t`.  rejectLeaf: leaf links carrying any of these
 // bits are skipped (halo leaves of a slab tree, see c2d_comm.cu).
 template <bool SELF>
-void launch_traverse_trees(c2d_gpu_ctx* ctx, const TreeBuf& q, const TreeBuf& t, uint32_t lo, uint32_t hi, uint32_t rejectLeaf)
+void launch_traverse_trees(c2d_gpu_ctx* ctx, const TreeBuf& q, const TreeBuf& t, uint32_t lo, uint32_t hi, uint32_t rejectLeaf,
+                           cudaStream_t st = nullptr)
 {
     if (q.n == 0 || t.n == 0 || (SELF && q.n < 2) || hi <= lo)
         return;
+    if (!st)
+        st = ctx->stream;
     uint32_t* overflow = &ctx->dScratch->stackOverflow;
     // few queries (bullets, whose swept leaves overlap hundreds of boxes): one WARP per query leaf
     if (static_cast<uint64_t>(hi - lo) * 32 <= 148ull * 2048 * 4)
-        C2D_TIMED(ctx, SELF ? "k_traverse_warp<self>" : "k_traverse_warp<cross>",
-                  k_traverse_warp<SELF><<<blocks_for(static_cast<size_t>(hi - lo) * 32, 128), 128, 0, ctx->stream>>>(
+        C2D_TIMED_ON(ctx, st, SELF ? "k_traverse_warp<self>" : "k_traverse_warp<cross>",
+                  k_traverse_warp<SELF><<<blocks_for(static_cast<size_t>(hi - lo) * 32, 128), 128, 0, st>>>(
                       q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, rejectLeaf,
                       ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
     else if (ctx->traverseVariant == 0 || t.n < 2)
-        C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+        C2D_TIMED_ON(ctx, st, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse<SELF><<<blocks_for(hi - lo, 128), 128, 0, st>>>(
         q.vals.ptr, q.n, lo, hi, t.vals.ptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, ctx->cand.ptr,
         static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
     else
-        C2D_TIMED(ctx, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse_sync<SELF><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
+        C2D_TIMED_ON(ctx, st, SELF ? "k_traverse<self>" : "k_traverse<cross>", k_traverse_sync<SELF><<<blocks_for(hi - lo, 128), 128, 0, st>>>(
         q.vals.ptr, q.n, lo, hi, nullptr, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category, rejectLeaf, ctx->cand.ptr,
         static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, overflow));
     ++ctx->launches;
 }
 
 template <bool SELF>
-void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody)
+void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody, cudaStream_t st = nullptr)
 {
     const TreeBuf& q = ctx->tree[qBody];
     const TreeBuf& t = ctx->tree[tBody];
     // multi-GPU: this context owns the query leaves of Morton-rank slab [lo, hi)
     const uint32_t lo = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * ctx->shardRank / ctx->shardWorld);
     const uint32_t hi = static_cast<uint32_t>(static_cast<uint64_t>(q.n) * (ctx->shardRank + 1) / ctx->shardWorld);
-    launch_traverse_trees<SELF>(ctx, q, t, lo, hi, 0u);
+    launch_traverse_trees<SELF>(ctx, q, t, lo, hi, 0u, st);
 }
 
 void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats);
@@ -710,7 +732,7 @@ inline uint64_t result_count(const c2d_gpu_ctx* ctx)
 
 // One attempt at traversal + narrowphase with the current pair-list capacities; everything is enqueued on the
 // stream, the frame counters follow in an asynchronous copy to the pinned FrameScratch.
-int pipeline_attempt(c2d_gpu_ctx* ctx)
+int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
 {
     cudaStream_t s = ctx->stream;
     if (ctx->frame.smallScene)
@@ -739,14 +761,27 @@ int pipeline_attempt(c2d_gpu_ctx* ctx)
     }
     else
     {
-        // groups in the reference's order (Registry.hpp:487-545)
+        // The five groups of the reference (Registry.hpp:487-545).  Dynamic x Static needs the Static tree and the Dynamic
+        // ORDER only, not the Dynamic tree's node boxes: it runs on the side stream next to that tree's bottom-up fit
+        // (k_fit) and to the Dynamic x Dynamic traversal - all three are latency bound.
+        cudaStream_t side = ctx->overlap ? ctx->sideStream : s;
+        if (side != s)
+        {
+            if (ctx->preFitRecorded && !retry)
+                C2D_CUDA(ctx, cudaStreamWaitEvent(side, ctx->evPreFit, 0));
+            else
+            {
+                C2D_CUDA(ctx, cudaEventRecord(ctx->evFork, s));
+                C2D_CUDA(ctx, cudaStreamWaitEvent(side, ctx->evFork, 0));
+            }
+        }
         if (ctx->slabInUse)
         {
             // multi-GPU slab: the rank's tree holds its owned Dynamic leaves; the halo shapes (higher ranks) query it;
             // every bullet meets the owned Dynamic leaves of each rank exactly once
             const TreeBuf& slab = ctx->slabTree;
             const TreeBuf& bullets = ctx->tree[C2D_BULLET];
-            launch_traverse_trees<false>(ctx, slab, ctx->tree[C2D_STATIC], 0, slab.n, 0u);
+            launch_traverse_trees<false>(ctx, slab, ctx->tree[C2D_STATIC], 0, slab.n, 0u, side);
             launch_traverse_trees<true>(ctx, slab, slab, 0, slab.n, 0u);
             launch_traverse_halo(ctx);
             launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
@@ -755,11 +790,16 @@ int pipeline_attempt(c2d_gpu_ctx* ctx)
         }
         else
         {
-            launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC);
+            launch_traverse<false>(ctx, C2D_DYNAMIC, C2D_STATIC, side);
             launch_traverse<true>(ctx, C2D_DYNAMIC, C2D_DYNAMIC);
             launch_traverse<false>(ctx, C2D_BULLET, C2D_STATIC);
             launch_traverse<false>(ctx, C2D_BULLET, C2D_DYNAMIC);
             launch_traverse<true>(ctx, C2D_BULLET, C2D_BULLET);
+        }
+        if (side != s)
+        {
+            C2D_CUDA(ctx, cudaEventRecord(ctx->evJoin, side));
+            C2D_CUDA(ctx, cudaStreamWaitEvent(s, ctx->evJoin, 0));
         }
     }
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
@@ -769,13 +809,40 @@ int pipeline_attempt(c2d_gpu_ctx* ctx)
     C2D_TIMED(ctx, "k_bin_count", k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch));
     C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
     C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
-    C2D_TIMED(ctx, "k_narrow_filter", k_narrow_filter<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+    // the polygon bin (8 lanes per pair) and the other bins are disjoint slices of the binned list with their own hit
+    // counters and output ranges: the two filter kernels, and later the two manifold kernels, run side by side
+    cudaStream_t side = ctx->overlap ? ctx->sideStream : s;
+    const auto fork = [&]() -> int {
+        if (side != s)
+        {
+            C2D_CUDA(ctx, cudaEventRecord(ctx->evFork, s));
+            C2D_CUDA(ctx, cudaStreamWaitEvent(side, ctx->evFork, 0));
+        }
+        return 0;
+    };
+    const auto join = [&]() -> int {
+        if (side != s)
+        {
+            C2D_CUDA(ctx, cudaEventRecord(ctx->evJoin, side));
+            C2D_CUDA(ctx, cudaStreamWaitEvent(s, ctx->evJoin, 0));
+        }
+        return 0;
+    };
+    if (int rc = fork())
+        return rc;
+    C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<<<148 * 16, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
     C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
+    if (int rc = join())
+        return rc;
     C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
+    if (int rc = fork())
+        return rc;
+    C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<<<148 * 16, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                     static_cast<uint32_t>(ctx->out.capacity)));
     C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                      static_cast<uint32_t>(ctx->out.capacity)));
-    C2D_TIMED(ctx, "k_narrow_manifold", k_narrow_manifold<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
-                                     static_cast<uint32_t>(ctx->out.capacity)));
+    if (int rc = join())
+        return rc;
     ctx->launches += 8;
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
     C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
@@ -793,6 +860,7 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
     cudaStream_t s = ctx->stream;
     ctx->launches = 0;
     ctx->h2dBytes = 0;
+    ctx->preFitRecorded = false;
 
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[0], s));
     if (int rc = flush(ctx, true))
@@ -879,7 +947,7 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
             C2D_CUDA(ctx, ctx->out.reserve(static_cast<size_t>(pairCount) + pairCount / 4));
         C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
         ++ctx->launches;
-        if (int rc = pipeline_attempt(ctx))
+        if (int rc = pipeline_attempt(ctx, true))
             return rc;
     }
     ctx->lastCandidates = candCount;
@@ -983,6 +1051,11 @@ int c2d_gpu_create(int device, c2d_gpu_ctx** out_ctx)
     if (e == cudaSuccess)
         e = cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking);
     if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&ctx->sideStream, cudaStreamNonBlocking);
+    for (cudaEvent_t* ev : {&ctx->evPreFit, &ctx->evFork, &ctx->evJoin})
+        if (e == cudaSuccess)
+            e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+    if (e == cudaSuccess)
         e = cudaEventCreateWithFlags(&ctx->transApplied, cudaEventDisableTiming);
     if (e == cudaSuccess)
         e = cudaEventCreateWithFlags(&ctx->transUploadedEv, cudaEventDisableTiming);
@@ -1042,6 +1115,14 @@ void c2d_gpu_destroy(c2d_gpu_ctx* ctx)
         cudaStreamSynchronize(ctx->copyStream);
         cudaStreamDestroy(ctx->copyStream);
     }
+    if (ctx->sideStream)
+    {
+        cudaStreamSynchronize(ctx->sideStream);
+        cudaStreamDestroy(ctx->sideStream);
+    }
+    for (cudaEvent_t ev : {ctx->evPreFit, ctx->evFork, ctx->evJoin})
+        if (ev)
+            cudaEventDestroy(ev);
     if (ctx->transApplied)
         cudaEventDestroy(ctx->transApplied);
     if (ctx->transUploadedEv)
@@ -1152,6 +1233,12 @@ int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world)
     ctx->shardWorld = world;
     ctx->slabDirty = true;
     ctx->slab.valid = false;
+    return 0;
+}
+
+int c2d_gpu_set_overlap(c2d_gpu_ctx* ctx, int on)
+{
+    ctx->overlap = on != 0;
     return 0;
 }
 

@@ -194,6 +194,10 @@ typedef struct c2d_gpu_comm_stats
 } c2d_gpu_comm_stats;
 int c2d_gpu_comm_get_stats(c2d_gpu_ctx* ctx, c2d_gpu_comm_stats* out);
 
+/* Independent kernels of a frame run side by side on a second stream (the Dynamic x Static traversal next to the Dynamic
+ * tree's refit and self traversal, the two filter kernels, the two manifold kernels).  Results are identical; 0 puts
+ * everything back on one stream (for per-kernel timing that should not see the neighbours).  Default on. */
+int c2d_gpu_set_overlap(c2d_gpu_ctx* ctx, int on);
 /* Per-kernel CUDA-event timing of the queries (off by default).  c2d_gpu_kernel_profile writes one line per
  * kernel name, "name<TAB>launches<TAB>total_ms", accumulated since the last reset. */
 int c2d_gpu_set_profiling(c2d_gpu_ctx* ctx, int on);
