@@ -380,6 +380,24 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
         b.group_options(results=capi.RESULTS_ROOT, exchange=True)
         root = e2e_loop(min(K, 8), 1)
         b.group_options(results=capi.RESULTS_LOCAL, exchange=False)
+    # N2: the same frame driven through Registry::moveEntities (one call for the whole batch) instead of one moveEntity
+    # call per entity
+    bulk_move_ms, bulk_call_ms = [], []
+    if world > 1:
+        b.group_options(results=capi.RESULTS_LOCAL, exchange=True)
+    for f in range(1 + min(K, 8)):
+        d = frame_moves()
+        tb = b.move_entities_bulk(dyn[chunk], d[chunk])
+        if world > 1:
+            barrier()
+        sec = C.c_double(0.0)
+        b.lib.rn_get_colliding_pairs(b.ctx, C.byref(sec))
+        b._check()
+        if f >= 1:
+            bulk_move_ms.append(1e3 * tb)
+            bulk_call_ms.append(1e3 * sec.value)
+    if world > 1:
+        b.group_options(results=capi.RESULTS_LOCAL, exchange=False)
     # same loop through the zero-copy extension (a view of the pinned result buffer instead of a fresh std::vector)
     view_times = []
     if world == 1:
@@ -475,6 +493,10 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
                "moves_host_ms": e2e["moves_ms"],
                "whole_frame_ms": e2e["moves_ms"] + 1e3 * e2e_elapsed / K,
                "rank0_stage_ms": e2e["stages"],
+               "bulk_moves": {"call": "Registry::moveEntities(ids, deltas): one call per frame instead of one moveEntity per entity",
+                              "moves_host_ms": float(np.mean(bulk_move_ms)),
+                              "query_ms": float(np.mean(bulk_call_ms)),
+                              "whole_frame_ms": float(np.mean(bulk_move_ms)) + float(np.mean(bulk_call_ms))},
                "call": ("c2d::Registry<uint32_t>::getCollidingPairs() after moveEntity(id, Translation) per entity" if world == 1
                         else "per rank: moveEntity(id, Translation) for the 1/N of the entities it drives, then the collective "
                              "c2d::Registry<uint32_t>::getCollidingPairs() returning the rank's share into host memory; time = "

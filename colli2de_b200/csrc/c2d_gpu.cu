@@ -1356,13 +1356,36 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
 int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shapes, const float* dxy)
 {
     ++ctx->mutationEpoch;
+    if (n == 0)
+        return 0;
+    if (!shapes || !dxy)
+        return fail(ctx, "c2d_gpu_shapes_translate: NULL argument");
     if (ctx->transUploaded && ctx->transLog->size + n > ctx->transLog->capacity)
         cudaStreamSynchronize(ctx->copyStream);
     if (!ctx->transLog->reserve(ctx->transLog->size + n))
         return fail(ctx, "pinned host allocation failed");
+    // the loop of c2d_gpu_shape_translate without its per-record function call, capacity check and upload check
+    const size_t known = ctx->hostMeta.size();
+    uint32_t bodies = 0;
     for (uint32_t i = 0; i < n; ++i)
-        if (int rc = c2d_gpu_shape_translate(ctx, shapes[i], dxy[2 * i], dxy[2 * i + 1]))
-            return rc;
+    {
+        const uint32_t shape = shapes[i];
+        if (shape >= known || !(ctx->hostMeta[shape] & META_ALIVE))
+            return fail(ctx, "c2d_gpu_shapes_translate: unknown shape");
+        claim(ctx, shape, PH_TRANS);
+        TransRec* r = &ctx->transLog->data[ctx->transLog->size++];
+        r->shape = shape;
+        r->dx = dxy[2 * i];
+        r->dy = dxy[2 * i + 1];
+        bodies |= 1u << meta_body(ctx->hostMeta[shape]);
+        if ((i & 0xfffu) == 0xfffu && ctx->earlyUpload && ctx->transLog->size - ctx->transUploaded >= kEarlyUploadRecords)
+            if (int rc = early_upload_translations(ctx))
+                return rc;
+    }
+    ctx->transBodies |= bodies;
+    for (uint32_t b = 0; b < 3; ++b)
+        if (bodies & (1u << b))
+            mark_dirty(ctx, b);
     return 0;
 }
 

@@ -132,6 +132,21 @@ class IndexMap
         }
     }
 
+    // bulk lookups (Registry::moveEntities): the slot of a key a few iterations ahead is fetched early, then peeked to
+    // fetch the entity record it names - a lookup in a table of a million entities is two dependent cache misses otherwise
+    void prefetch(const EntityId& id) const
+    {
+        if (!mSlots.empty())
+            __builtin_prefetch(&mSlots[home(id)]);
+    }
+    uint32_t peek(const EntityId& id) const // the home slot's entry (npos if empty / tombstone): a hint, not a lookup
+    {
+        if (mSlots.empty())
+            return npos;
+        const uint32_t slot = mSlots[home(id)];
+        return slot >= 2 ? slot - 2 : npos;
+    }
+
     // precondition: !needsRehash()
     void insert(const EntityId& id, uint32_t index)
     {
@@ -274,6 +289,10 @@ class Registry
     // ---- extensions (not in the reference) ------------------------------------------------------------
     // moveEntity(ids[i], deltas[i]) for every i, in order.
     void moveEntities(std::span<const EntityId> ids, std::span<const Translation> deltas);
+    // teleportEntity(ids[i], positions[i]) / teleportEntity(ids[i], transforms[i]) for every i, in order.  An entity may
+    // appear once per call (the translation variant resolves all deltas against the transforms at entry).
+    void teleportEntities(std::span<const EntityId> ids, std::span<const Translation> positions);
+    void teleportEntities(std::span<const EntityId> ids, std::span<const Transform> transforms);
     // getCollisions(id) for many entities in ONE device pass (a single call costs a ~30 us round trip whatever the
     // scene size): the concatenated results; entityA of a record names the queried entity.
     std::vector<EntityCollision> getCollisions(std::span<const EntityId> ids) const;
@@ -608,6 +627,9 @@ class Registry
     std::vector<ShapeId> mFreeShapeIds;
     mutable c2d_gpu_stats mStats{};
     std::vector<EntityCollision> mViewStorage;
+    std::vector<uint32_t> mBulkShapes; // scratch of moveEntities / teleportEntities
+    std::vector<float> mBulkDeltas;
+    std::vector<Translation> mBulkTargets;
     uint32_t mPreviousAllCollisionsCount = 1024; // reference Registry.hpp:168
     // memoised getCollisions(id) results, valid while the library's mutation epoch does not change
     static constexpr uint32_t kCollisionCacheWarmup = 4;
@@ -803,12 +825,74 @@ void Registry<EntityId, Method>::moveEntity(EntityId id, Translation d)
     entity.transform.translation += d;
 }
 
+// moveEntity(ids[i], deltas[i]) for every i, in order (reference Registry.hpp:434-453), as ONE pass: the index lookups
+// are software-pipelined (a million scattered lookups are cache-miss bound) and the per-shape records reach the library
+// in one c2d_gpu_shapes_translate call instead of one C-ABI call per shape.
 template <typename EntityId, PartitioningMethod Method>
 void Registry<EntityId, Method>::moveEntities(std::span<const EntityId> ids, std::span<const Translation> deltas)
 {
     C2D_DEBUG_ASSERT(ids.size() == deltas.size());
+    if (!mPendingApplies.empty())
+        syncHost();
+    const size_t n = ids.size();
+    mBulkShapes.clear();
+    mBulkDeltas.clear();
+    mBulkShapes.reserve(n);
+    mBulkDeltas.reserve(2 * n);
+    constexpr size_t kAhead = 16;
+    for (size_t i = 0; i < n; ++i)
+    {
+        if (i + 2 * kAhead < n)
+            mIndex.prefetch(ids[i + 2 * kAhead]);
+        if (i + kAhead < n)
+        {
+            const uint32_t hint = mIndex.peek(ids[i + kAhead]);
+            if (hint < mEntities.size())
+                __builtin_prefetch(&mEntities[hint]);
+        }
+        const uint32_t idx = indexOf(ids[i]);
+        C2D_DEBUG_ASSERT(idx != kNone, "Entity with this ID does not exist");
+        EntityInfo& entity = mEntities[idx];
+        const Translation d = deltas[i];
+        for (uint32_t s = entity.firstShape; s != kNone; s = mShapes[s].next)
+        {
+            mBulkShapes.push_back(s);
+            mBulkDeltas.push_back(d.x);
+            mBulkDeltas.push_back(d.y);
+        }
+        if (entity.type == BodyType::Bullet)
+            entity.previous = entity.transform;
+        entity.transform.translation += d;
+    }
+    check(c2d_gpu_shapes_translate(mCtx, static_cast<uint32_t>(mBulkShapes.size()), mBulkShapes.data(), mBulkDeltas.data()));
+}
+
+// teleportEntity(ids[i], positions[i]) for every i (reference Registry.hpp:403-411: a move by position - current).
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::teleportEntities(std::span<const EntityId> ids, std::span<const Translation> positions)
+{
+    C2D_DEBUG_ASSERT(ids.size() == positions.size());
+    syncHost();
+    mBulkTargets.resize(ids.size());
     for (size_t i = 0; i < ids.size(); ++i)
-        moveEntity(ids[i], deltas[i]);
+        mBulkTargets[i] = positions[i] - entityAt(ids[i]).transform.translation;
+    moveEntities(ids, std::span<const Translation>(mBulkTargets));
+}
+
+// teleportEntity(ids[i], transforms[i]) for every i (reference Registry.hpp:382-401).
+template <typename EntityId, PartitioningMethod Method>
+void Registry<EntityId, Method>::teleportEntities(std::span<const EntityId> ids, std::span<const Transform> transforms)
+{
+    C2D_DEBUG_ASSERT(ids.size() == transforms.size());
+    syncHost();
+    for (size_t i = 0; i < ids.size(); ++i)
+    {
+        EntityInfo& entity = entityAt(ids[i]);
+        if (entity.type == BodyType::Bullet)
+            entity.previous = entity.transform;
+        entity.transform = transforms[i];
+        pushShapeTransforms(entity);
+    }
 }
 
 template <typename EntityId, PartitioningMethod Method>

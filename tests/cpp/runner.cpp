@@ -149,6 +149,8 @@ struct IRegistry
     virtual void teleportEntity(uint32_t id, Translation t) = 0;
     virtual void moveEntity(uint32_t id, const Transform& d) = 0;
     virtual void moveEntity(uint32_t id, Translation d) = 0;
+    virtual void moveEntitiesBulk(uint32_t n, const uint32_t* ids, const float* dxy) = 0;
+    virtual void teleportEntitiesBulk(uint32_t n, const uint32_t* ids, const float* xy) = 0;
     virtual Transform getEntityTransform(uint32_t id) const = 0;
     virtual void getCollidingPairs(std::vector<PairRec>& out, double* seconds) = 0;
     virtual void getCollisions(uint32_t id, std::vector<PairRec>& out) const = 0;
@@ -302,6 +304,15 @@ struct RegistryHolder final : IRegistry
         return firstHitImpl(r, mask, out);
     }
 #if defined(RN_BACKEND_B200)
+    void moveEntitiesBulk(uint32_t n, const uint32_t* ids, const float* dxy) override
+    {
+        static_assert(sizeof(Translation) == 2 * sizeof(float));
+        reg.moveEntities(std::span<const uint32_t>(ids, n), std::span<const Translation>(reinterpret_cast<const Translation*>(dxy), n));
+    }
+    void teleportEntitiesBulk(uint32_t n, const uint32_t* ids, const float* xy) override
+    {
+        reg.teleportEntities(std::span<const uint32_t>(ids, n), std::span<const Translation>(reinterpret_cast<const Translation*>(xy), n));
+    }
     void setGhost(ShapeId s, bool g) override
     {
         reg.setShapeGhost(s, g);
@@ -491,6 +502,16 @@ struct RegistryHolder final : IRegistry
     }
     std::vector<std::pair<std::vector<uint32_t>, std::vector<Translation>>> staged;
     std::vector<typename Reg::EntityCollision> viewStorage;
+    void moveEntitiesBulk(uint32_t n, const uint32_t* ids, const float* dxy) override
+    {
+        for (uint32_t i = 0; i < n; ++i)
+            reg.moveEntity(ids[i], Translation{dxy[2 * i], dxy[2 * i + 1]});
+    }
+    void teleportEntitiesBulk(uint32_t n, const uint32_t* ids, const float* xy) override
+    {
+        for (uint32_t i = 0; i < n; ++i)
+            reg.teleportEntity(ids[i], Translation{xy[2 * i], xy[2 * i + 1]});
+    }
     void setGhost(ShapeId, bool) override
     {
         throw std::runtime_error("ghost shapes are an extension of the B200 build");
@@ -746,6 +767,21 @@ void rn_move_translate(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const float
         ctx->notePrev(ids[i]);
         ctx->reg->moveEntity(ids[i], Translation{dxy[2 * i], dxy[2 * i + 1]});
     }
+    RN_CATCH(ctx)
+}
+
+// Registry::moveEntities / teleportEntities (B200 extension; the reference loops over moveEntity / teleportEntity).  The
+// runner's own bookkeeping of bullets' previous transforms is skipped: seconds = the library's cost of the batch alone.
+void rn_move_entities_bulk(rn_ctx* ctx, uint32_t n, const uint32_t* ids, const float* dxy, int teleport, double* seconds)
+{
+    RN_TRY(ctx)
+    const auto t0 = std::chrono::steady_clock::now();
+    if (teleport)
+        ctx->reg->teleportEntitiesBulk(n, ids, dxy);
+    else
+        ctx->reg->moveEntitiesBulk(n, ids, dxy);
+    if (seconds)
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     RN_CATCH(ctx)
 }
 

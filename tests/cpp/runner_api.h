@@ -47,6 +47,9 @@ void rn_remove_entities(rn_ctx*, uint32_t n, const uint32_t* ids);
 void rn_set_active(rn_ctx*, uint32_t n, const uint32_t* shape_ids, const uint8_t* active);
 void rn_move_translate(rn_ctx*, uint32_t n, const uint32_t* ids, const float* dxy);
 void rn_move_transform(rn_ctx*, uint32_t n, const uint32_t* ids, const float* dxf3);
+/* B200: Registry::moveEntities (teleport = 0) / teleportEntities(positions) (teleport = 1); reference: the loop of single
+ * calls.  Bullets' previous transforms are not tracked by the runner here.  Not in the C oracle. */
+void rn_move_entities_bulk(rn_ctx*, uint32_t n, const uint32_t* ids, const float* dxy, int teleport, double* seconds);
 void rn_teleport_transform(rn_ctx*, uint32_t n, const uint32_t* ids, const float* xf3);
 void rn_teleport_translation(rn_ctx*, uint32_t n, const uint32_t* ids, const float* xy);
 void rn_get_transforms(rn_ctx*, uint32_t n, const uint32_t* ids, float* out_xf5);

@@ -116,6 +116,7 @@ def load(name: str) -> C.CDLL:
         "rn_set_active": (None, [vp, u32, pu32, pu8]),
         "rn_move_translate": (None, [vp, u32, pu32, pf]),
         "rn_move_transform": (None, [vp, u32, pu32, pf]),
+        "rn_move_entities_bulk": (None, [vp, u32, pu32, pf, i32, pd]),
         "rn_teleport_transform": (None, [vp, u32, pu32, pf]),
         "rn_teleport_translation": (None, [vp, u32, pu32, pf]),
         "rn_get_transforms": (None, [vp, u32, pu32, pf]),
@@ -161,7 +162,7 @@ def load(name: str) -> C.CDLL:
         "rn_polygon_normals": (None, [u32, pf, pu8, pf]),
     }
     optional = {"rn_serialize", "rn_copy_blob", "rn_deserialize", "rn_seed_entities", "rn_equals", "rn_group_id",
-                "rn_group_join", "rn_group_options", "rn_group_leave", "rn_group_ray_sharding", "rn_run_staged_frames"}  # not in the C oracle
+                "rn_group_join", "rn_group_options", "rn_group_leave", "rn_group_ray_sharding", "rn_run_staged_frames", "rn_move_entities_bulk"}  # not in the C oracle
     for fn, (res, args) in sig.items():
         if fn in optional and not hasattr(lib, fn):
             continue
@@ -322,6 +323,14 @@ class Backend:
         ids, dxy = _u32(ids), _f32(dxy)
         self.lib.rn_move_translate(self.ctx, len(ids), _p(ids, C.c_uint32), _p(dxy, C.c_float))
         self._check()
+
+    def move_entities_bulk(self, ids, dxy, teleport: bool = False) -> float:
+        """Registry::moveEntities / teleportEntities(positions) in one call (reference: the loop); returns its seconds"""
+        ids, dxy = _u32(ids), _f32(dxy)
+        sec = C.c_double(0.0)
+        self.lib.rn_move_entities_bulk(self.ctx, len(ids), _p(ids, C.c_uint32), _p(dxy, C.c_float), 1 if teleport else 0, C.byref(sec))
+        self._check()
+        return sec.value
 
     def move_transform(self, ids, dxf3):
         ids, d = _u32(ids), _f32(dxf3)

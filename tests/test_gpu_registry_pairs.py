@@ -132,3 +132,31 @@ def test_category_filter_and_same_entity():
         got = [(int(r["entityA"]), int(r["shapeA"]), int(r["entityB"]), int(r["shapeB"])) for r in p]
         # 1&2 = 0 -> no pair between entities 1 and 2; 3 matches both
         assert got == [(1, 0, 3, 3), (1, 1, 3, 3), (2, 2, 3, 3)], (name, got)
+
+
+def test_bulk_move_and_teleport_entities():
+    """Registry::moveEntities / teleportEntities (N2: one call per batch instead of one per entity) against the reference's
+    single calls (Registry.hpp:403-411, 434-453): same pairs, same manifolds, same transforms, bullets' sweeps included;
+    a batch that names an entity twice in a row applies both moves in order."""
+    sc = scenes.mixed_scene(30000, 3000, 900.0, seed=9)
+    sc["ent_body"][::40] = 2
+    ref, gpu, idx = _both(sc)
+    rng = scenes.LCG(16)
+    mov = np.nonzero(sc["ent_body"] != 0)[0].astype(np.uint32)
+    for frame in range(5):
+        if frame % 2 == 0:
+            d = scenes.jitter(rng, len(mov), 0.7)
+            ref.move_translate(mov, d)  # moveEntity(id, Translation) per entity
+            gpu.move_entities_bulk(mov, d)
+        else:
+            target = ref.get_transforms(mov)[:, :2] + scenes.jitter(rng, len(mov), 4.0)
+            ref.teleport_translation(mov, target)
+            gpu.move_entities_bulk(mov, target, teleport=True)
+        if frame == 2:  # the same entities twice in one batch
+            twice = np.concatenate([mov[:500], mov[:500]])
+            d2 = scenes.jitter(rng, len(twice), 0.3)
+            ref.move_translate(twice, d2)
+            gpu.move_entities_bulk(twice, d2)
+        res = _check(ref, gpu, idx, max_ambiguous=8)
+        assert res["expected"] > 5000 and res["not_bit_identical"] == 0, res
+        assert np.array_equal(ref.get_transforms(mov).view(np.uint32), gpu.get_transforms(mov).view(np.uint32))
