@@ -21,7 +21,7 @@ EXPORTS = [
     "c2d_gpu_read_candidates", "c2d_gpu_shape_slots", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
     "c2d_gpu_compute_aabb_batch",
     "c2d_gpu_set_slab_mode", "c2d_gpu_comm_unique_id", "c2d_gpu_comm_init", "c2d_gpu_comm_destroy",
-    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats", "c2d_gpu_read_transforms", "c2d_gpu_set_ray_sharding", "c2d_gpu_set_profile_filter", "c2d_gpu_set_overlap",
+    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats", "c2d_gpu_read_transforms", "c2d_gpu_set_ray_sharding", "c2d_gpu_set_profile_filter", "c2d_gpu_set_overlap", "c2d_gpu_set_result_order",
 ]
 
 _lib = None
@@ -65,6 +65,12 @@ def set_profile_filter(ctx, kernel_name: str | None):
     """with profiling on, time only this kernel's launches (None = all)"""
     lib().c2d_gpu_set_profile_filter.argtypes = [C.c_void_p, C.c_char_p]
     _check(ctx, lib().c2d_gpu_set_profile_filter(ctx, kernel_name.encode() if kernel_name else None))
+
+
+def set_result_order(ctx, reference_order: bool):
+    """records come back in the reference's order (five groups, each sorted by (shapeA, shapeB)), byte-identical run to run"""
+    lib().c2d_gpu_set_result_order.argtypes = [C.c_void_p, C.c_int]
+    _check(ctx, lib().c2d_gpu_set_result_order(ctx, 1 if reference_order else 0))
 
 
 def set_overlap(ctx, on: bool):

@@ -152,6 +152,7 @@ int c2d_host::comm_gather_results(c2d_gpu_ctx* ctx)
     for (uint32_t r = 0; r < world; ++r)
         total += cm.hPairCounts[1 + r];
     const bool receiver = cm.resultMode == C2D_RESULTS_ALL || rank == 0;
+    const PairOut* local = ctx->resultsOrdered ? ctx->order.sorted.ptr : ctx->out.ptr; // this rank's records
     if (receiver)
         C2D_CUDA(ctx, cm.outAll.reserve(total ? total : 1));
     C2D_NCCL(ctx, api.GroupStart());
@@ -163,18 +164,18 @@ int c2d_host::comm_gather_results(c2d_gpu_ctx* ctx)
         if (n)
         {
             if (cm.resultMode == C2D_RESULTS_ALL)
-                C2D_NCCL(ctx, api.Broadcast(ctx->out.ptr, cm.outAll.ptr + offset, bytes, ncclChar, static_cast<int>(r),
+                C2D_NCCL(ctx, api.Broadcast(local, cm.outAll.ptr + offset, bytes, ncclChar, static_cast<int>(r),
                                             comm_of(ctx), s));
             else if (rank == 0 && r != 0)
                 C2D_NCCL(ctx, api.Recv(cm.outAll.ptr + offset, bytes, ncclChar, static_cast<int>(r), comm_of(ctx), s));
             else if (rank == r && r != 0)
-                C2D_NCCL(ctx, api.Send(ctx->out.ptr, bytes, ncclChar, 0, comm_of(ctx), s));
+                C2D_NCCL(ctx, api.Send(local, bytes, ncclChar, 0, comm_of(ctx), s));
         }
         offset += n;
     }
     C2D_NCCL(ctx, api.GroupEnd());
     if (cm.resultMode == C2D_RESULTS_ROOT && rank == 0 && cm.hPairCounts[1])
-        C2D_CUDA(ctx, cudaMemcpyAsync(cm.outAll.ptr, ctx->out.ptr, static_cast<size_t>(cm.hPairCounts[1]) * sizeof(PairOut),
+        C2D_CUDA(ctx, cudaMemcpyAsync(cm.outAll.ptr, local, static_cast<size_t>(cm.hPairCounts[1]) * sizeof(PairOut),
                                       cudaMemcpyDeviceToDevice, s));
     C2D_CUDA(ctx, cudaEventRecord(cm.evX[3], s));
     cm.gatherTimed = true;

@@ -296,6 +296,10 @@ struct c2d_gpu_ctx
     c2d_host::DevBuf<uint4> hits;
     c2d_host::DevBuf<c2d_dev::PairOut> out;
     c2d_host::PinnedVec<c2d_dev::PairOut> hostOut;
+    // small scenes: the narrowphase writes its records straight into this pinned, device-mapped buffer
+    c2d_host::PinnedVec<c2d_dev::PairOut> smallOut;
+    bool resultsOnHost = false; // the last frame's records are in smallOut
+    bool scratchClean = false;  // the device frame counters are zero (left so by the last small frame)
     uint64_t lastCandidates = 0;
     uint64_t lastPairs = 0;
     struct FrameState // one c2d_gpu_collide_begin .. c2d_gpu_collide_end bracket
@@ -309,6 +313,15 @@ struct c2d_gpu_ctx
     std::unique_ptr<c2d_host::CopyPool> copyPool; // created by the first large copy-out
     std::vector<cudaEvent_t> copyEvents;          // one per in-flight chunk of copy_out
     c2d_host::PinnedVec<unsigned char> copyStage; // pinned staging of copy_out (one 64 MB wave)
+    // reference result order (c2d_gpu_set_result_order)
+    struct OrderBuffers
+    {
+        c2d_host::DevBuf<uint32_t> keys, vals, keysTmp, valsTmp;
+        c2d_host::DevBuf<unsigned char> sortWs;
+        c2d_host::DevBuf<c2d_dev::PairOut> sorted;
+    } order;
+    bool referenceOrder = false; // the records of a frame are returned in the reference's order
+    bool resultsOrdered = false; // the last frame's records are in order.sorted
     c2d_host::RayBuffers rays;
     c2d_host::GridBuffers grid;
     c2d_host::QueryBuffers query;

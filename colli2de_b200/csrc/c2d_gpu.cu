@@ -723,7 +723,13 @@ void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats);
 // the records a query returns: this rank's, or the group's when the result mode gathered them (c2d_comm.cu)
 inline const PairOut* result_ptr(const c2d_gpu_ctx* ctx)
 {
-    return ctx->comm.resultsGathered ? ctx->comm.outAll.ptr : ctx->out.ptr;
+    return ctx->comm.resultsGathered ? ctx->comm.outAll.ptr
+                                     : (ctx->resultsOrdered ? ctx->order.sorted.ptr : (ctx->resultsOnHost ? ctx->smallOut.data : ctx->out.ptr));
+}
+// the records are already in host memory (a small scene's mapped output, neither reordered nor gathered)
+inline bool result_on_host(const c2d_gpu_ctx* ctx)
+{
+    return ctx->resultsOnHost && !ctx->resultsOrdered && !ctx->comm.resultsGathered;
 }
 inline uint64_t result_count(const c2d_gpu_ctx* ctx)
 {
@@ -745,12 +751,14 @@ int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
                 ctx->tree[C2D_STATIC].members.ptr, nS, ctx->tree[C2D_DYNAMIC].members.ptr, nD, ctx->tree[C2D_BULLET].members.ptr, nB,
                 ctx->d.fat, ctx->d.category, ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount));
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[3], s));
+        if (ctx->smallOut.capacity == 0 && !ctx->smallOut.reserve(1u << 14))
+            return fail(ctx, "pinned host allocation failed");
         C2D_TIMED(ctx, "k_small_narrow", k_small_narrow<<<148 * 2, 128, 0, s>>>(ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), ctx->d,
-                                                                             ctx->dScratch, ctx->out.ptr, static_cast<uint32_t>(ctx->out.capacity)));
+                                                                             ctx->dScratch, ctx->smallOut.data,
+                                                                             static_cast<uint32_t>(ctx->smallOut.capacity), ctx->hScratch));
         ctx->launches += 2;
         C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
-        C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
-        ctx->frame.d2h += sizeof(FrameScratch);
+        ctx->frame.d2h += 16;
         return 0;
     }
     if (ctx->broadphase == C2D_BROADPHASE_GRID)
@@ -867,12 +875,16 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
         return rc;
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
 
-    C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
-    ++ctx->launches;
     // small scenes: all-pairs box test + one narrowphase kernel instead of the tree pipeline (launch-latency bound);
     // like the grid broadphase this needs no tree, rays build them on demand (ensure_trees)
     const size_t alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
     ctx->frame.smallScene = alive <= ctx->smallSceneMax && ctx->shardWorld == 1;
+    if (!(ctx->frame.smallScene && ctx->scratchClean)) // a small frame leaves the counters zeroed for the next one
+    {
+        C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
+        ++ctx->launches;
+    }
+    ctx->scratchClean = false;
     if (ctx->frame.smallScene)
     {
         for (int body = 0; body < 3; ++body)
@@ -913,6 +925,36 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
     return 0;
 }
 
+// The frame's records in the reference's order (k_order_* in c2d_kernels.cuh): out -> order.sorted.
+int order_results(c2d_gpu_ctx* ctx, uint32_t n)
+{
+    ctx->resultsOrdered = false;
+    if (!ctx->referenceOrder || n == 0)
+        return 0;
+    if (ctx->shapeSlots > 0x1fffffffu)
+        return fail(ctx, "c2d_gpu_set_result_order: shape ids must stay below 2^29");
+    auto& ob = ctx->order;
+    const PairOut* produced = ctx->resultsOnHost ? ctx->smallOut.data : ctx->out.ptr; // mapped host memory reads fine on the device
+    cudaStream_t s = ctx->stream;
+    C2D_CUDA(ctx, ob.keys.reserve(n));
+    C2D_CUDA(ctx, ob.vals.reserve(n));
+    C2D_CUDA(ctx, ob.keysTmp.reserve(n));
+    C2D_CUDA(ctx, ob.valsTmp.reserve(n));
+    C2D_CUDA(ctx, ob.sortWs.reserve(sort_workspace_bytes(n, 4)));
+    C2D_CUDA(ctx, ob.sorted.reserve(n));
+    ProfScope ps(ctx, "result_order(2 sorts + gather)");
+    k_order_key_b<<<blocks_for(n, 256), 256, 0, s>>>(produced, n, ob.keys.ptr, ob.vals.ptr);
+    ctx->launches += 1 + radix_sort_pairs(s, ob.keys.ptr, ob.vals.ptr, ob.keysTmp.ptr, ob.valsTmp.ptr, n, 4, ob.sortWs.ptr);
+    k_order_key_a<<<blocks_for(n, 256), 256, 0, s>>>(produced, n, ob.vals.ptr, ctx->d.meta, ob.keys.ptr);
+    ctx->launches += 1 + radix_sort_pairs(s, ob.keys.ptr, ob.vals.ptr, ob.keysTmp.ptr, ob.valsTmp.ptr, n, 4, ob.sortWs.ptr);
+    k_order_gather<<<blocks_for(static_cast<size_t>(n) * 32, 256), 256, 0, s>>>(produced, n, ob.vals.ptr, ob.sorted.ptr);
+    ++ctx->launches;
+    C2D_CUDA(ctx, cudaGetLastError());
+    C2D_CUDA(ctx, cudaStreamSynchronize(s));
+    ctx->resultsOrdered = true;
+    return 0;
+}
+
 // Waits for the attempt in flight; on a pair-list overflow grows the lists and re-runs traversal + narrowphase
 // (boxes and trees are unchanged).
 int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
@@ -932,10 +974,17 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
             return fail(ctx, "polygon clip scratch overflow (non-convex polygon input?)");
         if (ctx->hScratch->stackOverflow)
             return fail(ctx, "LBVH traversal stack overflow (tree deeper than 64 levels)");
+        const bool small = ctx->frame.smallScene;
         const bool candOverflow = candCount > ctx->cand.capacity;
-        const bool outOverflow = pairCount > ctx->out.capacity;
+        const bool outOverflow = pairCount > (small ? ctx->smallOut.capacity : ctx->out.capacity);
         if (!candOverflow && !outOverflow)
+        {
+            ctx->scratchClean = small;
+            ctx->resultsOnHost = small;
+            if (small)
+                ctx->frame.d2h += static_cast<uint64_t>(pairCount) * sizeof(PairOut); // written across PCIe by the kernel
             break;
+        }
         ++ctx->frame.retries;
         if (candOverflow)
         {
@@ -943,7 +992,13 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
             C2D_CUDA(ctx, ctx->binned.reserve(ctx->cand.capacity));
             C2D_CUDA(ctx, ctx->hits.reserve(ctx->cand.capacity));
         }
-        if (outOverflow)
+        if (outOverflow && small)
+        {
+            ctx->smallOut.size = 0;
+            if (!ctx->smallOut.reserve(static_cast<size_t>(pairCount) + pairCount / 4))
+                return fail(ctx, "pinned host allocation failed");
+        }
+        else if (outOverflow)
             C2D_CUDA(ctx, ctx->out.reserve(static_cast<size_t>(pairCount) + pairCount / 4));
         C2D_TIMED(ctx, "k_frame_init", k_frame_init<<<1, 32, 0, s>>>(ctx->dScratch));
         ++ctx->launches;
@@ -952,6 +1007,8 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
     }
     ctx->lastCandidates = candCount;
     ctx->lastPairs = pairCount;
+    if (int rc = order_results(ctx, pairCount))
+        return rc;
     if (int rc = comm_gather_results(ctx)) // multi-GPU group with a result mode: collective, once per frame
         return rc;
     if (ctx->profiling)
@@ -984,7 +1041,7 @@ void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
 int download_records(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
 {
     const uint64_t pairCount = result_count(ctx);
-    if (pairCount)
+    if (pairCount && !result_on_host(ctx))
     {
         if (!ctx->hostOut.reserve(pairCount))
             return fail(ctx, "pinned host allocation failed");
@@ -1009,7 +1066,7 @@ int run_pipeline(c2d_gpu_ctx* ctx, bool download, const c2d_pair_record** outRec
         if (int rc = download_records(ctx, stats))
             return rc;
     if (outRecords)
-        *outRecords = reinterpret_cast<const c2d_pair_record*>(ctx->hostOut.data);
+        *outRecords = reinterpret_cast<const c2d_pair_record*>(result_on_host(ctx) ? ctx->smallOut.data : ctx->hostOut.data);
     if (outCount)
         *outCount = result_count(ctx);
     return 0;
@@ -1233,6 +1290,13 @@ int c2d_gpu_set_shard(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world)
     ctx->shardWorld = world;
     ctx->slabDirty = true;
     ctx->slab.valid = false;
+    return 0;
+}
+
+int c2d_gpu_set_result_order(c2d_gpu_ctx* ctx, int reference_order)
+{
+    ctx->referenceOrder = reference_order != 0;
+    ctx->resultsOrdered = false;
     return 0;
 }
 
@@ -1764,9 +1828,17 @@ int c2d_gpu_collide_fetch(c2d_gpu_ctx* ctx, c2d_pair_record* dst, uint64_t count
     if (count && !dst)
         return fail(ctx, "c2d_gpu_collide_fetch: dst is NULL");
     const uint64_t total = count * sizeof(PairOut);
-    if (int rc = c2d_host::copy_out(ctx, result_ptr(ctx), dst, total))
-        return rc;
-    ctx->frame.d2h += total;
+    if (result_on_host(ctx))
+    {
+        if (int rc = c2d_host::copy_host(ctx, ctx->smallOut.data, dst, total))
+            return rc;
+    }
+    else
+    {
+        if (int rc = c2d_host::copy_out(ctx, result_ptr(ctx), dst, total))
+            return rc;
+        ctx->frame.d2h += total;
+    }
     if (stats)
         fill_stats(ctx, stats);
     return 0;

@@ -102,7 +102,8 @@ struct FrameScratch
     uint32_t binCursor[16];
     uint32_t hitCount[16]; // narrowphase hits per bin (phase 1)
     uint32_t hitBase[17];  // exclusive scan of hitCount; [16] = total
-    uint32_t _pad2[3];
+    uint32_t ticket;       // blocks of k_small_narrow that have finished (the last one publishes and resets the counters)
+    uint32_t _pad2[2];
 };
 
 struct PairOut // 84 bytes, = Registry<uint32_t>::EntityCollision

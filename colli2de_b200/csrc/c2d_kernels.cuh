@@ -229,7 +229,10 @@ __global__ void k_frame_init(FrameScratch* fs)
         fs->hitBase[t - 16] = 0;
     }
     if (t == 15)
+    {
         fs->hitBase[16] = 0;
+        fs->ticket = 0;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_bounds(const uint32_t* __restrict__ members, uint32_t n,
@@ -1182,6 +1185,50 @@ __global__ void __launch_bounds__(128) k_narrow_manifold(const uint4* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Reference result order (c2d_gpu_set_result_order): the reference returns its five groups one after the other - Dynamic x
+// Static, Dynamic x Dynamic, Bullet x Static, Bullet x Dynamic, Bullet x Bullet - each sorted by (shapeA, shapeB)
+// (Registry.hpp:487-545: std::sort of the candidate list, narrowphase in that order).  The records come out of the
+// manifold kernels grouped by narrowphase bin; two stable radix sorts of an index permutation (by shapeB, then by
+// group | shapeA) and one gather put them in that order.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_order_key_b(const PairOut* __restrict__ out, uint32_t n, uint32_t* __restrict__ keys,
+                                                     uint32_t* __restrict__ vals)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    keys[i] = out[i].shapeB;
+    vals[i] = i;
+}
+
+__global__ void __launch_bounds__(256) k_order_key_a(const PairOut* __restrict__ out, uint32_t n, const uint32_t* __restrict__ perm,
+                                                     const uint32_t* __restrict__ meta, uint32_t* __restrict__ keys)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const PairOut* o = out + perm[i];
+    const uint32_t ba = meta_body(meta[o->shapeA]), bb = meta_body(meta[o->shapeB]);
+    // (Dynamic, Static) 0, (Dynamic, Dynamic) 1, (Bullet, Static) 2, (Bullet, Dynamic) 3, (Bullet, Bullet) 4
+    const uint32_t group = ba == 1u ? (bb == 0u ? 0u : 1u) : (bb == 0u ? 2u : (bb == 1u ? 3u : 4u));
+    keys[i] = (group << 29) | (o->shapeA & 0x1fffffffu);
+}
+
+// one warp per record: 21 coalesced 4-byte words
+__global__ void __launch_bounds__(256) k_order_gather(const PairOut* __restrict__ out, uint32_t n, const uint32_t* __restrict__ perm,
+                                                      PairOut* __restrict__ sorted)
+{
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n)
+        return;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(out + perm[w]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sorted + w);
+    if (lane < 21)
+        dst[lane] = src[lane];
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Small scenes (a few thousand shapes — the reference's own 1k / 10k benchmarks): the frame is bound by the ~30
 // dependent launches of the tree pipeline, not by work.  Two kernels replace sort + build + fit + 5 traversals and
 // the 8 narrowphase launches: an all-pairs box test over the member lists (tiles of targets staged in shared
@@ -1233,8 +1280,13 @@ __global__ void __launch_bounds__(kSmallQueries)
     }
 }
 
+// `out` is pinned host memory mapped into the device's address space: a small scene's few records cross PCIe as they are
+// written, so the host needs ONE synchronisation per frame (no count read-back followed by a second copy).  The last
+// block to finish publishes the frame counters to `hostFs` (mapped as well) and resets the device counters, which leaves
+// the scratch ready for the next small frame without a k_frame_init launch.
 __global__ void __launch_bounds__(128) k_small_narrow(const uint2* __restrict__ cand, uint32_t capacity, ShapeArrays s,
-                                                      FrameScratch* fs, PairOut* __restrict__ out, uint32_t outCapacity)
+                                                      FrameScratch* fs, PairOut* __restrict__ out, uint32_t outCapacity,
+                                                      FrameScratch* hostFs)
 {
     const uint32_t n = min(fs->candCount, capacity);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
@@ -1267,6 +1319,24 @@ __global__ void __launch_bounds__(128) k_small_narrow(const uint2* __restrict__ 
             o->shapeA = p.x;
             o->shapeB = p.y;
             manifold_store(m, o->manifold);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        __threadfence();
+        if (atomicAdd(&fs->ticket, 1u) == gridDim.x - 1)
+        {
+            hostFs->candCount = fs->candCount;
+            hostFs->outCount = atomicAdd(&fs->outCount, 0u);
+            hostFs->clipOverflow = atomicAdd(&fs->clipOverflow, 0u);
+            hostFs->stackOverflow = 0;
+            fs->candCount = 0;
+            fs->outCount = 0;
+            fs->clipOverflow = 0;
+            fs->stackOverflow = 0;
+            fs->ticket = 0;
+            __threadfence_system();
         }
     }
 }

@@ -194,6 +194,14 @@ typedef struct c2d_gpu_comm_stats
 } c2d_gpu_comm_stats;
 int c2d_gpu_comm_get_stats(c2d_gpu_ctx* ctx, c2d_gpu_comm_stats* out);
 
+/* Order of the records a query returns.  0 (default): grouped by narrowphase bin, order inside a bin unspecified and not
+ * reproducible from run to run (warp-aggregated appends).  1: the reference's order (Registry.hpp:487-545) - its five groups
+ * one after the other (Dynamic x Static, Dynamic x Dynamic, Bullet x Static, Bullet x Dynamic, Bullet x Bullet), each
+ * sorted by (shapeA, shapeB); byte-identical from run to run.  Same-tree groups use this library's canonical
+ * orientation shapeA < shapeB (the reference's orientation there is an accident of its tree layout).  Costs two radix sorts
+ * of an index permutation and one gather of the 84-byte records per frame.  In a multi-GPU group every rank orders its
+ * own share. */
+int c2d_gpu_set_result_order(c2d_gpu_ctx* ctx, int reference_order);
 /* Independent kernels of a frame run side by side on a second stream (the Dynamic x Static traversal next to the Dynamic
  * tree's refit and self traversal, the two filter kernels, the two manifold kernels).  Results are identical; 0 puts
  * everything back on one stream (for per-kernel timing that should not see the neighbours).  Default on. */

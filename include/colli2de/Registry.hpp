@@ -393,6 +393,10 @@ class Registry
         check(c2d_gpu_comm_get_stats(mCtx, &st));
         return st;
     }
+    // getCollidingPairs() returns its records in the reference's order (its five body-type groups one after the other,
+    // each sorted by (shapeA, shapeB); Registry.hpp:487-545), byte-identical from run to run.  Off by default: the
+    // unordered result saves two radix sorts and a gather per frame.
+    void setDeterministicOrder(bool on) { check(c2d_gpu_set_result_order(mCtx, on ? 1 : 0)); }
     // Counters and CUDA-event timings of the last getCollidingPairs() / rayCast().
     const c2d_gpu_stats& lastQueryStats() const { return mStats; }
     // Runs the pipeline but leaves the records on the device; returns the number of colliding pairs.

@@ -75,7 +75,7 @@ class Report:
             times.append(1e3 * func())
         self.rows.append((name, threshold_ms, times))
         avg = sum(times) / len(times)
-        print(f"{name}: avg {avg:.3f} ms (threshold {threshold_ms} ms)", file=sys.stderr)
+        print(f"{name}: avg {avg:.3f} ms (threshold {threshold_ms} ms)  samples " + " ".join(f"{t:.3f}" for t in times), file=sys.stderr)
 
     def export(self, folder):
         """exportBenchmarks (tests/utils/Performance.hpp:154-214): sorted by average, 3 decimals, padded columns."""
