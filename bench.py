@@ -327,6 +327,14 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
         b.release_staged(h)
     pairs_all = allsum(float(pairs_total))
     cand_all = allsum(float(cand_total))
+    per_rank = None
+    if world > 1:
+        rows = [None] * world
+        dist.all_gather_object(rows, {"pairs_per_frame": pairs_total / K, "candidates_per_frame": cand_total / K,
+                                      "ms_device": stage_ms["ms_device"] / K, "ms_broad": stage_ms["ms_broad"] / K,
+                                      "ms_narrow": stage_ms["ms_narrow"] / K, "ms_build": stage_ms["ms_build"] / K,
+                                      "slab_owned": slab["slab_owned"] / K, "slab_halo": (slab["slab_leaves"] - slab["slab_owned"]) / K})
+        per_rank = rows
     ms_per_step = 1e3 * elapsed / K
     value = pairs_all / elapsed
 
@@ -336,7 +344,8 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     # computes its Morton slab and returns ITS share of the pairs into its own host memory.
     def e2e_loop(frames: int, skip: int):
         times, moves, pairs, up, down, xms, gms, xbytes, gbytes = [], [], 0, 0.0, 0.0, [], [], 0.0, 0.0
-        stages = dict(ms_refit=0.0, ms_build=0.0, ms_broad=0.0, ms_narrow=0.0, ms_device=0.0, ms_total=0.0)
+        stages = dict(ms_refit=0.0, ms_build=0.0, ms_broad=0.0, ms_narrow=0.0, ms_device=0.0, ms_total=0.0, ms_host_enqueue=0.0,
+                      ms_host_wait=0.0)
         for f in range(skip + frames):
             d = frame_moves()
             if f == skip:
@@ -533,6 +542,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     }
     if world > 1:
         out["config"]["slab_ms_per_step"] = slab["ms_slab"] / K
+        out["config"]["per_rank"] = per_rank
     return out
 
 

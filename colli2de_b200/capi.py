@@ -21,7 +21,7 @@ EXPORTS = [
     "c2d_gpu_read_candidates", "c2d_gpu_shape_slots", "c2d_gpu_collide_batch", "c2d_gpu_sweep_batch", "c2d_gpu_raycast_shape_batch",
     "c2d_gpu_compute_aabb_batch",
     "c2d_gpu_set_slab_mode", "c2d_gpu_comm_unique_id", "c2d_gpu_comm_init", "c2d_gpu_comm_destroy",
-    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats", "c2d_gpu_read_transforms", "c2d_gpu_set_ray_sharding", "c2d_gpu_set_profile_filter", "c2d_gpu_set_overlap", "c2d_gpu_set_result_order",
+    "c2d_gpu_comm_set_move_exchange", "c2d_gpu_comm_set_result_mode", "c2d_gpu_comm_get_stats", "c2d_gpu_read_transforms", "c2d_gpu_set_ray_sharding", "c2d_gpu_set_profile_filter", "c2d_gpu_set_overlap", "c2d_gpu_set_incremental_refit", "c2d_gpu_set_result_order",
 ]
 
 _lib = None
@@ -49,7 +49,7 @@ class Stats(C.Structure):
     _fields_ = [("shapes_alive", C.c_uint64), ("candidates", C.c_uint64), ("pairs", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("kernel_launches", C.c_uint32), ("retries", C.c_uint32), ("ms_refit", C.c_float),
                 ("ms_build", C.c_float), ("ms_broad", C.c_float), ("ms_narrow", C.c_float), ("ms_device", C.c_float),
-                ("ms_total", C.c_float)]
+                ("ms_total", C.c_float), ("ms_host_enqueue", C.c_float), ("ms_host_wait", C.c_float), ("reserved", C.c_float)]
 
 
 def _check(ctx, rc: int):
@@ -71,6 +71,11 @@ def set_result_order(ctx, reference_order: bool):
     """records come back in the reference's order (five groups, each sorted by (shapeA, shapeB)), byte-identical run to run"""
     lib().c2d_gpu_set_result_order.argtypes = [C.c_void_p, C.c_int]
     _check(ctx, lib().c2d_gpu_set_result_order(ctx, 1 if reference_order else 0))
+
+
+def set_incremental_refit(ctx, on: bool):
+    lib().c2d_gpu_set_incremental_refit.argtypes = [C.c_void_p, C.c_int]
+    _check(ctx, lib().c2d_gpu_set_incremental_refit(ctx, 1 if on else 0))
 
 
 def set_overlap(ctx, on: bool):

@@ -263,6 +263,7 @@ struct c2d_gpu_ctx
     cudaEvent_t evFork = nullptr, evJoin = nullptr;
     bool preFitRecorded = false;      // evPreFit belongs to this frame
     bool overlap = true;              // c2d_gpu_set_overlap
+    bool incrementalRefit = true;     // frames that keep a tree's topology refit only the flagged leaves (k_refit_dirty)
     uint32_t transBodies = 0;            // bodies (bit per BodyType) touched by the translations logged since the last flush
     std::vector<Round> rounds;
     DevBuf<FlagRec> dFlagLog;
@@ -307,6 +308,7 @@ struct c2d_gpu_ctx
         bool open = false;
         bool smallScene = false; // this frame runs k_small_pairs / k_small_narrow instead of the tree pipeline
         std::chrono::steady_clock::time_point wall0{};
+        float msEnqueued = 0.0f, msWaited = 0.0f; // host clock since wall0: frame enqueued / device finished
         uint32_t retries = 0;
         uint64_t d2h = 0;
     } frame;

@@ -486,9 +486,16 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
             C2D_CUDA(ctx, cudaEventRecord(ctx->evPreFit, s));
             ctx->preFitRecorded = true;
         }
-        C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
-        C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
-                                                 t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
+        if (ctx->incrementalRefit)
+            // leaf boxes change only through the mutation kernels, which flag them: grow the ancestors of the flagged leaves
+            C2D_TIMED(ctx, "k_refit_dirty", k_refit_dirty<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.meta,
+                                                             t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr));
+        else
+        {
+            C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, n * sizeof(uint32_t), s));
+            C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(n, 256), 256, 0, s>>>(static_cast<int>(n), t.vals.ptr, ctx->d.fat, ctx->d.category,
+                                                     t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
+        }
         ++ctx->launches;
         return 0;
     }
@@ -610,9 +617,15 @@ int update_slab(c2d_gpu_ctx* ctx)
     ctx->preFitRecorded = true;
     if (m > 1)
     {
-        C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, m * sizeof(uint32_t), s));
-        C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(m, 256), 256, 0, s>>>(static_cast<int>(m), t.vals.ptr, ctx->d.fat, ctx->d.category,
-                                                 t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
+        if (!rebalance && ctx->incrementalRefit)
+            C2D_TIMED(ctx, "k_refit_dirty", k_refit_dirty<<<blocks_for(m, 256), 256, 0, s>>>(static_cast<int>(m), t.vals.ptr, ctx->d.fat, ctx->d.meta,
+                                                             t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr));
+        else
+        {
+            C2D_CUDA(ctx, cudaMemsetAsync(t.arrival.ptr, 0, m * sizeof(uint32_t), s));
+            C2D_TIMED(ctx, "k_fit", k_fit<<<blocks_for(m, 256), 256, 0, s>>>(static_cast<int>(m), t.vals.ptr, ctx->d.fat, ctx->d.category,
+                                                     t.nodes.ptr, t.nodeParent.ptr, t.leafParent.ptr, t.arrival.ptr));
+        }
         ++ctx->launches;
     }
     // the halo of this frame: exact for the CURRENT boxes
@@ -922,6 +935,7 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
     if (int rc = pipeline_attempt(ctx))
         return rc;
     ctx->frame.open = true;
+    ctx->frame.msEnqueued = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->frame.wall0).count();
     return 0;
 }
 
@@ -1007,6 +1021,7 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
     }
     ctx->lastCandidates = candCount;
     ctx->lastPairs = pairCount;
+    ctx->frame.msWaited = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->frame.wall0).count();
     if (int rc = order_results(ctx, pairCount))
         return rc;
     if (int rc = comm_gather_results(ctx)) // multi-GPU group with a result mode: collective, once per frame
@@ -1035,6 +1050,8 @@ void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
     cudaEventElapsedTime(&stats->ms_device, ctx->ev[0], ctx->ev[4]);
     stats->ms_total =
         std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->frame.wall0).count();
+    stats->ms_host_enqueue = ctx->frame.msEnqueued;
+    stats->ms_host_wait = ctx->frame.msWaited;
 }
 
 // Records of the last frame -> the library's pinned buffer (one copy), for the pointer-returning entry points.
@@ -1297,6 +1314,12 @@ int c2d_gpu_set_result_order(c2d_gpu_ctx* ctx, int reference_order)
 {
     ctx->referenceOrder = reference_order != 0;
     ctx->resultsOrdered = false;
+    return 0;
+}
+
+int c2d_gpu_set_incremental_refit(c2d_gpu_ctx* ctx, int on)
+{
+    ctx->incrementalRefit = on != 0;
     return 0;
 }
 

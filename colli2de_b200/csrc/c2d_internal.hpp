@@ -19,6 +19,7 @@ constexpr uint32_t META_GHOST = 1u << 6; // halo copy of a shape owned by anothe
 constexpr uint32_t META_TIGHT_EXACT = 1u << 7; // tight box == computeAABB(shape, current transform): set by add / Transform
                                                // moves, cleared by translations (which shift the box) and restores
 constexpr uint32_t META_COUNT_SHIFT = 8;
+constexpr uint32_t META_FAT_DIRTY = 1u << 12; // the leaf (fat) box changed since the shape's tree last saw it (k_refit_dirty)
 
 __host__ __device__ inline uint32_t meta_type(uint32_t m) { return m & META_TYPE_MASK; }
 __host__ __device__ inline uint32_t meta_body(uint32_t m) { return (m >> META_BODY_SHIFT) & 0x3u; }

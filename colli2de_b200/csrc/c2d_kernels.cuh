@@ -30,11 +30,11 @@ namespace cg = cooperative_groups;
 // DynamicBVH::moveProxy leaf rule with margin 0 (reference DynamicBVH.hpp:386-400, AABB.cpp:212-228):
 // keep the fat box if it still contains the target, else target grown by 2.2 x (target.min - fat.min)
 // in the direction of motion.
-__device__ __forceinline__ void fat_leaf_rule(float4* fatSlot, const Box& target)
+__device__ __forceinline__ bool fat_leaf_rule(float4* fatSlot, const Box& target) // true: the leaf box changed
 {
     const Box fat = box_from(*fatSlot);
     if (box_contains(fat, target))
-        return;
+        return false;
     const float dispx = (target.minx - fat.minx) * 2.2f;
     const float dispy = (target.miny - fat.miny) * 2.2f;
     Box nf = target; // fattened(margin = 0)
@@ -47,6 +47,7 @@ __device__ __forceinline__ void fat_leaf_rule(float4* fatSlot, const Box& target
     else
         nf.maxy += dispy;
     *fatSlot = box_to(nf);
+    return true;
 }
 
 __global__ void __launch_bounds__(256) k_apply_flags(const FlagRec* __restrict__ log, uint32_t n, ShapeArrays s)
@@ -109,8 +110,6 @@ __device__ __forceinline__ void apply_translate(const TransRec rec, const ShapeA
     const float dx = rec.dx, dy = rec.dy;
     const uint32_t meta = s.meta[shape];
     const bool bullet = meta_body(meta) == 2u;
-    if (meta & META_TIGHT_EXACT)
-        s.meta[shape] = meta & ~META_TIGHT_EXACT; // the box is shifted from now on, not recomputed (rounding drift)
 
     const Box old = box_from(s.tight[shape]);
     Box nt; // AABB::translate: min += d; max += d (AABB.cpp:248-252)
@@ -119,7 +118,11 @@ __device__ __forceinline__ void apply_translate(const TransRec rec, const ShapeA
     nt.maxx = old.maxx + dx;
     nt.maxy = old.maxy + dy;
     s.tight[shape] = box_to(nt);
-    fat_leaf_rule(&s.fat[shape], bullet ? box_combine(old, nt) : nt);
+    const bool leafChanged = fat_leaf_rule(&s.fat[shape], bullet ? box_combine(old, nt) : nt);
+    // the box is shifted from now on, not recomputed (rounding drift); a changed leaf box is flagged for the tree's refit
+    const uint32_t after = (meta & ~META_TIGHT_EXACT) | (leafChanged ? META_FAT_DIRTY : 0u);
+    if (after != meta)
+        s.meta[shape] = after;
 
     float4 t = s.xf[shape];
     if (bullet)
@@ -169,13 +172,14 @@ __global__ void __launch_bounds__(256) k_apply_moves(const MoveRec* __restrict__
     t.c = r1.y;
     const uint32_t meta = s.meta[shape];
     const bool bullet = meta_body(meta) == 2u;
-    if (!(meta & META_TIGHT_EXACT))
-        s.meta[shape] = meta | META_TIGHT_EXACT;
 
     const Box old = box_from(s.tight[shape]);
     const Box nt = compute_aabb(meta_type(meta), meta_count(meta), s.geom + static_cast<size_t>(shape) * 32, t);
     s.tight[shape] = box_to(nt);
-    fat_leaf_rule(&s.fat[shape], bullet ? box_combine(old, nt) : nt);
+    const bool leafChanged = fat_leaf_rule(&s.fat[shape], bullet ? box_combine(old, nt) : nt);
+    const uint32_t after = meta | META_TIGHT_EXACT | (leafChanged ? META_FAT_DIRTY : 0u);
+    if (after != meta)
+        s.meta[shape] = after;
     if (bullet)
     {
         s.pxf[shape] = s.xf[shape];
@@ -411,6 +415,69 @@ __global__ void __launch_bounds__(256) k_fit(int n, const uint32_t* __restrict__
         if (q == 0)
             return;
         code = nodeParent[q];
+    }
+}
+
+// Refit of a tree whose topology is kept (frames between two rebuilds) when only translations moved its leaves: most leaf
+// boxes did not change at all (the fat-leaf rule keeps a box while it still contains the shape), so instead of the
+// full bottom-up pass - a chain of ~log n dependent fence + atomic steps per leaf - only the leaves flagged
+// META_FAT_DIRTY act: the leaf's slot in its parent gets the exact new box, and every ancestor slot on the way up is
+// GROWN to contain it (component-wise atomic min / max), stopping at the first ancestor that already does.  Leaf slots
+// stay exact, so the candidate set is unchanged; internal boxes are conservative until the next rebuild (at most
+// rebuildPeriod - 1 frames later) recomputes them.  Why stopping early is safe: every bound a thread relies on was put
+// there by the last full fit (where parent slots contain child slots) or by a thread that lowered / raised that very
+// component and carries the same value further up.
+__device__ __forceinline__ void atomic_min_float(float* addr, float v)
+{
+    if (v >= 0.0f)
+        atomicMin(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_float(float* addr, float v)
+{
+    if (v >= 0.0f)
+        atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else
+        atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
+__global__ void __launch_bounds__(256) k_refit_dirty(int n, const uint32_t* __restrict__ sorted, const float4* __restrict__ fat,
+                                                     uint32_t* __restrict__ meta, BvhNode* nodes,
+                                                     const int* __restrict__ nodeParent, const int* __restrict__ leafParent)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n)
+        return;
+    const uint32_t shape = sorted[p] & kLeafIdMask;
+    const uint32_t m = meta[shape];
+    if (!(m & META_FAT_DIRTY))
+        return;
+    meta[shape] = m & ~META_FAT_DIRTY;
+    float4 box = fat[shape];
+    // -0.0f would order below +0.0f in the integer comparisons of the atomics: canonicalise
+    box.x += 0.0f, box.y += 0.0f, box.z += 0.0f, box.w += 0.0f;
+    int code = leafParent[p];
+    int q = code >> 1;
+    float4* slot = (code & 1) ? &nodes[q].boxR : &nodes[q].boxL;
+    *slot = fat[shape]; // the leaf's own slot: exact, single writer
+    while (q != 0)
+    {
+        code = nodeParent[q];
+        q = code >> 1;
+        slot = (code & 1) ? &nodes[q].boxR : &nodes[q].boxL;
+        const float4 cur = __ldcg(slot);
+        const bool gx = box.x < cur.x, gy = box.y < cur.y, gz = box.z > cur.z, gw = box.w > cur.w;
+        if (!(gx || gy || gz || gw))
+            return;
+        if (gx)
+            atomic_min_float(&slot->x, box.x);
+        if (gy)
+            atomic_min_float(&slot->y, box.y);
+        if (gz)
+            atomic_max_float(&slot->z, box.z);
+        if (gw)
+            atomic_max_float(&slot->w, box.w);
     }
 }
 

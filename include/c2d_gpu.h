@@ -109,6 +109,9 @@ typedef struct c2d_gpu_stats
     float ms_narrow;          /* binning + narrowphase/sweeps (K6/K7) */
     float ms_device;          /* first kernel -> last kernel */
     float ms_total;           /* host wall clock of the call incl. copies */
+    float ms_host_enqueue;    /* host wall clock from the start of the call until the whole frame was enqueued */
+    float ms_host_wait;       /* ... until the device had finished it (counters read, retries done) */
+    float _reserved;
 } c2d_gpu_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */
@@ -202,6 +205,10 @@ int c2d_gpu_comm_get_stats(c2d_gpu_ctx* ctx, c2d_gpu_comm_stats* out);
  * of an index permutation and one gather of the 84-byte records per frame.  In a multi-GPU group every rank orders its
  * own share. */
 int c2d_gpu_set_result_order(c2d_gpu_ctx* ctx, int reference_order);
+/* Refit of the frames that keep a tree's topology (c2d_gpu_set_rebuild_period): 1 (default) only the leaves whose leaf box
+ * changed act - the exact box goes into the leaf's slot and the ancestors are grown to contain it; internal boxes are
+ * conservative until the next rebuild, leaf boxes (hence the candidate set) stay exact.  0: full bottom-up fit every frame. */
+int c2d_gpu_set_incremental_refit(c2d_gpu_ctx* ctx, int on);
 /* Independent kernels of a frame run side by side on a second stream (the Dynamic x Static traversal next to the Dynamic
  * tree's refit and self traversal, the two filter kernels, the two manifold kernels).  Results are identical; 0 puts
  * everything back on one stream (for per-kernel timing that should not see the neighbours).  Default on. */

@@ -385,7 +385,7 @@ struct RegistryHolder final : IRegistry
         const c2d_gpu_stats& s = reg.lastQueryStats();
         const double v[16] = {double(s.shapes_alive), double(s.candidates), double(s.pairs), double(s.h2d_bytes),
                               double(s.d2h_bytes), double(s.kernel_launches), double(s.retries), s.ms_refit,
-                              s.ms_build, s.ms_broad, s.ms_narrow, s.ms_device, s.ms_total, 0, 0, 0};
+                              s.ms_build, s.ms_broad, s.ms_narrow, s.ms_device, s.ms_total, s.ms_host_enqueue, s.ms_host_wait, 0};
         std::memcpy(o, v, sizeof(v));
     }
     int stage(uint32_t n, const uint32_t* ids, const float* dxy) override

@@ -379,7 +379,7 @@ class Backend:
         return (out, sec.value) if with_time else out
 
     STAT_FIELDS = ("shapes_alive", "candidates", "pairs", "h2d_bytes", "d2h_bytes", "kernel_launches", "retries",
-                   "ms_refit", "ms_build", "ms_broad", "ms_narrow", "ms_device", "ms_total")
+                   "ms_refit", "ms_build", "ms_broad", "ms_narrow", "ms_device", "ms_total", "ms_host_enqueue", "ms_host_wait")
 
     def count_pairs_device(self):
         sec = C.c_double(0.0)

@@ -160,3 +160,37 @@ def test_bulk_move_and_teleport_entities():
         res = _check(ref, gpu, idx, max_ambiguous=8)
         assert res["expected"] > 5000 and res["not_bit_identical"] == 0, res
         assert np.array_equal(ref.get_transforms(mov).view(np.uint32), gpu.get_transforms(mov).view(np.uint32))
+
+
+def test_incremental_refit_many_frames_without_rebuild():
+    """k_refit_dirty: with the topology kept for many frames, internal boxes only grow (conservative) while the leaf slots
+    stay exact - the pair set must stay the reference's through large moves, Transform moves, teleports and bullets, and
+    be identical to the full bottom-up fit's."""
+    from colli2de_b200 import capi
+
+    sc = scenes.mixed_scene(30000, 3000, 900.0, seed=31, clustered=True)
+    sc["ent_body"][::50] = 2
+    ref, gpu, idx = _both(sc)
+    full = H.Backend(SUBJECT)
+    scenes.populate(full, sc)
+    capi.set_small_scene_limit(gpu.native_context(), 0)
+    capi.set_rebuild_period(gpu.native_context(), 64)
+    capi.set_rebuild_period(full.native_context(), 64)
+    capi.set_incremental_refit(full.native_context(), False)
+    rng = scenes.LCG(77)
+    mov = np.nonzero(sc["ent_body"] != 0)[0].astype(np.uint32)
+    for frame in range(12):
+        d = scenes.jitter(rng, len(mov), 3.0 if frame % 3 else 0.4)
+        for x in (ref, gpu, full):
+            x.move_translate(mov, d)
+        if frame in (4, 9):  # Transform moves and teleports flag their leaves as well
+            some = np.nonzero(sc["ent_body"] == 1)[0].astype(np.uint32)[frame::17]  # (rotating bullets are tolerance-only)
+            dxf = np.concatenate([scenes.jitter(rng, len(some), 2.0), scenes.jitter(rng, len(some), 0.3)[:, :1]], axis=1)
+            for x in (ref, gpu, full):
+                x.move_transform(some, dxf)
+        res = _check(ref, gpu, idx, max_ambiguous=8)
+        assert res["expected"] > 5000 and res["not_bit_identical"] == 0, (frame, res)
+        a, b = P.sort_pairs(gpu.get_colliding_pairs()), P.sort_pairs(full.get_colliding_pairs())
+        assert P.pair_keys(a).tobytes() == P.pair_keys(b).tobytes()
+        assert np.array_equal(gpu.candidates(), full.candidates()) or \
+            np.array_equal(np.sort(gpu.candidates().view("u8").ravel()), np.sort(full.candidates().view("u8").ravel()))
