@@ -427,7 +427,9 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
 
     # ---- roofline of the dominant kernel (live CUDA-event times) ----------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    dom_count, dom_ms = profile[dom_name]
+    dom_count, dom_ms = profile.get(dom_name, (0, 0.0))
+    if dom_count == 0:  # the kernel did not run in the timed frames (e.g. a rebuild-only kernel in a very short run)
+        dom_count, dom_ms = warm_profile[dom_name]
     n_shapes = n_dyn + n_sta
     cand_per_frame = cand_all / K / world        # per rank
     pairs_per_frame = pairs_all / K              # whole job

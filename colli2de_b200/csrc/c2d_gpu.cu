@@ -851,15 +851,23 @@ int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
     };
     if (int rc = fork())
         return rc;
-    C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<<<148 * 16, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+    const bool bullets = !ctx->members[C2D_BULLET].empty();
+    if (bullets)
+        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<true><<<148 * 16, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+    else
+        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<false><<<148 * 16, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
     C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
     if (int rc = join())
         return rc;
     C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
     if (int rc = fork())
         return rc;
-    C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<<<148 * 16, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
-                                     static_cast<uint32_t>(ctx->out.capacity)));
+    if (bullets)
+        C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<true><<<148 * 16, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                         static_cast<uint32_t>(ctx->out.capacity)));
+    else
+        C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<false><<<148 * 16, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+                                         static_cast<uint32_t>(ctx->out.capacity)));
     C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                      static_cast<uint32_t>(ctx->out.capacity)));
     if (int rc = join())

@@ -905,33 +905,46 @@ __global__ void k_bin_scan(FrameScratch* fs)
     }
 }
 
+// Tiles of 1024 candidates per block pass: ranks inside the tile come from shared-memory counters, the block reserves its
+// slice of every bin with ONE global atomic per bin (16 per tile instead of several per warp on the same 16 addresses).
 __global__ void __launch_bounds__(256) k_bin_scatter(const uint2* __restrict__ cand, uint32_t capacity,
                                                      const uint32_t* __restrict__ meta, FrameScratch* fs,
                                                      uint2* __restrict__ binned)
 {
+    constexpr int kPerThread = 4;
+    __shared__ uint32_t count[16];
+    __shared__ uint32_t base[16];
     const uint32_t n = min(fs->candCount, capacity);
-    const int lane = threadIdx.x & 31;
-    // warp-uniform trip count so the full-mask match below is always convergent
-    for (uint32_t base0 = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base0 < n; base0 += gridDim.x * blockDim.x)
+    const uint32_t tile = blockDim.x * kPerThread;
+    for (uint32_t t0 = blockIdx.x * tile; t0 < n; t0 += gridDim.x * tile)
     {
-        const uint32_t i = base0 + lane;
-        const bool valid = i < n;
-        uint2 p = make_uint2(0, 0);
-        int bin = 31;
-        if (valid)
+        if (threadIdx.x < 16)
+            count[threadIdx.x] = 0;
+        __syncthreads();
+        uint2 p[kPerThread];
+        int bin[kPerThread];
+        uint32_t rank[kPerThread];
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k)
         {
-            p = cand[i];
-            bin = pair_bin(meta[p.x], meta[p.y]);
+            const uint32_t i = t0 + k * blockDim.x + threadIdx.x;
+            bin[k] = -1;
+            if (i < n)
+            {
+                p[k] = cand[i];
+                bin[k] = pair_bin(meta[p[k].x], meta[p[k].y]);
+                rank[k] = atomicAdd(&count[bin[k]], 1u);
+            }
         }
-        // warp-aggregated cursor bump per bin
-        const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (valid && lane == leader)
-            base = atomicAdd(&fs->binCursor[bin], __popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid)
-            binned[fs->binOffset[bin] + base + __popc(peers & ((1u << lane) - 1u))] = p;
+        __syncthreads();
+        if (threadIdx.x < 16)
+            base[threadIdx.x] = count[threadIdx.x] ? fs->binOffset[threadIdx.x] + atomicAdd(&fs->binCursor[threadIdx.x], count[threadIdx.x]) : 0u;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kPerThread; ++k)
+            if (bin[k] >= 0)
+                binned[base[bin[k]] + rank[k]] = p[k];
+        __syncthreads();
     }
 }
 
@@ -1128,6 +1141,8 @@ __device__ __forceinline__ void run_sweeps(const SweepTodo* queue, int count, co
     append_hits(hit, i, p, fraction, fs, hits, lane);
 }
 
+// BULLETS = false: the scene holds no Bullet shape, the sweep code (and its registers: 96 -> occupancy 28 %) is compiled out.
+template <bool BULLETS>
 __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__ binned, uint32_t capacity,
                                                        ShapeArrays s, FrameScratch* fs, uint4* __restrict__ hits)
 {
@@ -1157,7 +1172,7 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
             PairCtx c;
             if (load_pair(s, p, c))
             {
-                if (!c.bulletA && !c.bulletB)
+                if (!BULLETS || (!c.bulletA && !c.bulletB))
                 {
                     Manifold unused;
                     hit = narrow_test<false>(c.A, c.xa, c.B, c.xb, unused);
@@ -1172,8 +1187,8 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
         }
         __syncwarp();
         append_hits(hit, i, p, 0.0f, fs, hits, lane);
-        const uint32_t todo = __ballot_sync(0xffffffffu, sweep);
-        if (todo)
+        const uint32_t todo = BULLETS ? __ballot_sync(0xffffffffu, sweep) : 0u;
+        if (BULLETS && todo)
         {
             if (sweep)
                 queue[queued + __popc(todo & ((1u << lane) - 1u))] = SweepTodo{p, i};
@@ -1187,7 +1202,7 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
             }
         }
     }
-    if (queued > 0)
+    if (BULLETS && queued > 0)
         run_sweeps(queue, queued, s, fs, hits, lane);
 }
 
@@ -1208,6 +1223,7 @@ __global__ void k_hit_scan(FrameScratch* fs)
 
 // Phase 2: the manifold of every hit (collide(), or collide() at the sweep fraction), written as an 84-byte
 // EntityCollision record at out[hitBase[bin] + k]: no atomics, output grouped by bin.
+template <bool BULLETS>
 __global__ void __launch_bounds__(128) k_narrow_manifold(const uint4* __restrict__ hits, ShapeArrays s,
                                                          const FrameScratch* __restrict__ fs,
                                                          PairOut* __restrict__ out, uint32_t outCapacity)
@@ -1227,7 +1243,7 @@ __global__ void __launch_bounds__(128) k_narrow_manifold(const uint4* __restrict
         PairCtx c;
         load_pair(s, p, c);
         Manifold m;
-        if (!c.bulletA && !c.bulletB)
+        if (!BULLETS || (!c.bulletA && !c.bulletB))
         {
             narrow_test<true>(c.A, c.xa, c.B, c.xb, m);
         }
