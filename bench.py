@@ -374,7 +374,13 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
                     xbytes += cs["exchange_bytes"]
                     gbytes += cs["gather_bytes"]
         barrier()
-        return dict(elapsed=allmax(float(np.sum(times))), pairs=pairs, h2d=allsum(up) / frames, d2h=allsum(down) / frames,
+        ranks = None
+        if world > 1:
+            ranks = [None] * world
+            dist.all_gather_object(ranks, {"mean_ms": 1e3 * float(np.mean(times)), "max_ms": 1e3 * float(np.max(times)),
+                                           "median_ms": 1e3 * float(np.median(times)), "lib_ms_total": stages["ms_total"],
+                                           "lib_ms_host_wait": stages["ms_host_wait"], "pairs": pairs / frames})
+        return dict(ranks=ranks, elapsed=allmax(float(np.sum(times))), pairs=pairs, h2d=allsum(up) / frames, d2h=allsum(down) / frames,
                     moves_ms=allmax(1e3 * float(np.mean(moves))), exchange_ms=float(np.mean(xms)) if xms else 0.0,
                     gather_ms=float(np.mean(gms)) if gms else 0.0, exchange_bytes=xbytes / frames, gather_bytes=gbytes / frames,
                     stages=stages)
@@ -516,6 +522,7 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
         e2e_out["view_ms_per_step"] = 1e3 * float(np.mean(view_times))
         e2e_out["view_call"] = "Registry::getCollidingPairsView() (extension: span over the pinned result buffer)"
     else:
+        e2e_out["per_rank_call_ms"] = e2e["ranks"]
         e2e_out["collective"] = {"name": "ncclAllGather of a 16-byte header + one grouped ncclBroadcast per rank of its 12-byte move records (device to device)",
                                  "bytes_received_per_rank_per_step": e2e["exchange_bytes"],
                                  "device_ms_per_step": e2e["exchange_ms"]}

@@ -109,6 +109,20 @@ int c2d_host::comm_allgather(c2d_gpu_ctx* ctx, const void* send, void* recv, siz
     return 0;
 }
 
+int c2d_host::comm_allgather2(c2d_gpu_ctx* ctx, const void* sendA, void* recvA, size_t bytesA, const void* sendB, void* recvB,
+                              size_t bytesB)
+{
+    if (!ctx->comm.comm)
+        return fail(ctx, "no communicator: call c2d_gpu_comm_init first");
+    NcclApi& api = nccl_api();
+    C2D_NCCL(ctx, api.GroupStart());
+    C2D_NCCL(ctx, api.AllGather(sendA, recvA, bytesA, ncclChar, comm_of(ctx), ctx->stream));
+    if (bytesB)
+        C2D_NCCL(ctx, api.AllGather(sendB, recvB, bytesB, ncclChar, comm_of(ctx), ctx->stream));
+    C2D_NCCL(ctx, api.GroupEnd());
+    return 0;
+}
+
 int c2d_host::comm_gatherv(c2d_gpu_ctx* ctx, const void* send, void* recvBase, const size_t* bytes, size_t strideBytes)
 {
     if (!ctx->comm.comm)
@@ -244,7 +258,7 @@ int c2d_gpu_comm_init(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world, const voi
     cm.comm = comm;
     for (auto& ev : cm.evX)
         C2D_CUDA(ctx, cudaEventCreate(&ev));
-    C2D_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&cm.hHeader), (world + 1) * 4 * sizeof(uint32_t), cudaHostAllocDefault));
+    C2D_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&cm.hHeader), ((world + 1) * 4 + 1) * sizeof(uint32_t), cudaHostAllocDefault));
     C2D_CUDA(ctx, cudaHostAlloc(reinterpret_cast<void**>(&cm.hPairCounts), (world + 1) * sizeof(uint64_t), cudaHostAllocDefault));
     return c2d_gpu_set_shard(ctx, rank, world);
 }
@@ -264,6 +278,7 @@ int c2d_gpu_comm_set_move_exchange(c2d_gpu_ctx* ctx, int on)
     if (ctx->transLog->size)
         return fail(ctx, "c2d_gpu_comm_set_move_exchange: translations are pending; switch right after a query");
     ctx->comm.exchangeMoves = on != 0;
+    ctx->comm.stride = 0; // the first exchange after a switch uses the exact protocol and learns the counts
     return 0;
 }
 

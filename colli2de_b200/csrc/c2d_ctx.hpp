@@ -164,7 +164,9 @@ struct CommState
     void* comm = nullptr;       // ncclComm_t (NCCL is loaded with dlopen: libc2d_gpu.so has no link-time NCCL dependency)
     bool exchangeMoves = false; // translation records logged on one rank are all-gathered to every rank at the frame's flush
     int resultMode = 0;         // C2D_RESULTS_*
-    DevBuf<uint32_t> dHeader;   // [world x 4] per-rank header of the move exchange: count, body mask, 0, 0
+    DevBuf<uint32_t> dHeader;   // [4] mine + [world x 4] per-rank header of the move exchange (count, body mask, 0, 0) + [1] overflow flag
+    uint32_t stride = 0;        // records per rank of the one-step exchange, agreed from the previous frame's headers (0: unknown)
+    bool fastExchanged = false; // this frame used the one-step exchange: its headers / overflow flag come back with the frame
     uint32_t* hHeader = nullptr; // pinned: [0..3] mine, [4 ..] everybody's
     DevBuf<TransRec> gathered;  // world x stride translation records
     DevBuf<PairOut> outAll;     // gathered results
@@ -350,6 +352,8 @@ int copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, uint64_t by
 int copy_host(c2d_gpu_ctx* ctx, const void* srcHost, void* dstHost, uint64_t bytes);  // pinned -> pageable, threaded
 // c2d_comm.cu (all collective over the group, enqueued on the context's stream)
 int comm_allgather(c2d_gpu_ctx* ctx, const void* send, void* recv, size_t bytesPerRank);
+// two all-gathers in one NCCL group (one launch): a small header and a payload
+int comm_allgather2(c2d_gpu_ctx* ctx, const void* sendA, void* recvA, size_t bytesA, const void* sendB, void* recvB, size_t bytesB);
 // rank r's bytes[r] bytes at `send` arrive at recvBase + r * strideBytes on every rank (one grouped ncclBroadcast per rank)
 int comm_gatherv(c2d_gpu_ctx* ctx, const void* send, void* recvBase, const size_t* bytes, size_t strideBytes);
 int comm_gather_results(c2d_gpu_ctx* ctx); // after a frame: the records of all ranks -> comm.outAll (per the result mode)

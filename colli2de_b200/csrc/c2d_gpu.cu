@@ -225,20 +225,56 @@ void member_remove(c2d_gpu_ctx* ctx, uint32_t shape, uint32_t body)
 
 namespace
 {
+// block size of the next one-step exchange: the largest count of this frame + 25 %, in steps of 4096 records
+inline uint32_t next_exchange_stride(uint32_t largestCount)
+{
+    const uint64_t want = static_cast<uint64_t>(largestCount) + largestCount / 4 + 1;
+    return static_cast<uint32_t>(std::min<uint64_t>((want + 4095) / 4096 * 4096, 0xfffff000ull));
+}
+
 // Move exchange of a multi-GPU group (c2d_gpu_comm_set_move_exchange): the frame's translation records of every rank are
 // all-gathered device to device and applied on every rank.  Collective: called by every rank's c2d_gpu_collide* flush,
 // also by ranks that logged nothing.  `local` = this rank's records in the device log, bodies = the trees they touch.
-int exchange_translations(c2d_gpu_ctx* ctx, uint32_t count, uint32_t bodies)
+// Two protocols.  Exact (first exchange, or after an overflow): all-gather of the headers, a host round trip for the counts,
+// then one broadcast per rank of exactly its records.  One-step (every later frame): the block size `stride` was agreed
+// from the previous frame's counts (+25 %), so headers and padded record blocks go out in ONE grouped NCCL launch with no
+// host round trip; the gathered headers come back to the host with the frame's other counters and size the next frame.
+int exchange_translations(c2d_gpu_ctx* ctx, uint32_t count, uint32_t bodies, bool exact)
 {
     CommState& cm = ctx->comm;
     cudaStream_t s = ctx->stream;
     const uint32_t world = ctx->shardWorld;
+    const size_t headerWords = 4 * (static_cast<size_t>(world) + 1) + 1;
     C2D_CUDA(ctx, cudaEventRecord(cm.evX[0], s));
-    C2D_CUDA(ctx, cm.dHeader.reserve(4 * (world + 1)));
+    C2D_CUDA(ctx, cm.dHeader.reserve(headerWords));
     cm.hHeader[0] = count;
     cm.hHeader[1] = bodies;
     cm.hHeader[2] = cm.hHeader[3] = 0;
     C2D_CUDA(ctx, cudaMemcpyAsync(cm.dHeader.ptr, cm.hHeader, 16, cudaMemcpyHostToDevice, s));
+    uint32_t* dOverflow = cm.dHeader.ptr + 4 * (world + 1);
+    cm.fastExchanged = false;
+    if (!exact && cm.stride > 0)
+    {
+        const uint32_t stride = cm.stride;
+        C2D_CUDA(ctx, cudaMemsetAsync(dOverflow, 0, sizeof(uint32_t), s));
+        C2D_CUDA(ctx, cm.gathered.reserve(static_cast<size_t>(stride) * world));
+        if (int rc = comm_allgather2(ctx, cm.dHeader.ptr, cm.dHeader.ptr + 4, 16, ctx->dTransLog.ptr, cm.gathered.ptr,
+                                     static_cast<size_t>(stride) * sizeof(TransRec)))
+            return rc;
+        const size_t threads = static_cast<size_t>(stride) * world;
+        C2D_TIMED(ctx, "k_apply_translates", k_apply_translates_gathered<<<blocks_for(threads, 256), 256, 0, s>>>(
+                      cm.gathered.ptr, stride, cm.dHeader.ptr + 4, world, ctx->d, dOverflow));
+        ++ctx->launches;
+        // headers + flag follow the frame home (read in pipeline_end after its synchronise)
+        C2D_CUDA(ctx, cudaMemcpyAsync(cm.hHeader + 4, cm.dHeader.ptr + 4, (4 * world + 1) * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        cm.fastExchanged = true;
+        cm.exchangeBytes = static_cast<uint64_t>(stride) * (world - 1) * sizeof(TransRec);
+        mark_dirty(ctx, C2D_DYNAMIC); // which bodies the other ranks moved is not known yet: Static is excluded by contract
+        mark_dirty(ctx, C2D_BULLET);
+        C2D_CUDA(ctx, cudaEventRecord(cm.evX[1], s));
+        cm.exchangeTimed = true;
+        return 0;
+    }
     if (int rc = comm_allgather(ctx, cm.dHeader.ptr, cm.dHeader.ptr + 4, 16))
         return rc;
     C2D_CUDA(ctx, cudaMemcpyAsync(cm.hHeader + 4, cm.dHeader.ptr + 4, 16 * world, cudaMemcpyDeviceToHost, s));
@@ -252,6 +288,7 @@ int exchange_translations(c2d_gpu_ctx* ctx, uint32_t count, uint32_t bodies)
         touched |= cm.hHeader[4 + 4 * r + 1];
     }
     cm.exchangeBytes = (total - count) * sizeof(TransRec);
+    cm.stride = next_exchange_stride(stride);
     if (stride)
     {
         // this rank's records are in dTransLog already (flush: early chunks + tail); every rank broadcasts exactly its
@@ -264,7 +301,7 @@ int exchange_translations(c2d_gpu_ctx* ctx, uint32_t count, uint32_t bodies)
             return rc;
         const size_t threads = static_cast<size_t>(stride) * world;
         C2D_TIMED(ctx, "k_apply_translates", k_apply_translates_gathered<<<blocks_for(threads, 256), 256, 0, s>>>(
-                      cm.gathered.ptr, stride, cm.dHeader.ptr + 4, world, ctx->d));
+                      cm.gathered.ptr, stride, cm.dHeader.ptr + 4, world, ctx->d, nullptr));
         ++ctx->launches;
         for (uint32_t b = 0; b < 3; ++b)
             if (touched & (1u << b))
@@ -345,15 +382,17 @@ int c2d_host::flush(c2d_gpu_ctx* ctx, bool collective)
         C2D_CUDA(ctx, ctx->dAddLog.reserve(na));
         C2D_CUDA(ctx, cudaMemcpyAsync(ctx->dAddLog.ptr, ctx->addLog->data, na * sizeof(AddRec), cudaMemcpyHostToDevice, s));
     }
-    if (ntLogged)
+    if (ntLogged || (exchange && collective))
     {
         // the chunks that went up during the caller's move loop, then the tail (in a group with the move exchange the
         // device log is this rank's send buffer)
         size_t done = std::min(ctx->transUploaded, ntLogged);
-        if (ctx->dTransLog.capacity < ntLogged)
+        // (the one-step move exchange sends `stride` records out of this buffer whatever the count)
+        const size_t needed = std::max<size_t>(ntLogged, exchange && collective ? ctx->comm.stride : 0);
+        if (ctx->dTransLog.capacity < needed)
         {
             C2D_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream));
-            C2D_CUDA(ctx, ctx->dTransLog.reserve(ntLogged));
+            C2D_CUDA(ctx, ctx->dTransLog.reserve(needed));
             done = 0;
         }
         if (done)
@@ -418,7 +457,7 @@ int c2d_host::flush(c2d_gpu_ctx* ctx, bool collective)
     }
     if (exchange && collective)
     {
-        if (int rc = exchange_translations(ctx, static_cast<uint32_t>(ntLogged), ctx->transBodies))
+        if (int rc = exchange_translations(ctx, static_cast<uint32_t>(ntLogged), ctx->transBodies, false))
             return rc;
     }
     ctx->transBodies = 0;
@@ -658,10 +697,14 @@ void launch_traverse_halo(c2d_gpu_ctx* ctx)
         return;
     // most launches have a few thousand halo shapes: a grid for laterCount would be mostly empty blocks, so the grid covers
     // a quarter of the later shapes per pass (every pass reads the count; passes beyond it exit at once)
-    const uint32_t span = std::max<uint32_t>(4096u, (sl.laterCount + 3) / 4);
-    for (uint32_t lo = 0; lo < sl.laterCount; lo += span)
+    // most frames have a few thousand halo shapes: the first pass covers twice the halo of the LAST frame (known on the host
+    // since that frame's counters came back), a second pass covers whatever could lie beyond it - its blocks read the real
+    // count on the device and exit at once
+    const uint32_t lastHalo = sl.hCounters ? sl.hCounters[kSlabHaloCount] : 0u;
+    const uint32_t span = std::min(sl.laterCount, std::max<uint32_t>(4096u, 2u * lastHalo));
+    for (uint32_t lo = 0; lo < sl.laterCount; lo = (lo == 0 ? span : sl.laterCount))
     {
-        const uint32_t hi = std::min(sl.laterCount, lo + span);
+        const uint32_t hi = lo == 0 ? span : sl.laterCount;
         C2D_TIMED(ctx, "k_traverse<halo>", (k_traverse_sync<false, true><<<blocks_for(hi - lo, 128), 128, 0, ctx->stream>>>(
                       sl.halo.ptr, sl.laterCount, lo, hi, sl.counters.ptr + kSlabHaloCount, t.n, t.nodes.ptr, ctx->d.fat, ctx->d.category,
                       0u, ctx->cand.ptr, static_cast<uint32_t>(ctx->cand.capacity), &ctx->dScratch->candCount, &ctx->dScratch->stackOverflow)));
@@ -879,6 +922,8 @@ int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
     return 0;
 }
 
+int pipeline_build(c2d_gpu_ctx* ctx);
+
 // Replays the mutation log, refreshes the trees and enqueues the first attempt; returns without waiting for the GPU.
 int pipeline_begin(c2d_gpu_ctx* ctx)
 {
@@ -895,7 +940,18 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
     if (int rc = flush(ctx, true))
         return rc;
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[1], s));
+    if (int rc = pipeline_build(ctx))
+        return rc;
+    ctx->frame.open = true;
+    ctx->frame.msEnqueued = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->frame.wall0).count();
+    return 0;
+}
 
+// Frame counters, the trees (or slab / grid / small-scene inputs) of the current boxes, then the first attempt.
+int pipeline_build(c2d_gpu_ctx* ctx)
+{
+    cudaStream_t s = ctx->stream;
+    ctx->preFitRecorded = false;
     // small scenes: all-pairs box test + one narrowphase kernel instead of the tree pipeline (launch-latency bound);
     // like the grid broadphase this needs no tree, rays build them on demand (ensure_trees)
     const size_t alive = ctx->members[0].size() + ctx->members[1].size() + ctx->members[2].size();
@@ -940,11 +996,7 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
     }
     if (ctx->out.capacity == 0)
         C2D_CUDA(ctx, ctx->out.reserve(1u << 15));
-    if (int rc = pipeline_attempt(ctx))
-        return rc;
-    ctx->frame.open = true;
-    ctx->frame.msEnqueued = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - ctx->frame.wall0).count();
-    return 0;
+    return pipeline_attempt(ctx);
 }
 
 // The frame's records in the reference's order (k_order_* in c2d_kernels.cuh): out -> order.sorted.
@@ -990,6 +1042,34 @@ int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
     {
         C2D_CUDA(ctx, cudaStreamSynchronize(s));
         C2D_CUDA(ctx, cudaGetLastError());
+        if (ctx->comm.fastExchanged)
+        {
+            // the one-step move exchange of this frame: its headers size the next frame's blocks; if a rank logged more
+            // than its block held, nothing was applied (on any rank: all see the same headers) and the frame is redone
+            // after an exchange with exact sizes
+            CommState& cm = ctx->comm;
+            cm.fastExchanged = false;
+            const uint32_t world = ctx->shardWorld;
+            uint32_t largest = 0;
+            uint64_t total = 0;
+            for (uint32_t r = 0; r < world; ++r)
+            {
+                largest = std::max(largest, cm.hHeader[4 + 4 * r]);
+                total += cm.hHeader[4 + 4 * r];
+            }
+            const bool overflow = cm.hHeader[4 + 4 * world] != 0;
+            cm.stride = next_exchange_stride(largest);
+            if (overflow)
+            {
+                ++ctx->frame.retries;
+                if (int rc = exchange_translations(ctx, cm.hHeader[0], cm.hHeader[1], true))
+                    return rc;
+                if (int rc = pipeline_build(ctx))
+                    return rc;
+                continue;
+            }
+            cm.exchangeBytes = (total - cm.hHeader[0]) * sizeof(TransRec);
+        }
         candCount = ctx->hScratch->candCount;
         pairCount = ctx->hScratch->outCount;
         if (ctx->hScratch->clipOverflow)
@@ -1441,6 +1521,8 @@ int c2d_gpu_shape_translate(c2d_gpu_ctx* ctx, uint32_t shape, float dx, float dy
     r->dx = dx;
     r->dy = dy;
     const uint32_t body = meta_body(ctx->hostMeta[shape]);
+    if (body == C2D_STATIC && ctx->comm.exchangeMoves)
+        return fail(ctx, "move exchange: translations of Static shapes are not exchanged (move them on every rank with the exchange off)");
     ctx->transBodies |= 1u << body;
     mark_dirty(ctx, body);
     if (ctx->earlyUpload && ctx->transLog->size - ctx->transUploaded >= kEarlyUploadRecords)
@@ -1473,6 +1555,8 @@ int c2d_gpu_shapes_translate(c2d_gpu_ctx* ctx, uint32_t n, const uint32_t* shape
         r->dx = dxy[2 * i];
         r->dy = dxy[2 * i + 1];
         bodies |= 1u << meta_body(ctx->hostMeta[shape]);
+        if ((bodies & (1u << C2D_STATIC)) && ctx->comm.exchangeMoves)
+            return fail(ctx, "move exchange: translations of Static shapes are not exchanged (move them on every rank with the exchange off)");
         if ((i & 0xfffu) == 0xfffu && ctx->earlyUpload && ctx->transLog->size - ctx->transUploaded >= kEarlyUploadRecords)
             if (int rc = early_upload_translations(ctx))
                 return rc;
@@ -1692,17 +1776,22 @@ int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, u
         uint64_t off, len;
     };
     const auto wave_bytes = [&](uint64_t w) { return (w + 1) * waveBytes <= total ? waveBytes : total - w * waveBytes; };
+    // a mid-size result (a rank's share of a multi-GPU frame, 4-16 MB) is cut into 6 DMA pieces instead: the 256 KB tail
+    // pieces would cover all of it, ~8 us of API calls each
+    const bool midSize = total < 4 * chunkBytes;
+    const uint64_t midChunk = ((total / 6 + (64u << 10)) >> 16) << 16;
     const auto plan = [&](uint64_t w, std::vector<Chunk>& chunks, std::vector<Unit>& units) {
         chunks.clear();
         units.clear();
         const uint64_t bytes = wave_bytes(w);
         for (uint64_t off = 0; off < bytes;)
         {
-            uint64_t len = std::min(chunkBytes, bytes - off);
-            if (w + 1 == waves && off + len + chunkBytes >= bytes) // tail region of the transfer: small DMA pieces
+            uint64_t len = std::min(midSize ? midChunk : chunkBytes, bytes - off);
+            if (!midSize && w + 1 == waves && off + len + chunkBytes >= bytes) // tail region of the transfer: small DMA pieces
                 len = std::min(tailPiece, bytes - off);
-            for (uint64_t p = 0; p < len; p += unitBytes)
-                units.push_back(Unit{off + p, std::min(unitBytes, len - p), static_cast<uint32_t>(chunks.size())});
+            const uint64_t unit = midSize ? std::min<uint64_t>(unitBytes, 256u << 10) : unitBytes;
+            for (uint64_t p = 0; p < len; p += unit)
+                units.push_back(Unit{off + p, std::min(unit, len - p), static_cast<uint32_t>(chunks.size())});
             chunks.push_back(Chunk{off, len});
             off += len;
         }
@@ -1818,15 +1907,24 @@ int c2d_gpu_collide_begin(c2d_gpu_ctx* ctx)
 
 int c2d_gpu_prefault(c2d_gpu_ctx* ctx, void* dst, uint64_t bytes)
 {
-    if (!dst || bytes < kPoolThresholdBytes)
+    const uint64_t page = 4096;
+    char* base = static_cast<char*>(dst);
+    if (!dst || bytes < (64u << 10))
         return 0;
+    if (bytes < kPoolThresholdBytes)
+    {
+        // a mid-size result (a rank's share of a multi-GPU frame): the calling thread has nothing to do until the device
+        // finishes, so it takes the ~1000 first-touch page faults itself now instead of inside the copy afterwards
+        // (measured at N = 8: 3.9 MB results took 0.4 ms longer than 4.4 MB ones, which the helpers pre-fault)
+        for (uint64_t off = 0; off < bytes; off += page)
+            *reinterpret_cast<volatile char*>(base + off) = 0;
+        return 0;
+    }
     c2d_host::CopyPool* pool = copy_pool(ctx);
     advise_huge_pages(dst, bytes);
     const unsigned workers = pool->helpers();
     if (workers == 0)
         return 0;
-    const uint64_t page = 4096;
-    char* base = static_cast<char*>(dst);
     pool->launch([=](unsigned index) {
         // interleaved 2 MB stripes: neighbouring threads fault neighbouring regions (and whole huge pages with THP)
         const uint64_t stripe = 2ull << 20;

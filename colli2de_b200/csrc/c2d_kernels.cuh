@@ -145,11 +145,25 @@ __global__ void __launch_bounds__(256) k_apply_translates(const TransRec* __rest
 
 // The same over the all-gathered records of a multi-GPU group (c2d_gpu.cu: flush with the move exchange on):
 // `world` blocks of `stride` records, block r holding header[4 * r] valid ones.
+// overflow (may be null): the one-step exchange sized every rank's block from the PREVIOUS frame's counts; if a rank logged
+// more records than fit, nothing is applied anywhere, the flag goes up and the host repeats the exchange with exact sizes.
 __global__ void __launch_bounds__(256) k_apply_translates_gathered(const TransRec* __restrict__ gathered, uint32_t stride,
                                                                    const uint32_t* __restrict__ header, uint32_t world,
-                                                                   ShapeArrays s)
+                                                                   ShapeArrays s, uint32_t* overflow)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (overflow)
+    {
+        bool any = false;
+        for (uint32_t q = 0; q < world; ++q)
+            any = any || header[4 * q] > stride;
+        if (any)
+        {
+            if (i == 0)
+                *overflow = 1;
+            return;
+        }
+    }
     const uint32_t r = i / stride, k = i - r * stride;
     if (r >= world || k >= header[4 * r])
         return;

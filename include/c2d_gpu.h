@@ -171,10 +171,14 @@ int c2d_gpu_comm_unique_id(void* out_id128);
 int c2d_gpu_comm_init(c2d_gpu_ctx* ctx, uint32_t rank, uint32_t world, const void* id128);
 int c2d_gpu_comm_destroy(c2d_gpu_ctx* ctx);
 /* Move exchange (off by default = every rank logs every move itself).  On: each rank logs only the translations
- * (c2d_gpu_shape_translate / c2d_gpu_shapes_translate) of the entities IT drives; the next c2d_gpu_collide* all-gathers
- * the 12-byte records of all ranks over NVLink (ncclAllGather, device to device) and applies them everywhere, so the
- * host-to-device upload of a frame shrinks to 1 / world per rank.  Contract: an entity is translated by one rank and at
- * most once per frame; every other mutation stays replicated and is applied BEFORE the frame's translations; while
+ * (c2d_gpu_shape_translate / c2d_gpu_shapes_translate) of the entities IT drives; the next c2d_gpu_collide* exchanges the
+ * 12-byte records of all ranks over NVLink, device to device, straight out of each rank's device log, and applies them
+ * everywhere, so the host-to-device upload of a frame shrinks to 1 / world per rank.  The first exchange all-gathers the
+ * counts, waits for them on the host and broadcasts exactly each rank's records; every later frame sends fixed-size
+ * blocks (the previous frame's largest count + 25 %) and their headers in ONE grouped NCCL launch without a host round
+ * trip - if a rank logged more than its block holds, no rank applies anything and the frame is redone with exact sizes.
+ * Contract: an entity is translated by one rank and at most once per frame; Static shapes are not translated while the
+ * exchange is on; every other mutation stays replicated and is applied BEFORE the frame's translations; while
  * translations are pending only c2d_gpu_collide* may flush them (it is the collective). */
 int c2d_gpu_comm_set_move_exchange(c2d_gpu_ctx* ctx, int on);
 /* Where the 84-byte records of a frame end up: C2D_RESULTS_LOCAL every rank keeps its share; C2D_RESULTS_ALL every rank

@@ -100,6 +100,36 @@ def main():
             want = [mine.tobytes() if rank != 0 else ref.get_transforms(probe).tobytes()]
             dist.broadcast_object_list(want, src=0)
             assert mine.tobytes() == want[0], "host transforms differ from the reference after a move exchange"
+    # one-step exchange (blocks sized from the previous frame) and its overflow path: two ordinary frames, then rank 0
+    # suddenly drives EVERY entity (its count exceeds the agreed block: nothing is applied, the frame is redone exactly),
+    # then a frame in which only the last rank moves anything
+    b.group_options(results=capi.RESULTS_ROOT, exchange=True)
+    ids = movable[alive]
+    for step in range(5):
+        dd = scenes.jitter(rng, len(ids), 0.5)
+        lo, hi = (len(ids) * rank) // world, (len(ids) * (rank + 1)) // world
+        if step == 2:
+            lo, hi = (0, len(ids)) if rank == 0 else (0, 0)
+        if step == 3:
+            lo, hi = (0, len(ids)) if rank == world - 1 else (0, 0)
+        b.move_translate(ids[lo:hi], dd[lo:hi])
+        print(f"[rank {rank}] one-step exchange frame {step}: {hi - lo} moves logged", file=sys.stderr, flush=True)
+        got = b.get_colliding_pairs()
+        print(f"[rank {rank}] frame {step} returned {len(got)} records, retries {int(b.stats()['retries'])}", file=sys.stderr, flush=True)
+        st = capi.comm_stats(ctx)
+        assert st["exchange_bytes"] == 12 * (len(ids) - (hi - lo)), (step, st)
+        # the host mirror of the entities other ranks moved is refreshed by the first call that reads a transform; that has
+        # to happen before this rank logs its next moves (the runner reads bullets' transforms while it moves them)
+        b.get_transforms(ids[:1])
+        retries = [None] * world
+        dist.all_gather_object(retries, int(b.stats()["retries"]))
+        assert all(r >= 1 for r in retries) if step == 2 else True, (step, retries)  # every rank redid the overflowing frame
+        if rank == 0:
+            ref.move_translate(ids, dd)
+            res = P.compare_pairs(which, ref, idx, ref.get_colliding_pairs(), got, max_ambiguous=20)
+            assert res["not_bit_identical"] == 0, res
+            totals["expected"] += res["expected"]
+    b.group_options(results=capi.RESULTS_LOCAL, exchange=False)
     # batched rayCast with ray sharding: every rank is handed the same batch and casts its contiguous share; the per-ray
     # lists of the ranks concatenate to the reference's rayCast results
     ray4, inf = scenes.rays(1200, 1700.0 * (n_dyn / 120000.0) ** 0.5, seed=31, finite_len=60.0)

@@ -1,6 +1,7 @@
 """GPU, >= 2 devices: the multi-GPU group on real ranks over NCCL (tests/multigpu_check.py under torchrun).  Skipped on a
 one-GPU box; the same decomposition with emulated ranks runs in tests/test_gpu_sharding.py."""
 import os
+import signal
 import socket
 import subprocess
 import sys
@@ -30,6 +31,13 @@ def test_group_on_real_ranks(world):
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(REPO, "tests", "multigpu_check.py")]
-    r = subprocess.run(cmd, cwd=REPO, capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert "MULTIGPU_OK" in r.stdout
+    # own session: on a timeout the whole process group goes (a killed torchrun would leave its ranks spinning on the GPUs)
+    proc = subprocess.Popen(cmd, cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, start_new_session=True)
+    try:
+        out, err = proc.communicate(timeout=300)
+    except subprocess.TimeoutExpired:
+        os.killpg(proc.pid, signal.SIGKILL)
+        out, err = proc.communicate()
+        raise AssertionError("multigpu_check.py timed out\n" + out[-2000:] + err[-3000:])
+    assert proc.returncode == 0, out[-3000:] + err[-3000:]
+    assert "MULTIGPU_OK" in out
