@@ -284,7 +284,7 @@ int c2d_gpu_collide_device(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats*
  * Helper threads: min(8, hardware threads / 2) including the caller (with torchrun's LOCAL_WORLD_SIZE = R > 1:
  * min(8, hardware threads / R)), C2D_GPU_COPY_THREADS overrides
  * (1 = none);
- * results below 4 MB are copied by the calling thread alone.  Records are the same as c2d_gpu_collide's. */
+ * results below 1 MB are copied by the calling thread alone.  Records are the same as c2d_gpu_collide's. */
 int c2d_gpu_collide_begin(c2d_gpu_ctx* ctx);
 int c2d_gpu_prefault(c2d_gpu_ctx* ctx, void* dst, uint64_t bytes);
 int c2d_gpu_collide_end(c2d_gpu_ctx* ctx, uint64_t* out_count, c2d_gpu_stats* stats);
