@@ -13,7 +13,8 @@ scripts/compare_tests.sh (compare_tests_parse.py / compare_tests_format.py) can 
 
 Timing: the clock brackets the same Registry calls as the reference's BENCHMARK_FUNCTION (reset excluded); queries are
 timed inside the native runner, insert/move batches around one ctypes call that loops the per-entity API natively.
-Catch2 picks its own sample count; here it is --samples (default 10), each sample one call like in the reference.
+Catch2 picks its own sample count and warms the function up first; here it is --samples (default 10) after --warmup
+(default 1) untimed calls, each sample one call like in the reference.
 The B200 Registry defers device work to the next query, so "Insert"/"Move" measure its host-side logging only, and
 each query sample that follows a reset also pays the replay of that log.
 """
@@ -62,13 +63,19 @@ def xf3(centres):
 
 
 class Report:
-    def __init__(self, samples, name_filter):
-        self.samples, self.filter, self.rows = samples, name_filter, []
+    def __init__(self, samples, name_filter, warmup=1):
+        self.samples, self.filter, self.rows, self.warmup = samples, name_filter, [], warmup
 
     def run(self, name, threshold_ms, func, reset=None):
         if self.filter not in name:
             return
         times = []
+        # Catch2 runs the benchmarked function for a warm-up period (benchmark-warmup-time, 100 ms by default) before it
+        # samples; here: --warmup untimed calls (default 1)
+        for _ in range(self.warmup):
+            if reset:
+                reset()
+            func()
         for _ in range(self.samples):
             if reset:
                 reset()
@@ -204,12 +211,13 @@ def main():
     ap.add_argument("--backend", default="b200", choices=["b200", "reference", "oracle"])
     ap.add_argument("--out", default="bench_out", help="folder of the benchmarks--*.md file (tests/main.cpp:42)")
     ap.add_argument("--samples", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=1, help="untimed calls before the samples (Catch2's warm-up phase)")
     ap.add_argument("--seed", type=int, default=42)
     ap.add_argument("--filter", default="", help="substring of the benchmark name (the reference's --filter-benchmark)")
     args = ap.parse_args()
     if not harness.available(args.backend):
         sys.exit(f"backend {args.backend!r} is not built (python colli2de_b200/build.py)")
-    rep = Report(args.samples, args.filter)
+    rep = Report(args.samples, args.filter, args.warmup)
     for bench in (bench_insert, bench_move, bench_all_pairs, bench_single_queries, bench_bullet_raycast):
         bench(rep, args.backend, args.seed)
     path = rep.export(args.out)
