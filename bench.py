@@ -20,18 +20,24 @@ is moved by a jitter in U(-0.5, 0.5)^2, then getCollidingPairs runs.
   * `parity`: before the timed regions two frames are compared with the UNMODIFIED reference (oracle/_ref) on rank 0 —
     sorted tuple set, manifolds, orientation-ambiguous pairs classified (tests/parity.py).  At N > 1 the records of all
     ranks are gathered to rank 0 by the library (C2D_RESULTS_ROOT) for it.
-  * `roofline`: the dominant kernel by live CUDA-event time (c2d_gpu_set_profiling), algorithmic bytes per
-    launch as defined in DESIGN.md section "Roofline", against MEASURED_PEAKS.json hbm_gbs.
+  * `roofline`: the dominant kernel (chosen from warm-up frames profiled with CUDA events around every kernel), its
+    average launch duration measured with CUDA events around each of its launches INSIDE the timed region
+    (c2d_gpu_set_profiling + c2d_gpu_set_profile_filter: events around every kernel would cost 0.12 ms per frame),
+    algorithmic bytes per launch as defined in DESIGN.md section 3, against MEASURED_PEAKS.json hbm_gbs; `traffic` from the
+    newest profiles/*_ncu_traffic.json.
   * `cpu_baseline`: the UNMODIFIED reference (oracle/_ref, compiled from /root/reference by oracle/Makefile)
     timed on this host on a bounded sample (same scene, a few frames).
 Reference arm (--impl reference): the reference's own CPU getCollidingPairs on the same scene, K steps.
 
 Multi-GPU (torchrun, one rank per GPU): the decomposition lives in the library (include/c2d_gpu.h "multi-GPU").  Every
-rank holds a Registry of the whole scene joined to one NCCL group (c2d_gpu_comm_init); each frame a rank sorts, builds
-and traverses only its Morton-key slab of the Dynamic tree (+ halo) and returns its share of the pairs.  Default
-`scaling` is "strong": the metric's fixed 1 M-shape scene on N GPUs.  `--scaling weak` runs an N-times larger world.
-In the e2e loop every rank logs the moves of 1/N of the entities and the library all-gathers the 12-byte records over
-NVLink (c2d_gpu_comm_set_move_exchange) before it replays them.
+rank holds a Registry of the whole scene joined to one NCCL group (Registry::joinGroup); each frame a rank refits and
+traverses only its slab of the Morton order of the Dynamic tree, lets the halo shapes of higher ranks query it, and
+returns its share of the pairs.  Default `scaling` is "strong": the metric's fixed 1 M-shape scene on N GPUs.
+`--scaling weak` runs an N-times larger world.  In the e2e loop every rank calls moveEntity for 1/N of the entities and
+the library exchanges the 12-byte records over NVLink (Registry::setGroupMoveExchange) inside getCollidingPairs.
+
+--workload cfg5-rays: 1 M batched rays (half finite, half infinite) against a 4 M-shape scene, rays/s; device-resident =
+c2d_gpu_raycast_begin (hits stay in HBM), e2e = Registry::rayCastBatch with host buffers; N > 1 = ray sharding.
 """
 from __future__ import annotations
 

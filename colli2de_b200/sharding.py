@@ -1,4 +1,6 @@
-"""Multi-GPU plumbing of the collision query path (one process per GPU, torch.distributed).
+"""Application-level multi-GPU helpers of round 1 (one process per GPU, torch.distributed), kept for the tests that
+exercise the ghost-copy owner rule and the record gather.  The decomposition itself now lives INSIDE the library
+(include/c2d_gpu.h "multi-GPU": c2d_gpu_comm_init, Morton slabs, move exchange, result gather) - bench.py uses that.
 
 The path shards by space: each rank owns one Morton-rank slab of the query leaves (the C ABI's
 ``c2d_gpu_set_shard(rank, world)`` uses :func:`slab_bounds`) and emits only the pairs whose query leaf it owns;
