@@ -145,6 +145,7 @@ int c2d_host::comm_gatherv(c2d_gpu_ctx* ctx, const void* send, void* recvBase, c
 // exactly once per frame whatever its local overflow retries were.
 int c2d_host::comm_gather_results(c2d_gpu_ctx* ctx)
 {
+    NvtxRange nvtx("c2d gather results (NCCL)");
     CommState& cm = ctx->comm;
     cm.resultsGathered = false;
     cm.gatherBytes = 0;

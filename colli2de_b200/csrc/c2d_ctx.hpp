@@ -6,6 +6,8 @@
 #include "../../include/c2d_gpu.h"
 #include "c2d_copy_pool.hpp"
 
+#include <nvtx3/nvToolsExt.h> // header-only: ranges cost nothing unless a profiler is attached
+
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -16,6 +18,16 @@
 namespace c2d_host
 {
 using namespace c2d_dev;
+
+// NVTX range of one pipeline stage (the reference has no tracing; timelines of this library show
+// flush / build / traverse / narrow / copy-out per frame in Nsight Systems)
+struct NvtxRange
+{
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 // ---- small RAII helpers ---------------------------------------------------------------------------
 template <typename T>

@@ -343,6 +343,7 @@ int early_upload_translations(c2d_gpu_ctx* ctx)
 // collective: this flush is the one inside c2d_gpu_collide*, which every rank of a group calls in step
 int c2d_host::flush(c2d_gpu_ctx* ctx, bool collective)
 {
+    NvtxRange nvtx("c2d flush (mutation log -> device, refit)");
     const bool exchange = ctx->comm.exchangeMoves && ctx->comm.comm && ctx->shardWorld > 1;
     if (exchange && !collective && ctx->transLog->size)
         return fail(ctx, "translations are pending while the move exchange is on: only c2d_gpu_collide* (the collective) may "
@@ -584,6 +585,7 @@ int build_tree(c2d_gpu_ctx* ctx, int body)
 // Nothing here waits for the device.
 int update_slab(c2d_gpu_ctx* ctx)
 {
+    NvtxRange nvtx("c2d slab (order / refit / halo)");
     SlabState& sl = ctx->slab;
     TreeBuf& t = ctx->slabTree;
     cudaStream_t s = ctx->stream;
@@ -796,6 +798,7 @@ inline uint64_t result_count(const c2d_gpu_ctx* ctx)
 // stream, the frame counters follow in an asynchronous copy to the pinned FrameScratch.
 int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
 {
+    NvtxRange nvtx("c2d traverse + narrowphase (enqueue)");
     cudaStream_t s = ctx->stream;
     if (ctx->frame.smallScene)
     {
@@ -950,6 +953,7 @@ int pipeline_begin(c2d_gpu_ctx* ctx)
 // Frame counters, the trees (or slab / grid / small-scene inputs) of the current boxes, then the first attempt.
 int pipeline_build(c2d_gpu_ctx* ctx)
 {
+    NvtxRange nvtx("c2d build (trees / slab)");
     cudaStream_t s = ctx->stream;
     ctx->preFitRecorded = false;
     // small scenes: all-pairs box test + one narrowphase kernel instead of the tree pipeline (launch-latency bound);
@@ -1033,6 +1037,7 @@ int order_results(c2d_gpu_ctx* ctx, uint32_t n)
 // (boxes and trees are unchanged).
 int pipeline_end(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats)
 {
+    NvtxRange nvtx("c2d wait for the frame");
     if (!ctx->frame.open)
         return fail(ctx, "c2d_gpu_collide_end without c2d_gpu_collide_begin");
     ctx->frame.open = false;
@@ -1742,6 +1747,7 @@ c2d_host::CopyPool* copy_pool(c2d_gpu_ctx* ctx)
 // (1 MB chunks = units: 0.85-0.93 ms; 8 MB: 0.83 ms; 256 KB: 1.2 ms, issue bound).
 int c2d_host::copy_out(c2d_gpu_ctx* ctx, const void* srcDevice, void* dstHost, uint64_t total)
 {
+    NvtxRange nvtx("c2d copy-out (device -> caller memory)");
     if (!total)
         return 0;
     cudaStream_t s = ctx->stream;

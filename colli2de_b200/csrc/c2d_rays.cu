@@ -1101,6 +1101,7 @@ int raycast_chunk(const RayRun& run, const RayIn* dr, uint32_t m, c2d_host::DevB
 // rb.resultOnHost) or, ray-ordered, in the per-chunk device buffers rb.chunkOut / rb.chunkCount.
 int raycast_run(c2d_gpu_ctx* ctx, uint32_t n, const c2d_ray* rays, bool firstHitOnly, c2d_gpu_stats* stats)
 {
+    NvtxRange nvtx("c2d rayCast batch");
     const auto wall0 = std::chrono::steady_clock::now();
     cudaSetDevice(ctx->device);
     cudaStream_t s = ctx->stream;
