@@ -33,7 +33,9 @@ Multi-GPU (torchrun, one rank per GPU): the decomposition lives in the library (
 rank holds a Registry of the whole scene joined to one NCCL group (Registry::joinGroup); each frame a rank refits and
 traverses only its slab of the Morton order of the Dynamic tree, lets the halo shapes of higher ranks query it, and
 returns its share of the pairs.  Default `scaling` is "strong": the metric's fixed 1 M-shape scene on N GPUs.
-`--scaling weak` runs an N-times larger world.  In the e2e loop every rank calls moveEntity for 1/N of the entities and
+The same invocation then measures a second line, `weak`: an N-times larger world (N x the scene, mirrored on every rank)
+through the same library path, device-resident loop only (`--no-weak-line` skips it; `--scaling weak` runs the whole
+bench on the larger world instead).  In the e2e loop every rank calls moveEntity for 1/N of the entities and
 the library exchanges the 12-byte records over NVLink (Registry::setGroupMoveExchange) inside getCollidingPairs.
 
 --workload cfg5-rays: 1 M batched rays (half finite, half infinite) against a 4 M-shape scene, rays/s; device-resident =
@@ -562,6 +564,52 @@ def run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak):
     return out
 
 
+def run_weak_line(args, rank, world, local):
+    """Second line of a multi-GPU run: the same in-library decomposition on an N-times larger world
+    (weak scaling), device-resident loop only.  Returns the sub-object `weak` of the JSON line (rank 0) or None."""
+    import torch
+    import torch.distributed as dist
+
+    from colli2de_b200 import capi
+    from tests import harness as H
+
+    scene, n_dyn, n_sta = build_scene(args.workload, world)
+    b = H.Backend("b200")
+    scenes.populate(b, scene)
+    dyn = np.arange(n_dyn, dtype=np.uint32)
+    ctx = b.native_context()
+    b.group_join_torch()
+    capi.set_rebuild_period(ctx, args.rebuild_period)
+    K, W = min(args.steps, 10), max(args.warmup, 3)
+    rng = scenes.LCG(2024)
+    handles = [b.stage_translations(dyn, scenes.jitter(rng, n_dyn, 0.5)) for _ in range(W + K)]
+    for h in handles[:W]:
+        b.apply_staged(h)
+        b.count_pairs_device()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pairs, sums, _ = b.run_staged_frames(handles[W:])
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0, float(pairs), -float(pairs)], dtype=torch.float64, device="cuda")
+    mx = t.clone()
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    elapsed, pairs_all, pairs_max, pairs_min = float(mx[0]), float(t[1]), float(mx[1]), -float(mx[2])
+    for h in handles:
+        b.release_staged(h)
+    b.group_leave()
+    b.close()
+    if rank != 0:
+        return None
+    return {"scaling": "weak", "value": pairs_all / elapsed, "unit": UNIT, "ms_per_step": 1e3 * elapsed / K, "steps": K, "warmup": W,
+            "workload": workload_label(args.workload, n_dyn, n_sta) + f" = {world} x the metric's scene in one world, mirrored on every rank",
+            "pairs_per_frame": pairs_all / K, "pairs_per_frame_per_rank_min_max": [pairs_min / K, pairs_max / K],
+            "rank0_ms_device": sums["ms_device"] / K,
+            "note": "device-resident loop only (moves staged in HBM); same library path as the strong line above"}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # cfg 5: batched rayCast, 1 M rays (odd: finite, length 50; even: infinite) against a 4 M-shape scene
 RAY_METRIC = "batched rayCast rays/sec, 1M rays vs 4M shapes (ms/batch = ms_per_step)"
@@ -768,6 +816,8 @@ def main():
     ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
                     help="multi-GPU mode: strong (default) = the metric's fixed workload on N GPUs; weak = an N-times larger "
                          "world at the same density.  Either way the library cuts the Dynamic tree into Morton-key slabs")
+    ap.add_argument("--no-weak-line", action="store_true",
+                    help="N > 1, strong scaling: skip the second measurement (`weak`: an N-times larger world)")
     ap.add_argument("--parity-frames", type=int, default=2,
                     help="frames compared with the unmodified reference on rank 0 before the timed regions (0 = skip)")
     ap.add_argument("--grid-cell", type=int, default=0,
@@ -812,6 +862,11 @@ def main():
     weak = world > 1 and args.scaling == "weak"
     scene, n_dyn, n_sta = build_scene(args.workload, world if weak else 1)
     out = run_b200(args, scene, n_dyn, n_sta, rank, world, local, weak)
+    if world > 1 and not weak and not args.no_weak_line:
+        del scene
+        second = run_weak_line(args, rank, world, local)
+        if rank == 0:
+            out["weak"] = second
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             r = run_reference(args, scene, n_dyn, as_baseline=True)
