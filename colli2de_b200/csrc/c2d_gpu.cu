@@ -737,8 +737,8 @@ int c2d_host::ensure_trees(c2d_gpu_ctx* ctx)
 namespace
 {
 
-// Traversal of the query leaves [lo, hi) of tree `q` against tree `t`.  rejectLeaf: leaf links carrying any of these
-// bits are skipped (halo leaves of a slab tree, see c2d_comm.cu).
+// Traversal of the query leaves [lo, hi) of tree `q` against tree `t` on stream `st` (default: the context's stream).
+// rejectLeaf: leaf links carrying any of these bits are skipped (no caller uses it at present).
 template <bool SELF>
 void launch_traverse_trees(c2d_gpu_ctx* ctx, const TreeBuf& q, const TreeBuf& t, uint32_t lo, uint32_t hi, uint32_t rejectLeaf,
                            cudaStream_t st = nullptr)

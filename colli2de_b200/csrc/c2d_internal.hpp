@@ -70,9 +70,10 @@ struct ShapeArrays
 
 // ---- LBVH node: both children's boxes live in the parent so one 64 B read serves both tests -------------
 // child link of a node: >= 0 internal node index; < 0 (bit 31) a leaf that carries its ShapeId in the low 30 bits, so
-// emitting a candidate needs no dependent load of the sorted id array; bit 30 marks a halo leaf of a multi-GPU slab tree
+// emitting a candidate needs no dependent load of the sorted id array; bit 30 is a spare leaf flag (unused: the
+// traversal kernels can skip leaves by flag, see rejectLeaf)
 constexpr uint32_t kLeafBit = 0x80000000u;
-constexpr uint32_t kLeafGhost = 0x40000000u; // also carried by the sorted value array of a slab tree
+constexpr uint32_t kLeafGhost = 0x40000000u; // spare leaf flag
 constexpr uint32_t kLeafIdMask = 0x3fffffffu;
 __host__ __device__ inline uint32_t leaf_shape(int link) { return static_cast<uint32_t>(link) & kLeafIdMask; }
 

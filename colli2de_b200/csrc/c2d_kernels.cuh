@@ -599,8 +599,8 @@ __global__ void __launch_bounds__(128)
 //     become two full-mask ballots,
 //   * candidates are staged in a per-warp shared-memory buffer and flushed 32 at a time: one global atomic and one
 //     coalesced 256-byte store per 32 candidates instead of one contended same-address atomic per (partial) warp emit.
-// rejectLeaf: leaf links with any of these bits are skipped (kLeafGhost: halo leaves of a multi-GPU slab tree when the
-// query side is replicated on every rank, i.e. Bullet x Dynamic).
+// rejectLeaf: leaf links with any of these bits are skipped.  No tree of the current decomposition flags its leaves (the
+// first slab trees of round 2 carried their halo leaves, bit 30); every launch passes 0.
 constexpr int kStageCap = 96; // < 32 staged + <= 64 new entries per iteration
 
 __device__ __forceinline__ void stage_flush32(uint2* stage, int& staged, uint2* __restrict__ out, uint32_t capacity,
