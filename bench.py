@@ -822,7 +822,7 @@ def main():
                     help="frames compared with the unmodified reference on rank 0 before the timed regions (0 = skip)")
     ap.add_argument("--grid-cell", type=int, default=0,
                     help="> 0: use Registry<Grid>(cell) = the uniform-grid sort-and-sweep broadphase instead of the LBVH")
-    ap.add_argument("--rebuild-period", type=int, default=4,
+    ap.add_argument("--rebuild-period", type=int, default=8,
                     help="LBVH topology rebuilt every N-th frame, bottom-up refit in between (1 = every frame)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -300,7 +300,7 @@ struct c2d_gpu_ctx
     c2d_host::SlabState slab;
     c2d_host::CommState comm;
     int traverseVariant = 1;    // 0: divergent emit (k_traverse), 1: convergent loop + staged appends (k_traverse_sync)
-    uint32_t rebuildPeriod = 4; // LBVH topology rebuilt every N-th dirty frame, refit in between
+    uint32_t rebuildPeriod = 8; // LBVH topology rebuilt every N-th dirty frame, refit in between
     uint64_t mutationEpoch = 0;    // bumped by every entry point that changes what a query would answer
     uint32_t smallSceneMax = 8192; // <= this many live shapes: all-pairs broadphase (c2d_gpu_set_small_scene_limit)
 

@@ -125,8 +125,8 @@ int c2d_gpu_clear(c2d_gpu_ctx* ctx);
 /* PartitioningMethod::None -> LBVH; PartitioningMethod::Grid(cellSize) -> uniform grid (BroadPhaseTree.hpp:96). */
 int c2d_gpu_set_broadphase(c2d_gpu_ctx* ctx, int mode, uint32_t cell_size);
 /* LBVH maintenance policy: the topology (Morton sort + Karras links) of a tree whose membership did not change is
- * rebuilt every `frames`-th dirty frame and only refit (exact boxes, bottom-up) in between.  1 = rebuild every
- * frame.  Default 4.  Results do not depend on it. */
+ * rebuilt every `frames`-th dirty frame and only refit in between (leaf boxes exact, see c2d_gpu_set_incremental_refit).
+ * 1 = rebuild every frame.  Default 8.  Results do not depend on it. */
 int c2d_gpu_set_rebuild_period(c2d_gpu_ctx* ctx, uint32_t frames);
 /* A counter bumped by every call that changes what a query would answer (add / remove / activate / ghost / translate /
  * move / apply_staged / clear / write_boxes).  Equal epochs = identical answers: lets a host layer memoise query results
