@@ -6,6 +6,8 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <span>
+#include <vector>
 #include <cstdlib>
 #include <sstream>
 #include <string>
@@ -108,6 +110,24 @@ void scenario(MakeId id)
         // the bullet's previous transform travelled too: the sweep still hits entity 3
         auto again = loaded.getCollidingPairs();
         CHECK(std::any_of(again.begin(), again.end(), [&](const auto& c) { return c.entityA == id(4) && c.entityB == id(3); }));
+    }
+    // extensions with every id type: batched moves / teleports (one pass), the reference's result order
+    {
+        const std::vector<Id> ids{id(3), id(1)}; // (not the bullet: a move would end the sweep the expected pairs come from)
+        const std::vector<Translation> back{Translation{-0.25f, 0.0f}, Translation{0.0f, 0.5f}};
+        const Transform before3 = reg.getEntityTransform(id(3)), before1 = reg.getEntityTransform(id(1));
+        reg.moveEntities(ids, back);
+        CHECK(reg.getEntityTransform(id(3)).translation == before3.translation + Vec2(-0.25f, 0.0f));
+        CHECK(reg.getEntityTransform(id(1)).translation == before1.translation + Vec2(0.0f, 0.5f));
+        const std::vector<Translation> home{before3.translation, before1.translation};
+        reg.teleportEntities(std::span<const Id>(ids), std::span<const Translation>(home));
+        CHECK(reg.getEntityTransform(id(3)).translation == before3.translation);
+        reg.setDeterministicOrder(true);
+        const auto ordered = reg.getCollidingPairs();
+        CHECK(ordered.size() == pairs.size());
+        for (size_t k = 1; k < ordered.size(); ++k) // same group here (Bullet x ...): ascending (shapeA, shapeB) inside a group
+            CHECK(ordered[k - 1].shapeA != ordered[k].shapeA || ordered[k - 1].shapeB < ordered[k].shapeB);
+        reg.setDeterministicOrder(false);
     }
     Registry<Id> moved = std::move(reg);
     CHECK(moved.size() == 3 && moved.getCollidingPairs().size() == pairs.size());
