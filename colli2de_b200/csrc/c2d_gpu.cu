@@ -874,7 +874,6 @@ int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
     const uint32_t cap = static_cast<uint32_t>(ctx->cand.capacity);
     const uint32_t grid = 148 * 4;
     C2D_TIMED(ctx, "k_bin_count", k_bin_count<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch));
-    C2D_TIMED(ctx, "k_bin_scan", k_bin_scan<<<1, 32, 0, s>>>(ctx->dScratch));
     C2D_TIMED(ctx, "k_bin_scatter", k_bin_scatter<<<grid, 256, 0, s>>>(ctx->cand.ptr, cap, ctx->d.meta, ctx->dScratch, ctx->binned.ptr));
     // the polygon bin (8 lanes per pair) and the other bins are disjoint slices of the binned list with their own hit
     // counters and output ranges: the two filter kernels, and later the two manifold kernels, run side by side
@@ -898,14 +897,14 @@ int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
     if (int rc = fork())
         return rc;
     const bool bullets = !ctx->members[C2D_BULLET].empty();
+    constexpr uint32_t kFilterBlocks = 148 * 16; // per filter kernel; the last of the 2 x kFilterBlocks blocks scans the hit counts
     if (bullets)
-        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<true><<<148 * 16, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
+        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<true><<<kFilterBlocks, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr, 2 * kFilterBlocks));
     else
-        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<false><<<148 * 16, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr));
-    C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<148 * 16, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr));
+        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<false><<<kFilterBlocks, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr, 2 * kFilterBlocks));
+    C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<kFilterBlocks, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr, 2 * kFilterBlocks));
     if (int rc = join())
         return rc;
-    C2D_TIMED(ctx, "k_hit_scan", k_hit_scan<<<1, 32, 0, s>>>(ctx->dScratch));
     if (int rc = fork())
         return rc;
     if (bullets)
@@ -918,7 +917,7 @@ int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
                                      static_cast<uint32_t>(ctx->out.capacity)));
     if (int rc = join())
         return rc;
-    ctx->launches += 8;
+    ctx->launches += 6;
     C2D_CUDA(ctx, cudaEventRecord(ctx->ev[4], s));
     C2D_CUDA(ctx, cudaMemcpyAsync(ctx->hScratch, ctx->dScratch, sizeof(FrameScratch), cudaMemcpyDeviceToHost, s));
     ctx->frame.d2h += sizeof(FrameScratch);

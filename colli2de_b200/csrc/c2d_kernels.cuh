@@ -888,6 +888,45 @@ __device__ __forceinline__ int pair_bin(uint32_t ma, uint32_t mb)
     return mode * CORE_COUNT + core_of(static_cast<int>(meta_type(ma)), static_cast<int>(meta_type(mb)));
 }
 
+// "Last block done" (the threadFenceReduction pattern): every thread that published results with global atomics fences,
+// the block synchronises, one thread takes a ticket; the block that draws the last of `totalBlocks` tickets sees every
+// other block's results and runs the tiny serial step that used to be a kernel of its own (k_bin_scan, k_hit_scan: one
+// thread each, ~5 us of launch latency on the critical path of a 0.65 ms frame).  Call with the whole block converged.
+__device__ __forceinline__ bool last_block_done(FrameScratch* fs, uint32_t totalBlocks)
+{
+    __shared__ bool isLast;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0)
+        isLast = atomicAdd(&fs->ticket, 1u) == totalBlocks - 1;
+    __syncthreads();
+    return isLast;
+}
+
+__device__ __forceinline__ void scan_bins(FrameScratch* fs)
+{
+    uint32_t run = 0;
+    for (int b = 0; b < 16; ++b)
+    {
+        fs->binOffset[b] = run;
+        run += atomicAdd(&fs->binCount[b], 0u); // through L2: the other blocks' atomics are there
+    }
+    fs->ticket = 0;
+}
+
+__device__ __forceinline__ void scan_hits(FrameScratch* fs)
+{
+    uint32_t run = 0;
+    for (int b = 0; b < 16; ++b)
+    {
+        fs->hitBase[b] = run;
+        run += atomicAdd(&fs->hitCount[b], 0u);
+    }
+    fs->hitBase[16] = run;
+    fs->outCount = run;
+    fs->ticket = 0;
+}
+
 __global__ void __launch_bounds__(256) k_bin_count(const uint2* __restrict__ cand, uint32_t capacity,
                                                    const uint32_t* __restrict__ meta, FrameScratch* fs)
 {
@@ -904,9 +943,12 @@ __global__ void __launch_bounds__(256) k_bin_count(const uint2* __restrict__ can
     __syncthreads();
     if (threadIdx.x < 16 && sh[threadIdx.x])
         atomicAdd(&fs->binCount[threadIdx.x], sh[threadIdx.x]);
+    // the last block turns the counts into offsets (was: k_bin_scan)
+    if (last_block_done(fs, gridDim.x) && threadIdx.x == 0)
+        scan_bins(fs);
 }
 
-__global__ void k_bin_scan(FrameScratch* fs)
+__global__ void k_bin_scan(FrameScratch* fs) // (kept for reference; the pipeline no longer launches it)
 {
     if (threadIdx.x == 0)
     {
@@ -1156,9 +1198,12 @@ __device__ __forceinline__ void run_sweeps(const SweepTodo* queue, int count, co
 }
 
 // BULLETS = false: the scene holds no Bullet shape, the sweep code (and its registers: 96 -> occupancy 28 %) is compiled out.
+// scanBlocks: the number of blocks of k_narrow_filter AND k_narrow_filter_pp of this frame (they run side by side); the
+// block that finishes last among all of them turns the hit counts into output offsets (was: k_hit_scan).
 template <bool BULLETS>
 __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__ binned, uint32_t capacity,
-                                                       ShapeArrays s, FrameScratch* fs, uint4* __restrict__ hits)
+                                                       ShapeArrays s, FrameScratch* fs, uint4* __restrict__ hits,
+                                                       uint32_t scanBlocks)
 {
     // Bullet candidates: the conservative bound rejects nearly all of them (98 % among 1 M static polygons), and the few
     // survivors would each run their 19-test sweep search alone in a warp.  They are queued per warp instead and searched
@@ -1218,9 +1263,11 @@ __global__ void __launch_bounds__(128) k_narrow_filter(const uint2* __restrict__
     }
     if (BULLETS && queued > 0)
         run_sweeps(queue, queued, s, fs, hits, lane);
+    if (last_block_done(fs, scanBlocks) && threadIdx.x == 0)
+        scan_hits(fs);
 }
 
-__global__ void k_hit_scan(FrameScratch* fs)
+__global__ void k_hit_scan(FrameScratch* fs) // (kept for reference; the pipeline no longer launches it)
 {
     if (threadIdx.x == 0)
     {
@@ -1451,7 +1498,7 @@ __device__ __forceinline__ bool pp_setup(const ShapeArrays& s, uint2 p, bool val
 }
 
 __global__ void __launch_bounds__(128) k_narrow_filter_pp(const uint2* __restrict__ binned, ShapeArrays s,
-                                                          FrameScratch* fs, uint4* __restrict__ hits)
+                                                          FrameScratch* fs, uint4* __restrict__ hits, uint32_t scanBlocks)
 {
     __shared__ OctetShared sh[16];
     const uint32_t off = fs->binOffset[CORE_PP], cnt = fs->binCount[CORE_PP];
@@ -1481,6 +1528,8 @@ __global__ void __launch_bounds__(128) k_narrow_filter_pp(const uint2* __restric
         }
         __syncwarp();
     }
+    if (last_block_done(fs, scanBlocks) && threadIdx.x == 0)
+        scan_hits(fs);
 }
 
 __global__ void __launch_bounds__(128, 8) k_narrow_manifold_pp(const uint4* __restrict__ hits, ShapeArrays s,
