@@ -5,7 +5,7 @@
 //   K3  radix sort                                                         (c2d_sort.cu)
 //   K4  k_karras_build / k_fit                                             (LBVH topology, bottom-up boxes)
 //   K5  k_traverse<SELF> / k_traverse_warp<SELF>                           (candidate pairs; warp-per-query for bullets)
-//   K6  k_bin_* / k_narrow_filter(_pp) / k_hit_scan / k_narrow_manifold(_pp) (binning by code path, boolean tests and
+//   K6  k_bin_count / k_bin_scatter / k_narrow_filter(_pp) / k_narrow_manifold(_pp) (binning by code path, boolean tests and
 //       sweep searches, manifolds; the polygon bin runs 8 lanes per pair, c2d_narrow_pp.cuh)
 // The uniform-grid broadphase is in c2d_grid.cu, rays in c2d_rays.cu, per-entity queries in c2d_query.cu.
 //
