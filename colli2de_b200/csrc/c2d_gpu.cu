@@ -778,6 +778,13 @@ void launch_traverse(c2d_gpu_ctx* ctx, int qBody, int tBody, cudaStream_t st = n
 
 void fill_stats(c2d_gpu_ctx* ctx, c2d_gpu_stats* stats);
 
+inline uint32_t env_u32(const char* name, uint32_t fallback)
+{
+    const char* v = std::getenv(name);
+    const unsigned long n = v ? std::strtoul(v, nullptr, 10) : 0ul;
+    return n >= 1 && n <= 64 ? static_cast<uint32_t>(n) : fallback;
+}
+
 // the records a query returns: this rank's, or the group's when the result mode gathered them (c2d_comm.cu)
 inline const PairOut* result_ptr(const c2d_gpu_ctx* ctx)
 {
@@ -897,23 +904,26 @@ int pipeline_attempt(c2d_gpu_ctx* ctx, bool retry = false)
     if (int rc = fork())
         return rc;
     const bool bullets = !ctx->members[C2D_BULLET].empty();
-    constexpr uint32_t kFilterBlocks = 148 * 16; // per filter kernel; the last of the 2 x kFilterBlocks blocks scans the hit counts
+    // blocks per SM of the four narrowphase kernels (grid-stride loops: any grid is correct); C2D_GRID_* override them
+    static const uint32_t gFilter = 148 * env_u32("C2D_GRID_FILTER", 16), gFilterPP = 148 * env_u32("C2D_GRID_FILTER_PP", 16),
+                          gManifold = 148 * env_u32("C2D_GRID_MANIFOLD", 16), gManifoldPP = 148 * env_u32("C2D_GRID_MANIFOLD_PP", 16);
+    const uint32_t scanBlocks = gFilter + gFilterPP; // the last of them scans the hit counts
     if (bullets)
-        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<true><<<kFilterBlocks, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr, 2 * kFilterBlocks));
+        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<true><<<gFilter, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr, scanBlocks));
     else
-        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<false><<<kFilterBlocks, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr, 2 * kFilterBlocks));
-    C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<kFilterBlocks, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr, 2 * kFilterBlocks));
+        C2D_TIMED_ON(ctx, side, "k_narrow_filter", k_narrow_filter<false><<<gFilter, 128, 0, side>>>(ctx->binned.ptr, cap, ctx->d, ctx->dScratch, ctx->hits.ptr, scanBlocks));
+    C2D_TIMED(ctx, "k_narrow_filter_pp", k_narrow_filter_pp<<<gFilterPP, 128, 0, s>>>(ctx->binned.ptr, ctx->d, ctx->dScratch, ctx->hits.ptr, scanBlocks));
     if (int rc = join())
         return rc;
     if (int rc = fork())
         return rc;
     if (bullets)
-        C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<true><<<148 * 16, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+        C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<true><<<gManifold, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                          static_cast<uint32_t>(ctx->out.capacity)));
     else
-        C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<false><<<148 * 16, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+        C2D_TIMED_ON(ctx, side, "k_narrow_manifold", k_narrow_manifold<false><<<gManifold, 128, 0, side>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                          static_cast<uint32_t>(ctx->out.capacity)));
-    C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<148 * 16, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
+    C2D_TIMED(ctx, "k_narrow_manifold_pp", k_narrow_manifold_pp<<<gManifoldPP, 128, 0, s>>>(ctx->hits.ptr, ctx->d, ctx->dScratch, ctx->out.ptr,
                                      static_cast<uint32_t>(ctx->out.capacity)));
     if (int rc = join())
         return rc;
