@@ -140,8 +140,9 @@ int c2d_gpu_set_small_scene_limit(c2d_gpu_ctx* ctx, uint32_t shapes);
  * One context per GPU (one process per GPU under torchrun, or several contexts in one process).  Shape state is
  * REPLICATED: every rank of a group replays every mutation (or receives the other ranks' translations, below), so
  * ownership needs no communication - every rank derives the same Morton keys and the same slab boundaries from the same
- * boxes.  What is sharded is the per-frame work of Registry::getCollidingPairs (Registry.hpp:464-549): each rank sorts,
- * builds, refits and traverses only ITS slab and returns its share of the pairs; the union over the ranks is the
+ * boxes.  What is sharded is the per-frame work of Registry::getCollidingPairs (Registry.hpp:464-549): each rank links,
+ * refits and traverses only ITS slab and returns its share of the pairs (the Morton sort that defines the slabs is
+ * replicated, once per rebuild period); the union over the ranks is the
  * reference's pair set, each pair exactly once (owner rule).  (The grid broadphase splits its sorted cell entries instead.)
  *
  * c2d_gpu_set_shard: this context is `rank` of `world`.  Default 0 of 1.
@@ -193,11 +194,11 @@ typedef struct c2d_gpu_comm_stats
     uint64_t exchange_bytes;  /* translation records received from all ranks */
     uint64_t gather_bytes;    /* pair records received */
     uint64_t local_pairs;     /* pairs this rank computed */
-    uint64_t slab_owned;      /* Dynamic leaves this rank owns / leaves in its tree incl. the halo */
-    uint64_t slab_leaves;
+    uint64_t slab_owned;      /* Dynamic leaves this rank owns */
+    uint64_t slab_leaves;     /* ... plus the halo shapes that queried them this frame */
     float ms_exchange;
     float ms_gather;
-    float ms_slab;            /* keys + histogram + splitters + selection of the slab (before the sort) */
+    float ms_slab;            /* the slab step of the frame: (rebalance: keys + sort + links) + refit + halo selection */
 } c2d_gpu_comm_stats;
 int c2d_gpu_comm_get_stats(c2d_gpu_ctx* ctx, c2d_gpu_comm_stats* out);
 
